@@ -1,0 +1,136 @@
+/* repurpose_b200 — C ABI of the B200 (sm_100a) implementation of the Repurpose inference hot path.
+ *
+ * The reference (YosubShin/Repurpose) is 100 % Python and has no FFI of its own; its "operator
+ * interface" for this path is three Python callables plus the state-dict schema.  Each entry point
+ * below names the reference call it replaces (paths relative to the reference repo):
+ *
+ *   rp_forward        <- MMCTransformer.forward            models/MMCTransformer.py:109-151
+ *   rp_decode_nms     <- inference_single_video + the per-video loop of inference_
+ *                                                          models/MMCTransformer.py:181-229, 248-273
+ *   rp_soft_nms       <- soft_nms_intervals_cpu            models/softnms.py:3-38
+ *   rp_fmha (+ rp_gemm_bf16 / rp_cast_bf16)
+ *                     <- MultiHeadAttention.forward        models/transformer.py:52-81
+ *   rp_load_weight    <- model.load_state_dict(ckpt['model'])  inference.py:33-34 (same key names)
+ *
+ * Conventions: every pointer is a DEVICE pointer unless stated otherwise; sizes are explicit; the
+ * last argument is a cudaStream_t passed as void*; the return value is 0 on success, non-zero on
+ * failure (rp_last_error() returns a thread-local message).  Nothing throws or aborts across the
+ * ABI, nothing is allocated behind the caller's back except inside rp_create (weights) — activations
+ * live in a caller-provided workspace.  There is no CPU fallback: without an sm_100 device the
+ * compute entry points return RP_ERR_NO_DEVICE / a CUDA error.
+ */
+#ifndef REPURPOSE_B200_H_
+#define REPURPOSE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RP_ABI_VERSION 1
+
+enum {
+  RP_OK = 0,
+  RP_ERR_INVALID = 1,
+  RP_ERR_CUDA = 2,
+  RP_ERR_NO_DEVICE = 3,
+  RP_ERR_WORKSPACE = 4
+};
+
+typedef struct rp_handle rp_handle;
+
+/* models/MMCTransformer.py:26 constructor arguments that shape the graph
+ * (text_num_layers / cross_num_layers are accepted and ignored by the reference). */
+typedef struct rp_model_cfg {
+  int32_t vis_dim, aud_dim, text_dim; /* configs/Repurpose.yaml:22-32 : 512 / 2048 / 384 */
+  int32_t d_model;                    /* 512 (the kernels are specialised for 512)          */
+  int32_t num_layers;                 /* self_num_layers, 16                                 */
+  int32_t num_heads;                  /* 8  (head dim must be 64)                            */
+  int32_t d_ff;                       /* 2048                                                */
+  int32_t head_hidden;                /* 256 (models/MMCTransformer.py:60)                   */
+  int32_t max_len;                    /* rows of positional_encoding.pe the caller will load */
+} rp_model_cfg;
+
+/* configs/Repurpose.yaml:52-61 test_cfg (max_seg_per_min is applied by the host: it only feeds
+ * max_seg[b] = ceil((duration // 60) * max_seg_per_min), models/MMCTransformer.py:255-257). */
+typedef struct rp_decode_cfg {
+  int32_t pre_nms_topk;
+  float pre_nms_thresh;
+  float duration_thresh;
+  float duration_thresh_max;
+  float nms_sigma;
+  float min_score;
+} rp_decode_cfg;
+
+int32_t rp_abi_version(void);
+const char* rp_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py: gpu_launches) */
+int64_t rp_launch_count(void);
+
+/* ---- model handle ------------------------------------------------------------------------- */
+int32_t rp_create(const rp_model_cfg* cfg, rp_handle** out);
+void rp_destroy(rp_handle* h);
+/* name = reference state-dict key (e.g. "multimodal_encoder.layers.3.self_attn.in_proj_weight");
+ * src = fp32 device tensor with the reference shape, numel elements.  Matrices are repacked to bf16
+ * (the query rows of in_proj are pre-scaled by log2(e)/sqrt(64)); vectors stay fp32. */
+int32_t rp_load_weight(rp_handle* h, const char* name, const float* src, int64_t numel, void* stream);
+/* 0 when every tensor of the schema has been loaded, else RP_ERR_INVALID (+ message naming one) */
+int32_t rp_weights_complete(const rp_handle* h);
+int64_t rp_workspace_bytes(const rp_handle* h, int32_t B, int32_t T);
+/* vis [B,T,vis_dim] aud [B,T,aud_dim] txt [B,T,text_dim] fp32; lens [B] int32 valid steps
+ * (masks[b,0,t] = t < lens[b]); outputs logits [B,T] (== [B,T,1]), offsets [B,T,2], feats [B,T,512]. */
+int32_t rp_forward(rp_handle* h, const float* vis, const float* aud, const float* txt,
+                   const int32_t* lens, int32_t B, int32_t T, float* out_logits, float* out_offsets,
+                   float* out_feats, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- decode + Soft-NMS ------------------------------------------------------------------------ */
+/* logits [B,T], offsets [B,T,2], lens [B], max_seg [B] ->
+ * segs [B,Kcap,2] f32, scores [B,Kcap] f32 (probability of the kept candidate), dscores [B,Kcap]
+ * f32 (its decayed Soft-NMS score), labels [B,Kcap] i32 (centre step), counts [B] i32,
+ * ncand [B] i32 (candidates that entered Soft-NMS).  Optional (all NULL or all set) pre-NMS
+ * candidate list = the return value of inference_single_video: cand_segs [B,C,2], cand_scores [B,C],
+ * cand_labels [B,C], C = min(pre_nms_topk, T).  Requires T <= 8192, topk <= 4096, Kcap <= 64. */
+int32_t rp_decode_nms(const float* logits, const float* offsets, const int32_t* lens,
+                      const int32_t* max_seg, int32_t B, int32_t T, const rp_decode_cfg* cfg,
+                      int32_t Kcap, float* segs, float* scores, float* dscores, int32_t* labels,
+                      int32_t* counts, int32_t* ncand, float* cand_segs, float* cand_scores,
+                      int32_t* cand_labels, void* stream);
+/* scores [B,Nmax] (descending, as produced by decode), segs [B,Nmax,2], n [B], max_seg [B] ->
+ * keep [B,Kcap] i32 original indices in selection order, kscores [B,Kcap] decayed scores,
+ * counts [B].  Nmax <= 8192. */
+int32_t rp_soft_nms(const float* scores, const float* segs, const int32_t* n, const int32_t* max_seg,
+                    int32_t B, int32_t Nmax, float sigma, float thresh, int32_t Kcap, int32_t* keep,
+                    float* kscores, int32_t* counts, void* stream);
+
+/* ---- building blocks (also what the unit tests drive) ---------------------------------------- */
+/* D[M,N] = A[M,K] * W[N,K]^T + bias (+ReLU | +residual); A, W bf16 row-major with pitches lda/ldw
+ * (elements); epilogue: 0 bf16 out, 1 bf16 out + ReLU, 2 f32 out, 3 f32 out + residual (may alias D).
+ * N % 256 == 0, K % 64 == 0. */
+int32_t rp_gemm_bf16(int32_t epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
+                     int64_t ldd, const float* bias, const float* resid, int64_t ldr, int32_t M,
+                     int32_t N, int32_t K, void* stream);
+/* softmax(q k^T + mask) v per head of 64; q must be pre-scaled by log2(e)/8.  bf16 in/out; ld* row
+ * pitch and bs* batch pitch in elements.  mask_mode 0: keys >= kv_lens[b] are -inf (kv_lens may be
+ * NULL); mask_mode 1: uint8 mask, 0 => masked_fill(-1e9), mask_q_stride 0 broadcasts over queries. */
+int32_t rp_fmha(const void* q, const void* k, const void* v, void* o, int64_t ldq, int64_t ldk,
+                int64_t ldv, int64_t ldo, int64_t bsq, int64_t bsk, int64_t bsv, int64_t bso,
+                int32_t B, int32_t H, int32_t Tq, int32_t Tk, const int32_t* kv_lens, int32_t mask_mode,
+                const uint8_t* mask, int64_t mask_b_stride, int64_t mask_q_stride, void* stream);
+int32_t rp_concat_cast(const float* vis, const float* aud, const float* txt, int32_t Cv, int32_t Ca,
+                       int32_t Ct, void* out_bf16, int64_t M, void* stream);
+int32_t rp_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+/* LayerNorm over rows of 512, eps 1e-5.  mode 0: y=bf16(LN(x)); 1: h=LN(x)+pe[row%T] (f32 out),
+ * y=bf16(LN1(h)); 2: f=relu(LN(x)) (f32 out), y=bf16(LN1(f)), y2=bf16(LN2(f)); 3: f32 out = LN(x). */
+int32_t rp_layernorm512(int32_t mode, const float* x, int64_t M, int32_t T, const float* g0,
+                        const float* b0, const float* g1, const float* b1, const float* g2,
+                        const float* b2, const float* pe, float* out_f32, void* y_bf16, void* y2_bf16,
+                        void* stream);
+int32_t rp_head_out(const void* a_cls_bf16, const void* a_reg_bf16, const float* w_cls,
+                    const float* b_cls, const float* w_reg, const float* b_reg, float* logits,
+                    float* offsets, int64_t M, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REPURPOSE_B200_H_ */

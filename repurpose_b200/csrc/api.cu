@@ -1,0 +1,441 @@
+// C-ABI (include/repurpose_b200.h): model handle, reference-state-dict weight repacking, and the
+// forward-pass launch sequence that restates MMCTransformer.forward
+// (reference models/MMCTransformer.py:109-151; arithmetic in SURVEY.md Appendix A).
+#include <cuda_bf16.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/repurpose_b200.h"
+#include "host_util.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+using namespace rp;
+
+namespace {
+
+constexpr float kQScale = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64), folded into Wq, bq
+
+enum WeightKind { W_MAT_BF16, W_VEC_F32, W_QKV_MAT, W_QKV_VEC, W_PE };
+
+struct WeightSlot {
+  WeightKind kind;
+  int64_t numel;       // expected element count (W_PE: elements per position row * max_len)
+  void* dev = nullptr; // bf16 for matrices, f32 otherwise
+  bool loaded = false;
+};
+
+struct LayerW {
+  __nv_bfloat16 *w_qkv, *w_out, *w_ff1, *w_ff2;
+  float *b_qkv, *b_out, *b_ff1, *b_ff2;
+  float *n1_g, *n1_b, *n2_g, *n2_b;
+};
+
+}  // namespace
+
+struct rp_handle {
+  rp_model_cfg cfg;
+  std::map<std::string, WeightSlot> slots;
+  std::vector<LayerW> layers;
+  // non-layer weights
+  __nv_bfloat16 *w_in, *w_fm, *w_c1, *w_c4, *w_r1, *w_r4;
+  float *b_in, *in_g, *in_b, *enc_g, *enc_b, *b_fm, *fm_g, *fm_b;
+  float *c0_g, *c0_b, *b_c1, *b_c4, *w_c7, *b_c7;
+  float *r0_g, *r0_b, *b_r1, *b_r4, *w_r7, *b_r7;
+  float* pe;
+  int64_t pe_rows_loaded = 0;
+};
+
+namespace {
+
+__global__ void repack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                   int64_t n, int64_t n_scaled, float scale) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const float v = src[i];
+    dst[i] = __float2bfloat16_rn(i < n_scaled ? v * scale : v);
+  }
+}
+__global__ void repack_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n,
+                                  int64_t n_scaled, float scale) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const float v = src[i];
+    dst[i] = i < n_scaled ? v * scale : v;
+  }
+}
+
+template <typename T>
+int add_slot(rp_handle* h, const std::string& name, WeightKind kind, int64_t numel, T** field) {
+  WeightSlot s;
+  s.kind = kind;
+  s.numel = numel;
+  const size_t bytes = size_t(numel) * ((kind == W_MAT_BF16 || kind == W_QKV_MAT) ? 2 : 4);
+  RP_CUDA_CHECK(cudaMalloc(&s.dev, bytes));
+  *field = reinterpret_cast<T*>(s.dev);
+  h->slots[name] = s;
+  return RP_OK;
+}
+
+#define ADD(name, kind, numel, field)                                         \
+  do {                                                                        \
+    int _rc = add_slot(h, (name), (kind), (numel), &(field));                 \
+    if (_rc) return _rc;                                                      \
+  } while (0)
+
+int build_slots(rp_handle* h) {
+  const rp_model_cfg& c = h->cfg;
+  const int64_t D = c.d_model, F = c.d_ff, Hh = c.head_hidden;
+  const int64_t Cin = int64_t(c.vis_dim) + c.aud_dim + c.text_dim;
+  ADD("input_projection.weight", W_MAT_BF16, D * Cin, h->w_in);
+  ADD("input_projection.bias", W_VEC_F32, D, h->b_in);
+  ADD("input_norm.weight", W_VEC_F32, D, h->in_g);
+  ADD("input_norm.bias", W_VEC_F32, D, h->in_b);
+  ADD("positional_encoding.pe", W_PE, int64_t(c.max_len) * D, h->pe);
+  h->layers.resize(c.num_layers);
+  for (int l = 0; l < c.num_layers; ++l) {
+    const std::string p = "multimodal_encoder.layers." + std::to_string(l) + ".";
+    LayerW& L = h->layers[l];
+    ADD(p + "self_attn.in_proj_weight", W_QKV_MAT, 3 * D * D, L.w_qkv);
+    ADD(p + "self_attn.in_proj_bias", W_QKV_VEC, 3 * D, L.b_qkv);
+    ADD(p + "self_attn.out_proj.weight", W_MAT_BF16, D * D, L.w_out);
+    ADD(p + "self_attn.out_proj.bias", W_VEC_F32, D, L.b_out);
+    ADD(p + "linear1.weight", W_MAT_BF16, F * D, L.w_ff1);
+    ADD(p + "linear1.bias", W_VEC_F32, F, L.b_ff1);
+    ADD(p + "linear2.weight", W_MAT_BF16, D * F, L.w_ff2);
+    ADD(p + "linear2.bias", W_VEC_F32, D, L.b_ff2);
+    ADD(p + "norm1.weight", W_VEC_F32, D, L.n1_g);
+    ADD(p + "norm1.bias", W_VEC_F32, D, L.n1_b);
+    ADD(p + "norm2.weight", W_VEC_F32, D, L.n2_g);
+    ADD(p + "norm2.bias", W_VEC_F32, D, L.n2_b);
+  }
+  ADD("encoder_norm.weight", W_VEC_F32, D, h->enc_g);
+  ADD("encoder_norm.bias", W_VEC_F32, D, h->enc_b);
+  ADD("feature_map.0.weight", W_MAT_BF16, D * D, h->w_fm);
+  ADD("feature_map.0.bias", W_VEC_F32, D, h->b_fm);
+  ADD("feature_map.1.weight", W_VEC_F32, D, h->fm_g);
+  ADD("feature_map.1.bias", W_VEC_F32, D, h->fm_b);
+  ADD("cls_head.0.weight", W_VEC_F32, D, h->c0_g);
+  ADD("cls_head.0.bias", W_VEC_F32, D, h->c0_b);
+  ADD("cls_head.1.weight", W_MAT_BF16, Hh * D, h->w_c1);
+  ADD("cls_head.1.bias", W_VEC_F32, Hh, h->b_c1);
+  ADD("cls_head.4.weight", W_MAT_BF16, Hh * Hh, h->w_c4);
+  ADD("cls_head.4.bias", W_VEC_F32, Hh, h->b_c4);
+  ADD("cls_head.7.weight", W_VEC_F32, Hh, h->w_c7);
+  ADD("cls_head.7.bias", W_VEC_F32, 1, h->b_c7);
+  ADD("reg_head.0.weight", W_VEC_F32, D, h->r0_g);
+  ADD("reg_head.0.bias", W_VEC_F32, D, h->r0_b);
+  ADD("reg_head.1.weight", W_MAT_BF16, Hh * D, h->w_r1);
+  ADD("reg_head.1.bias", W_VEC_F32, Hh, h->b_r1);
+  ADD("reg_head.4.weight", W_MAT_BF16, Hh * Hh, h->w_r4);
+  ADD("reg_head.4.bias", W_VEC_F32, Hh, h->b_r4);
+  ADD("reg_head.7.weight", W_VEC_F32, 2 * Hh, h->w_r7);
+  ADD("reg_head.7.bias", W_VEC_F32, 2, h->b_r7);
+  return RP_OK;
+}
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  float* h;             // [M,512] fp32 residual stream
+  __nv_bfloat16* u;     // [M,512]
+  __nv_bfloat16* attn;  // [M,512]
+  __nv_bfloat16* qkv;   // [M,1536]   } contiguous: also holds xcat [M,Cin] during the input stage
+  __nv_bfloat16* ffn;   // [M,d_ff]   }
+  int64_t bytes;
+};
+
+Workspace carve(const rp_model_cfg& c, int64_t M, void* base) {
+  Workspace w;
+  const int64_t D = c.d_model;
+  const int64_t Cin = int64_t(c.vis_dim) + c.aud_dim + c.text_dim;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    const int64_t o = off;
+    off += align_up(bytes, 1024);
+    return o;
+  };
+  const int64_t o_h = take(M * D * 4);
+  const int64_t o_u = take(M * D * 2);
+  const int64_t o_a = take(M * D * 2);
+  int64_t wide = M * (3 * D + c.d_ff) * 2;
+  if (wide < M * Cin * 2) wide = M * Cin * 2;
+  const int64_t o_q = take(wide);
+  uint8_t* b = reinterpret_cast<uint8_t*>(base);
+  w.h = reinterpret_cast<float*>(b + o_h);
+  w.u = reinterpret_cast<__nv_bfloat16*>(b + o_u);
+  w.attn = reinterpret_cast<__nv_bfloat16*>(b + o_a);
+  w.qkv = reinterpret_cast<__nv_bfloat16*>(b + o_q);
+  w.ffn = w.qkv + M * 3 * D;
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t rp_abi_version(void) { return RP_ABI_VERSION; }
+const char* rp_last_error(void) { return rp::last_error(); }
+int64_t rp_launch_count(void) { return rp::launch_count(); }
+
+int32_t rp_create(const rp_model_cfg* cfg, rp_handle** out) {
+  RP_CHECK(cfg != nullptr && out != nullptr, "rp_create: null argument");
+  RP_CHECK(cfg->d_model == 512, "rp_create: d_model=%d unsupported (kernels are specialised for 512)",
+           cfg->d_model);
+  RP_CHECK(cfg->num_heads > 0 && cfg->d_model / cfg->num_heads == 64 &&
+               cfg->d_model % cfg->num_heads == 0,
+           "rp_create: head dim must be 64 (d_model=%d, heads=%d)", cfg->d_model, cfg->num_heads);
+  RP_CHECK(cfg->head_hidden == 256, "rp_create: head_hidden must be 256");
+  RP_CHECK(cfg->d_ff > 0 && cfg->d_ff % 256 == 0, "rp_create: d_ff must be a multiple of 256");
+  RP_CHECK(cfg->vis_dim % 8 == 0 && cfg->aud_dim % 8 == 0 && cfg->text_dim % 8 == 0 &&
+               (cfg->vis_dim + cfg->aud_dim + cfg->text_dim) % 64 == 0,
+           "rp_create: modality dims must be multiples of 8 and sum to a multiple of 64");
+  RP_CHECK(cfg->num_layers >= 1 && cfg->max_len >= 1, "rp_create: bad num_layers / max_len");
+  if (num_sms() <= 0) return RP_ERR_NO_DEVICE;
+  rp_handle* h = new rp_handle();
+  h->cfg = *cfg;
+  int rc = build_slots(h);
+  if (rc) {
+    rp_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return RP_OK;
+}
+
+void rp_destroy(rp_handle* h) {
+  if (h == nullptr) return;
+  for (auto& kv : h->slots)
+    if (kv.second.dev) cudaFree(kv.second.dev);
+  delete h;
+}
+
+int32_t rp_load_weight(rp_handle* h, const char* name, const float* src, int64_t numel, void* stream) {
+  RP_CHECK(h != nullptr && name != nullptr && src != nullptr, "rp_load_weight: null argument");
+  auto it = h->slots.find(name);
+  RP_CHECK(it != h->slots.end(), "rp_load_weight: unexpected key '%s'", name);
+  WeightSlot& s = it->second;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t D = h->cfg.d_model;
+  if (s.kind == W_PE) {
+    RP_CHECK(numel % D == 0 && numel >= D && numel <= s.numel,
+             "rp_load_weight: positional_encoding.pe has %lld elements, handle holds %lld",
+             (long long)numel, (long long)s.numel);
+    h->pe_rows_loaded = numel / D;
+  } else {
+    RP_CHECK(numel == s.numel, "rp_load_weight: '%s' has %lld elements, expected %lld", name,
+             (long long)numel, (long long)s.numel);
+  }
+  const int threads = 256;
+  int64_t blocks64 = (numel + threads - 1) / threads;
+  const int blocks = int(blocks64 > 4096 ? 4096 : blocks64);
+  switch (s.kind) {
+    case W_MAT_BF16:
+      repack_bf16_kernel<<<blocks, threads, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(s.dev),
+                                                     numel, 0, 1.0f);
+      break;
+    case W_QKV_MAT:  // rows [0, D) are the query projection
+      repack_bf16_kernel<<<blocks, threads, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(s.dev),
+                                                     numel, D * D, kQScale);
+      break;
+    case W_QKV_VEC:
+      repack_f32_kernel<<<blocks, threads, 0, st>>>(src, reinterpret_cast<float*>(s.dev), numel, D,
+                                                    kQScale);
+      break;
+    case W_VEC_F32:
+    case W_PE:
+      repack_f32_kernel<<<blocks, threads, 0, st>>>(src, reinterpret_cast<float*>(s.dev), numel, 0,
+                                                    1.0f);
+      break;
+  }
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  s.loaded = true;
+  return RP_OK;
+}
+
+int32_t rp_weights_complete(const rp_handle* h) {
+  RP_CHECK(h != nullptr, "rp_weights_complete: null handle");
+  for (const auto& kv : h->slots)
+    RP_CHECK(kv.second.loaded, "missing weight '%s'", kv.first.c_str());
+  return RP_OK;
+}
+
+int64_t rp_workspace_bytes(const rp_handle* h, int32_t B, int32_t T) {
+  if (h == nullptr || B <= 0 || T <= 0) return -1;
+  return carve(h->cfg, int64_t(B) * T, nullptr).bytes;
+}
+
+int32_t rp_forward(rp_handle* h, const float* vis, const float* aud, const float* txt,
+                   const int32_t* lens, int32_t B, int32_t T, float* out_logits, float* out_offsets,
+                   float* out_feats, void* workspace, int64_t workspace_bytes, void* stream) {
+  RP_CHECK(h && vis && aud && txt && lens && out_logits && out_offsets && out_feats && workspace,
+           "rp_forward: null argument");
+  RP_CHECK(B > 0 && T > 0, "rp_forward: empty batch");
+  int rc = rp_weights_complete(h);
+  if (rc) return rc;
+  RP_CHECK(T <= h->pe_rows_loaded,
+           "rp_forward: T=%d exceeds the %lld positional-encoding rows loaded", T,
+           (long long)h->pe_rows_loaded);
+  const rp_model_cfg& c = h->cfg;
+  const int64_t M64 = int64_t(B) * T;
+  RP_CHECK(M64 < (int64_t(1) << 31), "rp_forward: B*T too large");
+  const int M = int(M64);
+  Workspace w = carve(c, M, workspace);
+  if (w.bytes > workspace_bytes) {
+    set_last_error("rp_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes,
+                   (long long)w.bytes);
+    return RP_ERR_WORKSPACE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int D = c.d_model, F = c.d_ff, Hh = c.head_hidden, H = c.num_heads;
+  const int Cin = c.vis_dim + c.aud_dim + c.text_dim;
+  const float eps = 1e-5f;
+#define RUN(expr)            \
+  do {                       \
+    rc = (expr);             \
+    if (rc) return rc;       \
+  } while (0)
+
+  // (1) concat + cast, input projection (fp32 out), input_norm + PE -> h, layers[0].norm1 -> u
+  __nv_bfloat16* xcat = w.qkv;
+  RUN(launch_concat_cast(vis, aud, txt, c.vis_dim, c.aud_dim, c.text_dim, xcat, M, st));
+  RUN(launch_gemm(EPI_BIAS_F32, xcat, Cin, h->w_in, Cin, w.h, D, h->b_in, nullptr, 0, M, D, Cin, st));
+  {
+    LnArgs a{};
+    a.x = w.h; a.M = M; a.T = T; a.eps = eps;
+    a.g0 = h->in_g; a.b0 = h->in_b; a.pe = h->pe;
+    a.g1 = h->layers[0].n1_g; a.b1 = h->layers[0].n1_b;
+    a.out_f32 = w.h; a.y_bf16 = w.u;
+    RUN(launch_layernorm512(1, a, st));
+  }
+  // (2) encoder layers (pre-LN): h += MHA(LN1(h)); h += FFN(LN2(h))
+  for (int l = 0; l < c.num_layers; ++l) {
+    const LayerW& L = h->layers[l];
+    RUN(launch_gemm(EPI_BIAS_BF16, w.u, D, L.w_qkv, D, w.qkv, 3 * D, L.b_qkv, nullptr, 0, M, 3 * D, D, st));
+    FmhaArgs fa{};
+    fa.q = w.qkv; fa.k = w.qkv + D; fa.v = w.qkv + 2 * D; fa.o = w.attn;
+    fa.ldq = fa.ldk = fa.ldv = 3 * D; fa.ldo = D;
+    fa.bsq = fa.bsk = fa.bsv = int64_t(T) * 3 * D; fa.bso = int64_t(T) * D;
+    fa.B = B; fa.H = H; fa.Tq = T; fa.Tk = T; fa.kv_lens = lens; fa.mask_mode = 0;
+    RUN(launch_fmha(fa, st));
+    RUN(launch_gemm(EPI_BIAS_RESID_F32, w.attn, D, L.w_out, D, w.h, D, L.b_out, w.h, D, M, D, D, st));
+    {
+      LnArgs a{};
+      a.x = w.h; a.M = M; a.T = T; a.eps = eps; a.g0 = L.n2_g; a.b0 = L.n2_b; a.y_bf16 = w.u;
+      RUN(launch_layernorm512(0, a, st));
+    }
+    RUN(launch_gemm(EPI_BIAS_RELU_BF16, w.u, D, L.w_ff1, D, w.ffn, F, L.b_ff1, nullptr, 0, M, F, D, st));
+    RUN(launch_gemm(EPI_BIAS_RESID_F32, w.ffn, F, L.w_ff2, F, w.h, D, L.b_ff2, w.h, D, M, D, F, st));
+    {
+      LnArgs a{};
+      a.x = w.h; a.M = M; a.T = T; a.eps = eps; a.y_bf16 = w.u;
+      if (l + 1 < c.num_layers) { a.g0 = h->layers[l + 1].n1_g; a.b0 = h->layers[l + 1].n1_b; }
+      else { a.g0 = h->enc_g; a.b0 = h->enc_b; }  // encoder_norm feeds feature_map
+      RUN(launch_layernorm512(0, a, st));
+    }
+  }
+  // (3) feature_map: Linear -> LN -> ReLU = feats (returned); head LayerNorms
+  RUN(launch_gemm(EPI_BIAS_F32, w.u, D, h->w_fm, D, w.h, D, h->b_fm, nullptr, 0, M, D, D, st));
+  {
+    LnArgs a{};
+    a.x = w.h; a.M = M; a.T = T; a.eps = eps;
+    a.g0 = h->fm_g; a.b0 = h->fm_b; a.g1 = h->c0_g; a.b1 = h->c0_b; a.g2 = h->r0_g; a.b2 = h->r0_b;
+    a.out_f32 = out_feats; a.y_bf16 = w.u; a.y2_bf16 = w.attn;
+    RUN(launch_layernorm512(2, a, st));
+  }
+  // (4) heads: 512->256 ReLU -> 256->256 ReLU -> {1, 2 (+ReLU)}
+  __nv_bfloat16* a1c = w.qkv;
+  __nv_bfloat16* a2c = a1c + int64_t(M) * Hh;
+  __nv_bfloat16* a1r = a2c + int64_t(M) * Hh;
+  __nv_bfloat16* a2r = a1r + int64_t(M) * Hh;
+  RUN(launch_gemm(EPI_BIAS_RELU_BF16, w.u, D, h->w_c1, D, a1c, Hh, h->b_c1, nullptr, 0, M, Hh, D, st));
+  RUN(launch_gemm(EPI_BIAS_RELU_BF16, a1c, Hh, h->w_c4, Hh, a2c, Hh, h->b_c4, nullptr, 0, M, Hh, Hh, st));
+  RUN(launch_gemm(EPI_BIAS_RELU_BF16, w.attn, D, h->w_r1, D, a1r, Hh, h->b_r1, nullptr, 0, M, Hh, D, st));
+  RUN(launch_gemm(EPI_BIAS_RELU_BF16, a1r, Hh, h->w_r4, Hh, a2r, Hh, h->b_r4, nullptr, 0, M, Hh, Hh, st));
+  RUN(launch_head_out(a2c, a2r, h->w_c7, h->b_c7, h->w_r7, h->b_r7, out_logits, out_offsets, M, st));
+#undef RUN
+  return RP_OK;
+}
+
+int32_t rp_decode_nms(const float* logits, const float* offsets, const int32_t* lens,
+                      const int32_t* max_seg, int32_t B, int32_t T, const rp_decode_cfg* cfg,
+                      int32_t Kcap, float* segs, float* scores, float* dscores, int32_t* labels,
+                      int32_t* counts, int32_t* ncand, float* cand_segs, float* cand_scores,
+                      int32_t* cand_labels, void* stream) {
+  RP_CHECK(logits && offsets && lens && max_seg && cfg && segs && scores && dscores && labels &&
+               counts && ncand,
+           "rp_decode_nms: null argument");
+  DecodeCfg d{cfg->pre_nms_topk, cfg->pre_nms_thresh, cfg->duration_thresh, cfg->duration_thresh_max,
+              cfg->nms_sigma, cfg->min_score};
+  return launch_decode_nms(logits, offsets, lens, max_seg, B, T, d, Kcap, segs, scores, dscores,
+                           labels, counts, ncand, cand_segs, cand_scores, cand_labels,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_soft_nms(const float* scores, const float* segs, const int32_t* n, const int32_t* max_seg,
+                    int32_t B, int32_t Nmax, float sigma, float thresh, int32_t Kcap, int32_t* keep,
+                    float* kscores, int32_t* counts, void* stream) {
+  RP_CHECK(scores && segs && n && max_seg && keep && kscores && counts, "rp_soft_nms: null argument");
+  return launch_soft_nms(scores, segs, n, max_seg, B, Nmax, sigma, thresh, Kcap, keep, kscores,
+                         counts, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_gemm_bf16(int32_t epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
+                     int64_t ldd, const float* bias, const float* resid, int64_t ldr, int32_t M,
+                     int32_t N, int32_t K, void* stream) {
+  RP_CHECK(A && W && D, "rp_gemm_bf16: null argument");
+  return launch_gemm(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_fmha(const void* q, const void* k, const void* v, void* o, int64_t ldq, int64_t ldk,
+                int64_t ldv, int64_t ldo, int64_t bsq, int64_t bsk, int64_t bsv, int64_t bso,
+                int32_t B, int32_t H, int32_t Tq, int32_t Tk, const int32_t* kv_lens, int32_t mask_mode,
+                const uint8_t* mask, int64_t mask_b_stride, int64_t mask_q_stride, void* stream) {
+  RP_CHECK(q && k && v && o, "rp_fmha: null argument");
+  FmhaArgs a{};
+  a.q = q; a.k = k; a.v = v; a.o = o;
+  a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
+  a.bsq = bsq; a.bsk = bsk; a.bsv = bsv; a.bso = bso;
+  a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.kv_lens = kv_lens; a.mask_mode = mask_mode;
+  a.mask = mask; a.mask_b_stride = mask_b_stride; a.mask_q_stride = mask_q_stride;
+  return launch_fmha(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_concat_cast(const float* vis, const float* aud, const float* txt, int32_t Cv, int32_t Ca,
+                       int32_t Ct, void* out_bf16, int64_t M, void* stream) {
+  RP_CHECK(vis && aud && txt && out_bf16, "rp_concat_cast: null argument");
+  return launch_concat_cast(vis, aud, txt, Cv, Ca, Ct, out_bf16, M,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream) {
+  RP_CHECK(in && out_bf16, "rp_cast_bf16: null argument");
+  return launch_cast_bf16(in, out_bf16, n, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_layernorm512(int32_t mode, const float* x, int64_t M, int32_t T, const float* g0,
+                        const float* b0, const float* g1, const float* b1, const float* g2,
+                        const float* b2, const float* pe, float* out_f32, void* y_bf16, void* y2_bf16,
+                        void* stream) {
+  RP_CHECK(x && g0 && b0, "rp_layernorm512: null argument");
+  LnArgs a{};
+  a.x = x; a.M = M; a.T = T; a.g0 = g0; a.b0 = b0; a.g1 = g1; a.b1 = b1; a.g2 = g2; a.b2 = b2;
+  a.pe = pe; a.out_f32 = out_f32; a.y_bf16 = y_bf16; a.y2_bf16 = y2_bf16; a.eps = 1e-5f;
+  return launch_layernorm512(mode, a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_head_out(const void* a_cls_bf16, const void* a_reg_bf16, const float* w_cls,
+                    const float* b_cls, const float* w_reg, const float* b_reg, float* logits,
+                    float* offsets, int64_t M, void* stream) {
+  RP_CHECK(a_cls_bf16 && a_reg_bf16 && w_cls && b_cls && w_reg && b_reg && logits && offsets,
+           "rp_head_out: null argument");
+  return launch_head_out(a_cls_bf16, a_reg_bf16, w_cls, b_cls, w_reg, b_reg, logits, offsets, M,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,305 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T (+ epilogue).
+//
+//   warp 0      : TMA producer   (A 128x64 and W 256x64 bf16 tiles, SWIZZLE_128B, 4-stage ring)
+//   warp 1      : tcgen05.mma issuer (one thread; UMMA 128x256x16, fp32 accumulators in TMEM,
+//                 two 256-column accumulator buffers so the epilogue of tile i overlaps the
+//                 main loop of tile i+1); also owns TMEM alloc/dealloc
+//   warps 2..5  : epilogue: tcgen05.ld -> bias / ReLU / residual -> swizzled smem slab -> TMA store
+//
+// This kernel implements the Linear layers of the reference hot path
+// (models/MMCTransformer.py:121 input_projection, :135-138 in_proj/out_proj/linear1/linear2 inside
+// nn.TransformerEncoderLayer, :144 feature_map[0], :147-149 head Linear layers).
+#include "ptx.cuh"
+#include "host_util.h"
+#include "kernels.h"
+
+namespace rp {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;                // 16 KB
+constexpr int B_BYTES = BN * BK * 2;                // 32 KB
+constexpr int SLAB_BYTES = 32 * 128;                // 32 rows x 128 B, one TMA-store box
+constexpr int SMEM_A_OFF = 0;
+constexpr int SMEM_B_OFF = STAGES * A_BYTES;        // 65536
+constexpr int SMEM_D_OFF = SMEM_B_OFF + STAGES * B_BYTES;  // 196608
+constexpr int SMEM_BAR_OFF = SMEM_D_OFF + 4 * 2 * SLAB_BYTES;  // 229376
+constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 128 + 1024;  // barriers + alignment slack
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+struct GemmArgs {
+  int M, N, K;
+  const float* bias;
+  const float* resid;
+  int64_t ldr;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmD, const GemmArgs g) {
+  constexpr bool OUT_F32 = (EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_RESID_F32);
+  constexpr int CPC = OUT_F32 ? 32 : 64;  // output columns per 128-byte slab row
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const uint32_t bar_base = base + SMEM_BAR_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
+  auto tfull_bar = [&](int b) { return bar_base + 64u + 8u * b; };
+  auto tempty_bar = [&](int b) { return bar_base + 80u + 8u * b; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR_OFF + 96);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (g.M + BM - 1) / BM;
+  const int n_tiles = g.N / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int k_blocks = g.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<TMEM_COLS>(base + SMEM_BAR_OFF + 96);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles;
+        const int n_blk = tile - m_blk * n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
+          tma_load_2d(base + SMEM_A_OFF + stage * A_BYTES, &tmA, full_bar(stage), kb * BK,
+                      m_blk * BM);
+          tma_load_2d(base + SMEM_B_OFF + stage * B_BYTES, &tmB, full_bar(stage), kb * BK,
+                      n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t use_parity = (uint32_t(it) >> 1) & 1u;
+        mbar_wait(tempty_bar(buf), use_parity ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(buf * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = base + SMEM_A_OFF + stage * A_BYTES;
+          const uint32_t b_addr = base + SMEM_B_OFF + stage * B_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 1024, 16);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 1024, 16);
+            mma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));  // smem slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(buf));  // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int ew = warp - 2; // staging slot
+    const uint32_t slab0 = base + SMEM_D_OFF + ew * 2 * SLAB_BYTES;
+    int it = 0;
+    int chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / n_tiles;
+      const int n_blk = tile - m_blk * n_tiles;
+      const int buf = it & 1;
+      const uint32_t use_parity = (uint32_t(it) >> 1) & 1u;
+      mbar_wait(tfull_bar(buf), use_parity);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN);
+      const int row0 = m_blk * BM + q * 32;
+      const int row = row0 + lane;
+      const bool row_ok = row < g.M;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / CPC; ++c, ++chunk_ctr) {
+        const uint32_t slab = slab0 + (chunk_ctr & 1) * SLAB_BYTES;
+        // the TMA store that last read this slab (two chunks ago) must have drained it
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int half = 0; half < CPC / 32; ++half) {
+          uint32_t v[32];
+          tmem_ld32(t_row + uint32_t(c * CPC + half * 32), v);
+          tmem_ld_wait();
+          const int col0 = n_blk * BN + c * CPC + half * 32;
+          if (g.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(g.bias + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = __ldg(bp + i);
+              v[4 * i + 0] = __float_as_uint(__uint_as_float(v[4 * i + 0]) + b4.x);
+              v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + b4.y);
+              v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + b4.z);
+              v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + b4.w);
+            }
+          }
+          if constexpr (EPI == EPI_BIAS_RESID_F32) {
+            if (row_ok) {
+              const float4* rp4 =
+                  reinterpret_cast<const float4*>(g.resid + int64_t(row) * g.ldr + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 r4 = rp4[i];
+                v[4 * i + 0] = __float_as_uint(__uint_as_float(v[4 * i + 0]) + r4.x);
+                v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + r4.y);
+                v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + r4.z);
+                v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + r4.w);
+              }
+            }
+          }
+          if constexpr (EPI == EPI_BIAS_RELU_BF16) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              v[i] = __float_as_uint(fmaxf(__uint_as_float(v[i]), 0.0f));
+          }
+          const uint32_t row_addr = slab + uint32_t(lane) * 128u;
+          if constexpr (OUT_F32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t dst = row_addr + (uint32_t(i ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[4 * i]),
+                           "r"(v[4 * i + 1]), "r"(v[4 * i + 2]), "r"(v[4 * i + 3])
+                           : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t p0 = pack_bf16x2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+              const uint32_t p1 = pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+              const uint32_t p2 = pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+              const uint32_t p3 = pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+              const int chunk16 = half * 4 + i;
+              const uint32_t dst = row_addr + (uint32_t(chunk16 ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p0), "r"(p1),
+                           "r"(p2), "r"(p3)
+                           : "memory");
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmD, slab, n_blk * BN + c * CPC, row0);
+          tma_store_commit();
+        }
+      }
+      // all TMEM reads of this accumulator buffer are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int EPI>
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+               const GemmArgs& g, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    RP_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    configured = true;
+  }
+  gemm_bf16_kernel<EPI><<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(tmA, tmB, tmD, g);
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+}  // namespace
+
+int launch_gemm(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
+                int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
+                cudaStream_t stream) {
+  RP_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  RP_CHECK(N % BN == 0, "gemm: N=%d must be a multiple of %d", N, BN);
+  RP_CHECK(K % BK == 0, "gemm: K=%d must be a multiple of %d", K, BK);
+  RP_CHECK(lda % 8 == 0 && ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 elements");
+  const bool out_f32 = (epilogue == EPI_BIAS_F32 || epilogue == EPI_BIAS_RESID_F32);
+  RP_CHECK((ldd * (out_f32 ? 4 : 2)) % 16 == 0, "gemm: output pitch must be 16-byte aligned");
+  RP_CHECK(epilogue != EPI_BIAS_RESID_F32 || (resid != nullptr && ldr % 4 == 0),
+           "gemm: residual epilogue needs a 16-byte aligned residual");
+  RP_CHECK((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) |
+            reinterpret_cast<uintptr_t>(D) | reinterpret_cast<uintptr_t>(bias) |
+            reinterpret_cast<uintptr_t>(resid)) % 16 == 0,
+           "gemm: pointers must be 16-byte aligned");
+
+  CUtensorMap tmA, tmB, tmD;
+  int rc;
+  if ((rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, A, K, M, lda * 2, BK, BM))) return rc;
+  if ((rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, W, K, N, ldw * 2, BK, BN))) return rc;
+  if (out_f32)
+    rc = make_tmap_2d(&tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, D, N, M, ldd * 4, 32, 32);
+  else
+    rc = make_tmap_2d(&tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, D, N, M, ldd * 2, 64, 32);
+  if (rc) return rc;
+
+  GemmArgs g{M, N, K, bias, resid, ldr};
+  const int total_tiles = ((M + BM - 1) / BM) * (N / BN);
+  const int sms = num_sms();
+  if (sms <= 0) return RP_ERR_NO_DEVICE;
+  const int grid = total_tiles < sms ? total_tiles : sms;
+  switch (epilogue) {
+    case EPI_BIAS_BF16: return launch_one<EPI_BIAS_BF16>(tmA, tmB, tmD, g, grid, stream);
+    case EPI_BIAS_RELU_BF16: return launch_one<EPI_BIAS_RELU_BF16>(tmA, tmB, tmD, g, grid, stream);
+    case EPI_BIAS_F32: return launch_one<EPI_BIAS_F32>(tmA, tmB, tmD, g, grid, stream);
+    case EPI_BIAS_RESID_F32: return launch_one<EPI_BIAS_RESID_F32>(tmA, tmB, tmD, g, grid, stream);
+    default: set_last_error("gemm: unknown epilogue %d", epilogue); return RP_ERR_INVALID;
+  }
+}
+
+}  // namespace rp

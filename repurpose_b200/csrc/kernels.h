@@ -1,0 +1,85 @@
+// Internal launcher declarations (C++ side of the C-ABI in include/repurpose_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rp {
+
+// ---- GEMM: D[M,N] = A[M,K] (bf16, K-major) * W[N,K]^T (bf16, K-major) + epilogue --------------
+enum GemmEpilogue : int {
+  EPI_BIAS_BF16 = 0,       // D(bf16) = acc + bias
+  EPI_BIAS_RELU_BF16 = 1,  // D(bf16) = relu(acc + bias)
+  EPI_BIAS_F32 = 2,        // D(f32)  = acc + bias
+  EPI_BIAS_RESID_F32 = 3,  // D(f32)  = acc + bias + R   (R may alias D)
+};
+int launch_gemm(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
+                int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
+                cudaStream_t stream);
+
+// ---- fused multi-head attention (d_k = 64) -----------------------------------------------------
+// q/k/v: bf16, row pitch ld* elements, batch pitch bs* elements; head h occupies columns
+// [h*64, h*64+64) of each row.  q is expected pre-scaled by log2(e)/sqrt(d_k).
+// mask_mode 0: key-padding from kv_lens[b] (keys >= len get -inf, reference nn.MultiheadAttention
+//              semantics).  kv_lens == nullptr means all Tk keys valid.
+// mask_mode 1: explicit uint8 mask[b, (q), k] (0 = masked_fill(-1e9), models/transformer.py:70-72);
+//              mask_q_stride == 0 broadcasts over queries.
+struct FmhaArgs {
+  const void* q; const void* k; const void* v; void* o;
+  int64_t ldq, ldk, ldv, ldo;
+  int64_t bsq, bsk, bsv, bso;
+  int B, H, Tq, Tk;
+  const int32_t* kv_lens;
+  int mask_mode;
+  const uint8_t* mask; int64_t mask_b_stride, mask_q_stride;
+};
+int launch_fmha(const FmhaArgs& a, cudaStream_t stream);
+
+// ---- memory-bound kernels ------------------------------------------------------------------------
+// concat(vis, aud, txt) fp32 -> bf16 [M, Cv+Ca+Ct]
+int launch_concat_cast(const float* vis, const float* aud, const float* txt, int Cv, int Ca, int Ct,
+                       void* out_bf16, int64_t M, cudaStream_t stream);
+// generic fp32 -> bf16 cast of a contiguous buffer (n % 8 == 0)
+int launch_cast_bf16(const float* in, void* out_bf16, int64_t n, cudaStream_t stream);
+
+// LayerNorm over rows of 512 (eps 1e-5, biased variance), one warp per row.
+//   mode 0: y(bf16) = LN(x; g0,b0)
+//   mode 1: h(f32)  = LN(x; g0,b0) + pe[row % T];  y(bf16) = LN(h; g1,b1)
+//   mode 2: f(f32)  = relu(LN(x; g0,b0));  y(bf16) = LN(f; g1,b1);  y2(bf16) = LN(f; g2,b2)
+//   mode 3: y(f32)  = LN(x; g0,b0)                (used by tests / MHA module)
+struct LnArgs {
+  const float* x; int64_t M; int T;
+  const float* g0; const float* b0; const float* g1; const float* b1; const float* g2; const float* b2;
+  const float* pe;
+  float* out_f32; void* y_bf16; void* y2_bf16;
+  float eps;
+};
+int launch_layernorm512(int mode, const LnArgs& a, cudaStream_t stream);
+
+// final head projections: logits[M] = a_c[M,256].w_c + b_c ; offs[M,2] = relu(a_r[M,256].W_r^T + b_r)
+int launch_head_out(const void* a_cls_bf16, const void* a_reg_bf16, const float* w_cls,
+                    const float* b_cls, const float* w_reg, const float* b_reg, float* logits,
+                    float* offsets, int64_t M, cudaStream_t stream);
+
+// ---- decode + Soft-NMS (one CTA per video) -------------------------------------------------------
+struct DecodeCfg {
+  int pre_nms_topk;
+  float pre_nms_thresh, duration_thresh, duration_thresh_max;
+  float nms_sigma, min_score;
+};
+// logits [B,T], offsets [B,T,2], lens [B] (valid steps), max_seg [B].
+// outputs (Kcap slots per video): segs [B,Kcap,2] f32, scores [B,Kcap] f32 (original probability),
+// dscores [B,Kcap] f32 (decayed), labels [B,Kcap] i32, counts [B] i32, ncand [B] i32.
+// Optional (all or none): cand_segs [B,C,2], cand_scores [B,C], cand_labels [B,C] with
+// C = min(pre_nms_topk, T): the pre-NMS candidate list in descending score order.
+int launch_decode_nms(const float* logits, const float* offsets, const int32_t* lens,
+                      const int32_t* max_seg, int B, int T, const DecodeCfg& cfg, int Kcap,
+                      float* segs, float* scores, float* dscores, int32_t* labels, int32_t* counts,
+                      int32_t* ncand, float* cand_segs, float* cand_scores, int32_t* cand_labels,
+                      cudaStream_t stream);
+// Soft-NMS alone on caller candidates: scores [B,Nmax], segs [B,Nmax,2], n [B], max_seg [B]
+// -> keep [B,Kcap] i32 (original indices, selection order), kscores [B,Kcap] (decayed), counts [B].
+int launch_soft_nms(const float* scores, const float* segs, const int32_t* n, const int32_t* max_seg,
+                    int B, int Nmax, float sigma, float thresh, int Kcap, int32_t* keep,
+                    float* kscores, int32_t* counts, cudaStream_t stream);
+
+}  // namespace rp

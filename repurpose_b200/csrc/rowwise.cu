@@ -1,0 +1,268 @@
+// Memory-bound row-wise kernels of the hot path: modality concat + bf16 cast, the LayerNorm family
+// (one warp per 512-wide row, row held in registers, 128-bit loads/stores), and the final
+// 256->1 / 256->2 head projections.  Reference: models/MMCTransformer.py:118 (cat), :124/:127
+// (input_norm, positional_encoding), :58/:141 (encoder_norm), :63-68 (feature_map LN+ReLU),
+// :71-93 (head LayerNorm and last Linear layers); nn.TransformerEncoderLayer norm1/norm2.
+#include <cuda_bf16.h>
+
+#include "ptx.cuh"
+#include "host_util.h"
+#include "kernels.h"
+
+namespace rp {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  uint2 r;
+  r.x = pack_bf16x2(a, b);
+  r.y = pack_bf16x2(c, d);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// concat + cast: out[m, :] = bf16(cat(vis[m], aud[m], txt[m]))
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+concat_cast_kernel(const float* __restrict__ vis, const float* __restrict__ aud,
+                   const float* __restrict__ txt, int Cv, int Ca, int Ct,
+                   __nv_bfloat16* __restrict__ out, int64_t M) {
+  const int C = Cv + Ca + Ct;
+  const int groups_per_row = C >> 3;  // 8 elements (32 B in, 16 B out) per thread-iteration
+  const int64_t total = M * groups_per_row;
+  for (int64_t g = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; g < total;
+       g += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t m = g / groups_per_row;
+    const int c = int(g - m * groups_per_row) << 3;
+    const float* src;
+    if (c < Cv) src = vis + m * Cv + c;
+    else if (c < Cv + Ca) src = aud + m * Ca + (c - Cv);
+    else src = txt + m * Ct + (c - Cv - Ca);
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + 1);
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y);
+    o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y);
+    o.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(out + m * C + c) = o;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n8) {
+  for (int64_t g = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; g < n8;
+       g += int64_t(gridDim.x) * blockDim.x) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(in) + 2 * g);
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(in) + 2 * g + 1);
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y);
+    o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y);
+    o.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(out)[g] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over 512 columns.  Lane l owns columns {128*i + 4*l .. +3}, i = 0..3, so every
+// warp-wide access is a contiguous 512-byte (fp32) or 256-byte (bf16) segment.
+// Two-pass statistics in registers (mean, then centred sum of squares) like ATen's CPU kernel.
+// ------------------------------------------------------------------------------------------
+struct Row {
+  float v[16];
+};
+
+__device__ __forceinline__ void row_load(Row& r, const float* __restrict__ p, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(p + 128 * i + 4 * lane);
+    r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void row_store_f32(const Row& r, float* __restrict__ p, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(p + 128 * i + 4 * lane) =
+        make_float4(r.v[4 * i], r.v[4 * i + 1], r.v[4 * i + 2], r.v[4 * i + 3]);
+}
+__device__ __forceinline__ void row_store_bf16(const Row& r, __nv_bfloat16* __restrict__ p, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<uint2*>(p + 128 * i + 4 * lane) =
+        pack4_bf16(r.v[4 * i], r.v[4 * i + 1], r.v[4 * i + 2], r.v[4 * i + 3]);
+}
+__device__ __forceinline__ void row_norm(Row& out, const Row& in, const float* __restrict__ g,
+                                         const float* __restrict__ b, float eps, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += in.v[i];
+  const float mean = warp_sum(s) * (1.0f / 512.0f);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float d = in.v[i] - mean;
+    ss += d * d;
+  }
+  const float var = warp_sum(ss) * (1.0f / 512.0f);
+  const float rstd = rsqrtf(var + eps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + 128 * i + 4 * lane));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + 128 * i + 4 * lane));
+    out.v[4 * i + 0] = (in.v[4 * i + 0] - mean) * rstd * g4.x + b4.x;
+    out.v[4 * i + 1] = (in.v[4 * i + 1] - mean) * rstd * g4.y + b4.y;
+    out.v[4 * i + 2] = (in.v[4 * i + 2] - mean) * rstd * g4.z + b4.z;
+    out.v[4 * i + 3] = (in.v[4 * i + 3] - mean) * rstd * g4.w + b4.w;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+layernorm512_kernel(const LnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = int64_t(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5); row < a.M;
+       row += warps_total) {
+    Row x, y;
+    row_load(x, a.x + row * 512, lane);
+    row_norm(y, x, a.g0, a.b0, a.eps, lane);
+    if constexpr (MODE == 0) {
+      row_store_bf16(y, reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + row * 512, lane);
+    } else if constexpr (MODE == 3) {
+      row_store_f32(y, a.out_f32 + row * 512, lane);
+    } else if constexpr (MODE == 1) {
+      Row pe;
+      row_load(pe, a.pe + int64_t(row % a.T) * 512, lane);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) y.v[i] += pe.v[i];
+      row_store_f32(y, a.out_f32 + row * 512, lane);
+      Row u;
+      row_norm(u, y, a.g1, a.b1, a.eps, lane);
+      row_store_bf16(u, reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + row * 512, lane);
+    } else {  // MODE 2
+#pragma unroll
+      for (int i = 0; i < 16; ++i) y.v[i] = fmaxf(y.v[i], 0.0f);
+      row_store_f32(y, a.out_f32 + row * 512, lane);
+      Row u;
+      row_norm(u, y, a.g1, a.b1, a.eps, lane);
+      row_store_bf16(u, reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + row * 512, lane);
+      row_norm(u, y, a.g2, a.b2, a.eps, lane);
+      row_store_bf16(u, reinterpret_cast<__nv_bfloat16*>(a.y2_bf16) + row * 512, lane);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// head outputs: one warp per row, 256-wide dot products against 3 weight rows held in registers
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_out_kernel(const __nv_bfloat16* __restrict__ ac, const __nv_bfloat16* __restrict__ ar,
+                const float* __restrict__ wc, const float* __restrict__ bc,
+                const float* __restrict__ wr, const float* __restrict__ br,
+                float* __restrict__ logits, float* __restrict__ offsets, int64_t M) {
+  const int lane = threadIdx.x & 31;
+  float w0[8], w1[8], w2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    w0[i] = wc[8 * lane + i];
+    w1[i] = wr[8 * lane + i];
+    w2[i] = wr[256 + 8 * lane + i];
+  }
+  const float bias_c = bc[0], bias_r0 = br[0], bias_r1 = br[1];
+  const int64_t warps_total = int64_t(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5); row < M;
+       row += warps_total) {
+    const uint4 c4 = *reinterpret_cast<const uint4*>(ac + row * 256 + 8 * lane);
+    const uint4 r4 = *reinterpret_cast<const uint4*>(ar + row * 256 + 8 * lane);
+    const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
+    const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float c_lo = __uint_as_float(cw[i] << 16), c_hi = __uint_as_float(cw[i] & 0xffff0000u);
+      const float r_lo = __uint_as_float(rw[i] << 16), r_hi = __uint_as_float(rw[i] & 0xffff0000u);
+      s0 += c_lo * w0[2 * i] + c_hi * w0[2 * i + 1];
+      s1 += r_lo * w1[2 * i] + r_hi * w1[2 * i + 1];
+      s2 += r_lo * w2[2 * i] + r_hi * w2[2 * i + 1];
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      logits[row] = s0 + bias_c;
+      offsets[2 * row] = fmaxf(s1 + bias_r0, 0.0f);
+      offsets[2 * row + 1] = fmaxf(s2 + bias_r1, 0.0f);
+    }
+  }
+}
+
+inline int grid_for(int64_t work_items, int per_block) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  const int64_t cap = int64_t(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return int(blocks);
+}
+
+}  // namespace
+
+int launch_concat_cast(const float* vis, const float* aud, const float* txt, int Cv, int Ca, int Ct,
+                       void* out_bf16, int64_t M, cudaStream_t stream) {
+  RP_CHECK(M > 0, "concat_cast: empty");
+  RP_CHECK(Cv % 8 == 0 && Ca % 8 == 0 && Ct % 8 == 0, "concat_cast: dims must be multiples of 8");
+  const int64_t groups = M * ((Cv + Ca + Ct) / 8);
+  concat_cast_kernel<<<grid_for(groups, 256), 256, 0, stream>>>(
+      vis, aud, txt, Cv, Ca, Ct, reinterpret_cast<__nv_bfloat16*>(out_bf16), M);
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+int launch_cast_bf16(const float* in, void* out_bf16, int64_t n, cudaStream_t stream) {
+  RP_CHECK(n > 0 && n % 8 == 0, "cast_bf16: n must be a positive multiple of 8");
+  cast_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(
+      in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n / 8);
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+int launch_layernorm512(int mode, const LnArgs& a, cudaStream_t stream) {
+  RP_CHECK(a.M > 0, "layernorm: empty");
+  const int grid = grid_for(a.M, 8);
+  switch (mode) {
+    case 0: layernorm512_kernel<0><<<grid, 256, 0, stream>>>(a); break;
+    case 1:
+      RP_CHECK(a.pe != nullptr && a.T > 0, "layernorm mode 1 needs pe and T");
+      layernorm512_kernel<1><<<grid, 256, 0, stream>>>(a);
+      break;
+    case 2: layernorm512_kernel<2><<<grid, 256, 0, stream>>>(a); break;
+    case 3: layernorm512_kernel<3><<<grid, 256, 0, stream>>>(a); break;
+    default: set_last_error("layernorm: unknown mode %d", mode); return RP_ERR_INVALID;
+  }
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+int launch_head_out(const void* a_cls_bf16, const void* a_reg_bf16, const float* w_cls,
+                    const float* b_cls, const float* w_reg, const float* b_reg, float* logits,
+                    float* offsets, int64_t M, cudaStream_t stream) {
+  RP_CHECK(M > 0, "head_out: empty");
+  head_out_kernel<<<grid_for(M, 8), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a_cls_bf16),
+      reinterpret_cast<const __nv_bfloat16*>(a_reg_bf16), w_cls, b_cls, w_reg, b_reg, logits,
+      offsets, M);
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+}  // namespace rp

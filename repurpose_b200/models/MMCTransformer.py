@@ -1,0 +1,265 @@
+"""Drop-in `MMCTransformer` for the Repurpose inference hot path, executed by hand-written sm_100a
+kernels through the C ABI (include/repurpose_b200.h).
+
+Mirrors the reference interface (paths relative to YosubShin/Repurpose):
+  * constructor              models/MMCTransformer.py:26   (same argument names; `text_num_layers`
+                                                            and `cross_num_layers` are ignored there too)
+  * forward(batch)           models/MMCTransformer.py:109-151  -> the same 6-tuple
+  * inference_(batch, cfg)   models/MMCTransformer.py:231-275  -> list of dicts
+  * inference_single_video   models/MMCTransformer.py:181-229
+  * state_dict keys / shapes models/MMCTransformer.py:32-93    (checkpoints load unchanged)
+
+The torch sub-modules below exist only as the parameter store (same construction order as the
+reference, so the same `torch.manual_seed` yields the same random init); no torch op of theirs is
+ever executed.  All compute happens in librepurpose_b200.so — there is no PyTorch/CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .._lib import RpDecodeCfg, RpModelCfg, check, cur_stream, ptr
+from .softnms import soft_nms_intervals_cpu  # noqa: F401  (re-exported like the reference module)
+
+HEAD_HIDDEN = 256
+
+
+class PositionalEncoding(nn.Module):
+    """Sinusoidal table, same formula/layout as models/MMCTransformer.py:9-22 (buffer `pe`
+    [1, max_len, d_model]); only the table is used — the add is fused into a LayerNorm kernel."""
+
+    def __init__(self, d_model: int, max_len: int = 5000):
+        super().__init__()
+        self.register_buffer("pe", self.table(d_model, max_len).unsqueeze(0))
+
+    @staticmethod
+    def table(d_model: int, max_len: int) -> torch.Tensor:
+        pe = torch.zeros(max_len, d_model)
+        position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        return pe
+
+
+class MMCTransformer(nn.Module):
+    def __init__(self, vis_dim, aud_dim, text_dim, d_model, self_num_layers, text_num_layers,
+                 cross_num_layers, num_heads, d_ff=2048, max_len=5000):
+        super().__init__()
+        self._cfg = dict(vis_dim=vis_dim, aud_dim=aud_dim, text_dim=text_dim, d_model=d_model,
+                         num_layers=self_num_layers, num_heads=num_heads, d_ff=d_ff,
+                         head_hidden=HEAD_HIDDEN, max_len=max_len)
+        # ---- parameter store (names, shapes and RNG order of the reference) -------------------
+        self.input_projection = nn.Linear(vis_dim + aud_dim + text_dim, d_model)
+        self.input_norm = nn.LayerNorm(d_model)
+        self.positional_encoding = PositionalEncoding(d_model, max_len)
+        layer = nn.TransformerEncoderLayer(d_model=d_model, nhead=num_heads, dim_feedforward=d_ff,
+                                           dropout=0.1, activation="relu", batch_first=True,
+                                           norm_first=True)
+        self.multimodal_encoder = nn.TransformerEncoder(layer, num_layers=self_num_layers,
+                                                        enable_nested_tensor=False)
+        self.encoder_norm = nn.LayerNorm(d_model)
+        self.feature_map = nn.Sequential(nn.Linear(d_model, d_model), nn.LayerNorm(d_model),
+                                         nn.ReLU(), nn.Dropout(0.1))
+        self.cls_head = nn.Sequential(
+            nn.LayerNorm(d_model), nn.Linear(d_model, HEAD_HIDDEN), nn.ReLU(), nn.Dropout(0.1),
+            nn.Linear(HEAD_HIDDEN, HEAD_HIDDEN), nn.ReLU(), nn.Dropout(0.1),
+            nn.Linear(HEAD_HIDDEN, 1))
+        self.reg_head = nn.Sequential(
+            nn.LayerNorm(d_model), nn.Linear(d_model, HEAD_HIDDEN), nn.ReLU(), nn.Dropout(0.1),
+            nn.Linear(HEAD_HIDDEN, HEAD_HIDDEN), nn.ReLU(), nn.Dropout(0.1),
+            nn.Linear(HEAD_HIDDEN, 2), nn.ReLU())
+        self._init_weights()
+        # ---- native state ---------------------------------------------------------------------
+        self._handle = None
+        self._weights_sig = None
+        self._workspace = None
+        self.register_load_state_dict_post_hook(lambda module, _keys: module._invalidate())
+
+    def _init_weights(self):
+        # models/MMCTransformer.py:98-107: Xavier for every nn.Linear, zero bias, LN gamma=1 beta=0
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    # ------------------------------------------------------------------------------- plumbing
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def _invalidate(self):
+        self._weights_sig = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._weights_sig = None
+        return out
+
+    def __del__(self):
+        try:
+            h = self.__dict__.get("_handle")
+            if h is not None:
+                self.__dict__["_handle"] = None
+                _lib.load().rp_destroy(h)
+        except Exception:
+            pass
+
+    def _signature(self):
+        sig = [self.device]
+        for p in self.parameters():
+            sig.append((p.data_ptr(), p._version))
+        return tuple(sig)
+
+    def refresh_weights(self):
+        """(Re)pack the current parameters into the native handle.  Called automatically when a
+        parameter's storage or autograd version changed (`load_state_dict`, `.to()`, optimizer
+        steps); call it by hand after editing weights through `.data`."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise _lib.RepurposeError(
+                "repurpose_b200.MMCTransformer runs only on a CUDA (sm_100) device; "
+                "move the module with .to('cuda') — there is no CPU path")
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            if self._handle is None:
+                cfg = RpModelCfg(**self._cfg)
+                h = C.c_void_p()
+                check(lib.rp_create(C.byref(cfg), C.byref(h)), "rp_create")
+                self._handle = h
+            st = cur_stream()
+            for name, t in self.state_dict().items():
+                t32 = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+                check(lib.rp_load_weight(self._handle, name.encode(), ptr(t32), t32.numel(), st),
+                      f"rp_load_weight({name})")
+            check(lib.rp_weights_complete(self._handle), "rp_weights_complete")
+            torch.cuda.current_stream().synchronize()  # staging copies above may be temporaries
+        self._weights_sig = self._signature()
+
+    def _ensure_ready(self):
+        if self._handle is None or self._weights_sig != self._signature():
+            self.refresh_weights()
+
+    def _get_workspace(self, B, T):
+        need = _lib.load().rp_workspace_bytes(self._handle, B, T)
+        if need < 0:
+            raise _lib.RepurposeError("rp_workspace_bytes failed")
+        ws = self._workspace
+        if ws is None or ws.numel() < need or ws.device != self.device:
+            self._workspace = ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return ws
+
+    @staticmethod
+    def _as_f32(t, dev):
+        return t.to(device=dev, dtype=torch.float32).contiguous()
+
+    # -------------------------------------------------------------------------------- forward
+    def forward(self, batch):
+        """batch: dict with visual_feats [B,T,Cv], audio_feats [B,T,Ca], text_feats [B,T,Ct] fp32,
+        masks [B,1,T] bool (True = valid, left-aligned as built by dataset/RepurposeClip.py:528-531),
+        labels, segments (passed through).  Returns (masks, cls_logits [B,T,1], offsets [B,T,2],
+        labels, segments, feats [B,T,d_model]) like the reference."""
+        self._ensure_ready()
+        dev = self.device
+        vis = self._as_f32(batch["visual_feats"], dev)
+        aud = self._as_f32(batch["audio_feats"], dev)
+        txt = self._as_f32(batch["text_feats"], dev)
+        masks = batch["masks"]
+        B, T = vis.shape[0], vis.shape[1]
+        lens = masks.to(dev).reshape(B, -1).ne(0).sum(dim=1, dtype=torch.int32).contiguous()
+        logits = torch.empty(B, T, 1, dtype=torch.float32, device=dev)
+        offsets = torch.empty(B, T, 2, dtype=torch.float32, device=dev)
+        feats = torch.empty(B, T, self._cfg["d_model"], dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = self._get_workspace(B, T)
+            check(_lib.load().rp_forward(self._handle, ptr(vis), ptr(aud), ptr(txt), ptr(lens), B, T,
+                                         ptr(logits), ptr(offsets), ptr(feats), ptr(ws), ws.numel(),
+                                         cur_stream()), "rp_forward")
+        self._last_lens = lens
+        return masks, logits, offsets, batch.get("labels"), batch.get("segments"), feats
+
+    def losses(self, masks, out_cls_logits, out_offsets, gt_cls_labels, gt_offsets, feats):
+        raise NotImplementedError(
+            "training losses are outside the inference hot path (SURVEY.md §8 f3)")
+
+    # --------------------------------------------------------------------------------- decode
+    @staticmethod
+    def _decode_cfg(s):
+        return RpDecodeCfg(int(s["pre_nms_topk"]), float(s["pre_nms_thresh"]),
+                           float(s["duration_thresh"]), float(s["duration_thresh_max"]),
+                           float(s.get("nms_sigma", 0.5)), float(s.get("min_score", 0.001)))
+
+    def _run_decode(self, logits, offsets, lens, max_seg, settings, want_candidates=False):
+        """logits [B,T] f32, offsets [B,T,2] f32, lens [B] i32 (device), max_seg: list[int]."""
+        dev = logits.device
+        B, T = logits.shape
+        kcap = max(1, max(max_seg))
+        if kcap > 64:
+            raise _lib.RepurposeError(f"max_seg_num={kcap} exceeds the 64 slots of the decode kernel")
+        max_seg_t = torch.tensor(max_seg, dtype=torch.int32).to(dev, non_blocking=True)
+        segs = torch.empty(B, kcap, 2, dtype=torch.float32, device=dev)
+        scores = torch.empty(B, kcap, dtype=torch.float32, device=dev)
+        dscores = torch.empty(B, kcap, dtype=torch.float32, device=dev)
+        labels = torch.empty(B, kcap, dtype=torch.int32, device=dev)
+        counts = torch.empty(B, dtype=torch.int32, device=dev)
+        ncand = torch.empty(B, dtype=torch.int32, device=dev)
+        cseg = cscore = clabel = None
+        if want_candidates:
+            ccap = min(int(settings["pre_nms_topk"]), T)
+            cseg = torch.empty(B, ccap, 2, dtype=torch.float32, device=dev)
+            cscore = torch.empty(B, ccap, dtype=torch.float32, device=dev)
+            clabel = torch.empty(B, ccap, dtype=torch.int32, device=dev)
+        cfg = self._decode_cfg(settings)
+        with torch.cuda.device(dev):
+            check(_lib.load().rp_decode_nms(ptr(logits), ptr(offsets), ptr(lens), ptr(max_seg_t), B, T,
+                                            C.byref(cfg), kcap, ptr(segs), ptr(scores), ptr(dscores),
+                                            ptr(labels), ptr(counts), ptr(ncand), ptr(cseg),
+                                            ptr(cscore), ptr(clabel), cur_stream()), "rp_decode_nms")
+        return dict(segments=segs, scores=scores, dscores=dscores, labels=labels, counts=counts,
+                    ncand=ncand, cand_segments=cseg, cand_scores=cscore, cand_labels=clabel)
+
+    @torch.no_grad()
+    def inference_single_video(self, masks, out_cls_logits, out_offsets, inference_settings):
+        """Pre-NMS candidates of one video (reference :181-229): dict(segments [N,2], scores [N]
+        descending, labels [N] int64)."""
+        dev = out_cls_logits.device
+        logits = out_cls_logits.reshape(1, -1).to(torch.float32).contiguous()
+        T = logits.shape[1]
+        offsets = out_offsets.reshape(1, T, 2).to(torch.float32).contiguous()
+        lens = masks.to(dev).reshape(1, -1).ne(0).sum(dim=1, dtype=torch.int32).contiguous()
+        r = self._run_decode(logits, offsets, lens, [1], inference_settings, want_candidates=True)
+        n = int(r["ncand"][0].item())
+        return {"segments": r["cand_segments"][0, :n], "scores": r["cand_scores"][0, :n],
+                "labels": r["cand_labels"][0, :n].to(torch.int64)}
+
+    @torch.no_grad()
+    def inference_(self, batch, inference_settings):
+        """forward -> per-video decode -> Soft-NMS, all on the device (reference :231-275).
+        Returns one dict per video: segments [K,2] f32 (feature-grid seconds), scores [K] f32
+        (the candidate's probability, i.e. the reference's CUDA semantics),
+        labels [K] int64, video_id, duration — in Soft-NMS selection order."""
+        masks, logits, offsets, _, _, _ = self.forward(batch)
+        vid_idxs = batch["video_id"]
+        vid_lens = batch["duration"]
+        max_seg = [int(np.ceil((int(v) // 60) * inference_settings["max_seg_per_min"]))
+                   for v in vid_lens]
+        B, T = logits.shape[0], logits.shape[1]
+        r = self._run_decode(logits.view(B, T), offsets, self._last_lens, max_seg,
+                             inference_settings)
+        counts = r["counts"].tolist()  # the single device->host sync of the whole batch
+        labels64 = r["labels"].to(torch.int64)
+        results = []
+        for i, (vidx, vlen) in enumerate(zip(vid_idxs, vid_lens)):
+            k = counts[i]
+            results.append({"segments": r["segments"][i, :k], "scores": r["scores"][i, :k],
+                            "labels": labels64[i, :k], "video_id": vidx, "duration": vlen})
+        return results
