@@ -1,0 +1,259 @@
+"""GPU parity tests at the reference-facing boundary: Soft-NMS / decode against the golden vectors
+produced by the reference and against the oracle; MMCTransformer.forward / inference_ against the
+golden vectors (T=700) and the fp32 oracle; MultiHeadAttention against the oracle.
+
+Tolerances (BASELINE.json north_star): logits / offsets within 2e-2 relative of the fp32
+reference (bf16 tensor-core path); Soft-NMS keep set and order bit-exact on identical fp32
+candidates with decayed scores within 1e-6; AtIoU within 0.1 point."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mmct, synth
+from oracle.softnms import soft_nms_intervals_oracle
+from repurpose_b200.models.MMCTransformer import MMCTransformer
+from repurpose_b200.models.softnms import (soft_nms_batched, soft_nms_intervals,
+                                           soft_nms_intervals_cpu)
+from repurpose_b200.models.transformer import MultiHeadAttention
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+REL_TOL = 2e-2
+
+
+def _rel_err(got, ref):
+    """max |got - ref| relative to max |ref| (the scale of the tensor)"""
+    got, ref = torch.as_tensor(got).float().cpu(), torch.as_tensor(ref).float().cpu()
+    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-6)).item()
+
+
+# ------------------------------------------------------------------------------------ Soft-NMS
+def test_softnms_golden_cases(golden_dir):
+    g = np.load(golden_dir / "softnms_cases.npz")
+    for name in g["names"]:
+        sigma, thresh, ms = g[f"{name}_params"]
+        s = torch.from_numpy(g[f"{name}_scores"])
+        seg = torch.from_numpy(g[f"{name}_segments"])
+        keep = soft_nms_intervals_cpu(s.to(DEV), seg.to(DEV), sigma=sigma, thresh=thresh,
+                                      max_seg_num=int(ms))
+        assert keep.dtype == np.int64
+        assert np.array_equal(keep, g[f"{name}_keep"]), (name, keep.tolist(), g[f"{name}_keep"].tolist())
+        # host tensors are accepted too (reference signature) and never mutated
+        s0 = s.clone()
+        keep2 = soft_nms_intervals_cpu(s, seg, sigma=sigma, thresh=thresh, max_seg_num=int(ms))
+        assert np.array_equal(keep2, keep) and torch.equal(s, s0)
+
+
+def test_softnms_decayed_scores_and_batched_vs_oracle():
+    B, nmax = 6, 1000
+    ns = [1000, 640, 1, 0, 333, 1000]
+    ms = [9, 5, 3, 4, 300, 0]
+    scores = torch.zeros(B, nmax)
+    segs = torch.zeros(B, nmax, 2)
+    for b, n in enumerate(ns):
+        if n:
+            s, g_ = synth.make_candidates(n, 1801, 100 + b)
+            scores[b, :n] = torch.from_numpy(s)
+            segs[b, :n] = torch.from_numpy(g_)
+    keep, ksc, counts = soft_nms_batched(scores.to(DEV), segs.to(DEV),
+                                         torch.tensor(ns, dtype=torch.int32, device=DEV),
+                                         torch.tensor(ms, dtype=torch.int32, device=DEV), 0.5, 0.01,
+                                         kcap=300)
+    keep, ksc, counts = keep.cpu().numpy(), ksc.cpu().numpy(), counts.cpu().numpy()
+    for b, (n, m) in enumerate(zip(ns, ms)):
+        ko, so = soft_nms_intervals_oracle(scores[b, :n].numpy(), segs[b, :n].numpy(), 0.5, 0.01, m,
+                                           return_scores=True)
+        assert counts[b] == len(ko), (b, counts[b], len(ko))
+        assert np.array_equal(keep[b, :counts[b]], ko), b
+        np.testing.assert_allclose(ksc[b, :counts[b]], so, atol=1e-6)
+
+
+def test_softnms_stress_4096_candidates():
+    s, g_ = synth.make_candidates(4096, 8192, 77)
+    ko, so = soft_nms_intervals_oracle(s, g_, 0.5, 0.01, 41, return_scores=True)
+    k = soft_nms_intervals(torch.from_numpy(s).to(DEV), torch.from_numpy(g_).to(DEV), 0.5, 0.01, 41)
+    assert k.is_cuda and k.dtype == torch.int64
+    assert np.array_equal(k.cpu().numpy(), ko)
+
+
+# ------------------------------------------------------------------------------------ decode
+def _decode(model, logits, offsets, lens, max_seg, cfg=synth.TEST_CFG):
+    return model._run_decode(logits.to(DEV).contiguous(), offsets.to(DEV).contiguous(),
+                             torch.tensor(lens, dtype=torch.int32, device=DEV), max_seg, cfg,
+                             want_candidates=True)
+
+
+@pytest.fixture(scope="module")
+def tiny_model():
+    torch.manual_seed(0)
+    return MMCTransformer(512, 2048, 384, 512, 1, 3, 3, 8).to(DEV).eval()
+
+
+def test_decode_golden_cases(tiny_model, golden_dir):
+    g = np.load(golden_dir / "decode_cases.npz")
+    for ci in range(int(g["n_cases"])):
+        logits = torch.from_numpy(g[f"c{ci}_logits"])[None]
+        offsets = torch.from_numpy(g[f"c{ci}_offsets"])[None]
+        r = _decode(tiny_model, logits, offsets, [int(g[f"c{ci}_len"])], [9])
+        n = int(r["ncand"][0])
+        assert n == len(g[f"c{ci}_scores"]), (ci, n)
+        assert np.array_equal(r["cand_labels"][0, :n].cpu().numpy(), g[f"c{ci}_labels"]), ci
+        np.testing.assert_allclose(r["cand_scores"][0, :n].cpu().numpy(), g[f"c{ci}_scores"], atol=1e-6)
+        np.testing.assert_allclose(r["cand_segments"][0, :n].cpu().numpy(), g[f"c{ci}_segments"], atol=1e-4)
+        # Soft-NMS on the candidates decoded by the reference -> same kept labels as our fused path
+        ko = soft_nms_intervals_oracle(g[f"c{ci}_scores"], g[f"c{ci}_segments"], 0.5, 0.01, 9)
+        k = int(r["counts"][0])
+        assert np.array_equal(r["labels"][0, :k].cpu().numpy(), g[f"c{ci}_labels"][ko]), ci
+        via_api = tiny_model.inference_single_video(
+            (torch.arange(logits.shape[1]) < int(g[f"c{ci}_len"]))[None].to(DEV),
+            logits[0].to(DEV), offsets[0].to(DEV), synth.TEST_CFG)
+        assert np.array_equal(via_api["labels"].cpu().numpy(), g[f"c{ci}_labels"])
+        assert via_api["labels"].dtype == torch.int64
+
+
+def test_decode_edge_cases(tiny_model):
+    T = 256
+    # nothing above threshold / everything filtered by duration / video shorter than a minute
+    logits = torch.full((3, T), -5.0)
+    logits[1] = 5.0
+    logits[2] = 5.0
+    offsets = torch.full((3, T, 2), 20.0)
+    offsets[1] = 1.0  # duration 2 < 10
+    r = _decode(tiny_model, logits, offsets, [T, T, 59], [2, 2, synth.max_seg_num(59, 0.3)])
+    assert r["counts"].tolist() == [0, 0, 0]
+    assert r["ncand"].tolist() == [0, 0, 59]
+    # topk truncation: all T steps pass, only pre_nms_topk survive
+    cfg = dict(synth.TEST_CFG, pre_nms_topk=100)
+    logits = torch.linspace(0.1, 6.0, T)[None]
+    offsets = torch.full((1, T, 2), 20.0)
+    r = _decode(tiny_model, logits, offsets, [T], [4], cfg)
+    assert int(r["ncand"][0]) == 100
+    assert r["cand_labels"][0, :100].tolist() == list(range(T - 1, T - 101, -1))
+
+
+# ------------------------------------------------------------------------------------ model
+@pytest.fixture(scope="module")
+def full_model():
+    torch.manual_seed(0)
+    return MMCTransformer(**synth.MODEL_CFG).to(DEV).eval()
+
+
+def test_forward_matches_reference_golden(full_model, golden_dir):
+    g = np.load(golden_dir / "forward_T700.npz")
+    batch = synth.make_batch(g["lens"].tolist(), seed=int(g["batch_seed"]))
+    dbatch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    masks, logits, offsets, labels, segments, feats = full_model(dbatch)
+    assert logits.shape == (2, 700, 1) and offsets.shape == (2, 700, 2) and feats.shape == (2, 700, 512)
+    assert masks is dbatch["masks"] and labels is dbatch["labels"] and segments is dbatch["segments"]
+    valid = batch["masks"][:, 0, :]
+    for name, got, ref in (("logits", logits, g["init_logits"]), ("offsets", offsets, g["init_offsets"]),
+                           ("feats", feats[:, :, ::16], g["init_feats_sub"])):
+        assert torch.isfinite(got).all(), f"{name} has non-finite values (padded rows must be finite)"
+        got_v = got.cpu()[valid]
+        ref_v = torch.from_numpy(ref)[valid]
+        err = _rel_err(got_v, ref_v)
+        assert err < REL_TOL, f"{name}: relative error {err:.4f} vs reference golden (valid steps)"
+
+
+def test_inference_matches_reference_golden(full_model, golden_dir):
+    g = np.load(golden_dir / "forward_T700.npz")
+    sd = {k: v.cpu() for k, v in full_model.state_dict().items()}
+    full_model.load_state_dict(synth.bias_reg_head(sd))
+    try:
+        batch = synth.make_batch(g["lens"].tolist(), seed=int(g["batch_seed"]))
+        dbatch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        _, logits, offsets, _, _, _ = full_model(dbatch)
+        valid = batch["masks"][:, 0, :]
+        assert _rel_err(logits.cpu()[valid], torch.from_numpy(g["regbias_logits"])[valid]) < REL_TOL
+        assert _rel_err(offsets.cpu()[valid], torch.from_numpy(g["regbias_offsets"])[valid]) < REL_TOL
+        res = full_model.inference_(dbatch, synth.TEST_CFG)
+        assert [r["video_id"] for r in res] == batch["video_id"]
+        assert [r["duration"] for r in res] == batch["duration"]
+        gts = [synth.make_gt_segments(l, 500 + i) for i, l in enumerate(batch["duration"])]
+        ours_pred = [r["segments"].tolist() for r in res]
+        ref_pred = [g[f"inf{i}_segments"].tolist() for i in range(len(res))]
+        a_ours, _ = mmct.atiou(gts, ours_pred)
+        a_ref, _ = mmct.atiou(gts, ref_pred)
+        assert abs(a_ours - a_ref) * 100 <= 0.1 + 100.0 / max(1, sum(len(p) for p in ref_pred)), \
+            f"AtIoU {a_ours:.4f} vs reference {a_ref:.4f}"
+        for i, r in enumerate(res):
+            assert r["labels"].dtype == torch.int64 and r["segments"].dtype == torch.float32
+            assert r["segments"].shape[0] <= synth.max_seg_num(batch["duration"][i], 0.3)
+        # identical fp32 candidates -> bit-exact keep: feed the reference's logits/offsets to our decode
+        lens = g["lens"].tolist()
+        ms = [synth.max_seg_num(l, 0.3) for l in lens]
+        r = full_model._run_decode(torch.from_numpy(g["regbias_logits"][:, :, 0]).to(DEV).contiguous(),
+                                   torch.from_numpy(g["regbias_offsets"]).to(DEV).contiguous(),
+                                   torch.tensor(lens, dtype=torch.int32, device=DEV), ms, synth.TEST_CFG)
+        for i in range(len(lens)):
+            k = int(r["counts"][i])
+            assert np.array_equal(r["labels"][i, :k].cpu().numpy(), g[f"inf{i}_labels"]), i
+            np.testing.assert_allclose(r["segments"][i, :k].cpu().numpy(), g[f"inf{i}_segments"], atol=1e-4)
+            np.testing.assert_allclose(r["scores"][i, :k].cpu().numpy(), g[f"inf{i}_scores"], atol=1e-6)
+    finally:
+        full_model.load_state_dict(sd)
+
+
+def test_forward_matches_oracle_ragged_small():
+    # 2-layer model, ragged batch whose T is not a multiple of any tile size
+    torch.manual_seed(3)
+    m = MMCTransformer(512, 2048, 384, 512, 2, 3, 3, 8).to(DEV).eval()
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    batch = synth.make_batch([333, 1, 130, 257], seed=4)
+    o_logits, o_offsets, o_feats = mmct.forward(sd, batch)
+    dbatch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    _, logits, offsets, _, _, feats = m(dbatch)
+    valid = batch["masks"][:, 0, :]
+    assert torch.isfinite(logits).all() and torch.isfinite(offsets).all() and torch.isfinite(feats).all()
+    assert _rel_err(logits.cpu()[valid], o_logits[valid]) < REL_TOL
+    assert _rel_err(offsets.cpu()[valid], o_offsets[valid]) < REL_TOL
+    assert _rel_err(feats.cpu()[valid], o_feats[valid]) < REL_TOL
+
+
+def test_weights_follow_load_state_dict_and_manual_refresh():
+    torch.manual_seed(5)
+    m = MMCTransformer(512, 2048, 384, 512, 1, 3, 3, 8).to(DEV).eval()
+    batch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in synth.make_batch([64], 1).items()}
+    _, l0, _, _, _, _ = m(batch)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    sd["cls_head.7.bias"] = sd["cls_head.7.bias"] + 3.0
+    m.load_state_dict(sd)
+    _, l1, _, _, _, _ = m(batch)
+    assert torch.allclose(l1, l0 + 3.0, atol=1e-4)
+    m.cls_head[7].bias.data += 2.0   # invisible to autograd versioning
+    m.refresh_weights()
+    _, l2, _, _, _, _ = m(batch)
+    assert torch.allclose(l2, l0 + 5.0, atol=1e-4)
+
+
+def test_extension_is_required_no_fallback(monkeypatch):
+    from repurpose_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", _lib.LIB_PATH.with_name("missing.so"))
+    with pytest.raises(_lib.RepurposeError):
+        _lib.load()
+
+
+# ------------------------------------------------------------------------------------ MHA (a10)
+@pytest.mark.parametrize("kind", ["self_nomask", "self_padding", "cross_band"])
+def test_multi_head_attention_module(kind):
+    torch.manual_seed(9)
+    mha = MultiHeadAttention(512, 8).to(DEV)
+    sd = {k: v.cpu() for k, v in mha.state_dict().items()}
+    B, Tq, Tk = 2, 150, 150
+    q = torch.randn(B, Tq, 512)
+    if kind == "cross_band":
+        Tk = 222
+        kv = torch.randn(B, Tk, 512)
+        i, j = torch.arange(Tq)[:, None], torch.arange(Tk)[None, :]
+        mask = ((i - j).abs() < 40).expand(B, Tq, Tk).contiguous()
+        k_in = v_in = kv
+    else:
+        k_in = v_in = q
+        mask = None
+        if kind == "self_padding":
+            mask = (torch.arange(Tk)[None, :] < torch.tensor([Tk, 50])[:, None])[:, None, :]
+    ref = mmct.mha_forward(sd, q, k_in, v_in, mask, 8)
+    got = mha(q.to(DEV), k_in.to(DEV), v_in.to(DEV), None if mask is None else mask.to(DEV))
+    assert got.shape == ref.shape
+    assert _rel_err(got, ref) < REL_TOL, f"{kind}: {_rel_err(got, ref)}"

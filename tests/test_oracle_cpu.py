@@ -1,0 +1,122 @@
+"""CPU suite, part 1: the oracle against the golden vectors produced by the reference itself
+(oracle/make_golden.py), and the oracle's own edge cases.  No GPU, no /root/reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mmct, synth
+from oracle.softnms import soft_nms_intervals_oracle
+from oracle.softnms_c import soft_nms_intervals_c
+from repurpose_b200.models.MMCTransformer import MMCTransformer
+
+
+@pytest.fixture(scope="module")
+def state_dict():
+    torch.manual_seed(0)
+    return {k: v.clone() for k, v in MMCTransformer(**synth.MODEL_CFG).state_dict().items()}
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    return ((a - b).abs().max() / a.abs().max().clamp_min(1e-6)).item()
+
+
+def test_state_dict_schema_matches_reference(state_dict):
+    # shapes documented in SURVEY.md §8b; exact equality with the reference's init is asserted by
+    # oracle/make_golden.py (tests/golden/PIN_REPORT.txt) where the reference is importable.
+    assert len(state_dict) == 219
+    assert state_dict["input_projection.weight"].shape == (512, 2944)
+    assert state_dict["positional_encoding.pe"].shape == (1, 5000, 512)
+    assert state_dict["multimodal_encoder.layers.15.self_attn.in_proj_weight"].shape == (1536, 512)
+    assert state_dict["multimodal_encoder.layers.0.linear1.weight"].shape == (2048, 512)
+    assert state_dict["cls_head.7.weight"].shape == (1, 256)
+    assert state_dict["reg_head.7.weight"].shape == (2, 256)
+    assert sum(v.numel() for k, v in state_dict.items() if not k.endswith(".pe")) == 52_608_771
+
+
+def test_oracle_forward_matches_reference_golden(state_dict, golden_dir):
+    g = np.load(golden_dir / "forward_T700.npz")
+    batch = synth.make_batch(g["lens"].tolist(), seed=int(g["batch_seed"]))
+    for tag, sd in (("init", state_dict), ("regbias", synth.bias_reg_head(state_dict))):
+        logits, offsets, feats = mmct.forward(sd, batch)
+        assert _rel(g[f"{tag}_logits"], logits) < 1e-5
+        assert _rel(g[f"{tag}_offsets"], offsets) < 1e-5
+        assert _rel(g[f"{tag}_feats_sub"], feats[:, :, ::16]) < 1e-5
+
+
+def test_oracle_inference_matches_reference_golden(state_dict, golden_dir):
+    g = np.load(golden_dir / "forward_T700.npz")
+    batch = synth.make_batch(g["lens"].tolist(), seed=int(g["batch_seed"]))
+    out = mmct.inference(synth.bias_reg_head(state_dict), batch, synth.TEST_CFG)
+    for i, r in enumerate(out):
+        assert np.array_equal(r["labels"].numpy(), g[f"inf{i}_labels"])
+        np.testing.assert_allclose(r["segments"].numpy(), g[f"inf{i}_segments"], atol=1e-4)
+        np.testing.assert_allclose(r["scores"].numpy(), g[f"inf{i}_scores"], atol=1e-6)
+        assert r["ncand"] == len(g[f"inf{i}_cand_scores"])
+
+
+def test_oracle_decode_matches_reference_golden(golden_dir):
+    g = np.load(golden_dir / "decode_cases.npz")
+    for ci in range(int(g["n_cases"])):
+        logits = torch.from_numpy(g[f"c{ci}_logits"])
+        offsets = torch.from_numpy(g[f"c{ci}_offsets"])
+        mask = (torch.arange(logits.numel()) < int(g[f"c{ci}_len"]))[None]
+        r = mmct.decode_single_video(mask, logits, offsets, synth.TEST_CFG)
+        assert np.array_equal(r["labels"].numpy(), g[f"c{ci}_labels"])
+        assert np.array_equal(r["scores"].numpy(), g[f"c{ci}_scores"])
+        assert np.array_equal(r["segments"].numpy(), g[f"c{ci}_segments"])
+
+
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+def test_oracle_softnms_matches_reference_golden(golden_dir, impl):
+    g = np.load(golden_dir / "softnms_cases.npz")
+    fn = soft_nms_intervals_oracle if impl == "numpy" else soft_nms_intervals_c
+    for name in g["names"]:
+        sigma, thresh, ms = g[f"{name}_params"]
+        keep, dsc = fn(g[f"{name}_scores"], g[f"{name}_segments"], sigma, thresh, int(ms),
+                       return_scores=True)
+        assert np.array_equal(keep, g[f"{name}_keep"]), name
+        np.testing.assert_allclose(dsc, g[f"{name}_dscores"], atol=1e-6, err_msg=name)
+
+
+def test_softnms_oracle_edge_cases():
+    # SURVEY.md App. B.4
+    e = soft_nms_intervals_oracle(np.zeros(0, np.float32), np.zeros((0, 2), np.float32))
+    assert e.shape == (0,)
+    one = soft_nms_intervals_oracle(np.array([0.9], np.float32), np.array([[0, 20]], np.float32),
+                                    thresh=0.01)
+    assert one.tolist() == [0]
+    low = soft_nms_intervals_oracle(np.array([0.005], np.float32), np.array([[0, 20]], np.float32),
+                                    thresh=0.01)
+    assert low.tolist() == []
+    s, seg = synth.make_candidates(30, 200, 0)
+    assert soft_nms_intervals_oracle(s, seg, max_seg_num=0).tolist() == []
+    # inputs are never mutated
+    s0, seg0 = s.copy(), seg.copy()
+    soft_nms_intervals_oracle(s, seg, max_seg_num=5)
+    assert np.array_equal(s, s0) and np.array_equal(seg, seg0)
+    # ties keep the lowest index first
+    tie = soft_nms_intervals_oracle(np.full(4, 0.8, np.float32),
+                                    np.array([[0, 20], [100, 120], [200, 220], [300, 320]], np.float32),
+                                    max_seg_num=4, thresh=0.01)
+    assert tie.tolist() == [0, 1, 2, 3]
+
+
+def test_max_seg_num_formula():
+    assert synth.max_seg_num(1801, 0.3) == 9
+    assert synth.max_seg_num(8192, 0.3) == 41
+    assert synth.max_seg_num(59, 0.3) == 0
+
+
+def test_positional_table_extends_reference_buffer(state_dict):
+    pe = mmct.positional_table(512, 5000)
+    assert torch.equal(pe, state_dict["positional_encoding.pe"][0])
+    assert torch.equal(mmct.positional_table(512, 8192)[:5000], pe)
+
+
+def test_calculate_tiou_restatement():
+    gt = [[0.0, 10.0], [20.0, 30.0]]
+    pred = [[0.0, 10.0], [21.0, 29.0], [50.0, 60.0]]
+    r = mmct.calculate_tiou(gt, pred, (0.5, 0.9))
+    assert r[0.5] == pytest.approx(2 / 3) and r[0.9] == pytest.approx(1 / 3)
+    assert mmct.calculate_tiou(gt, [], (0.5,))[0.5] == 0
