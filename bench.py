@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Benchmark of the Repurpose inference hot path (MMCTransformer forward + per-video decode +
+Soft-NMS) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one batch of 32 synthetic videos at T = 1801 feature steps (BASELINE.json configs[1]:
+Repurpose.yaml model, batch 32 at max_seq_len) per GPU through forward -> decode -> Soft-NMS, plus
+(N > 1) the single all-gather of the fixed-slot segment lists.  `value` = videos/s with inputs
+resident in HBM; `e2e` = the same through the public `MMCTransformer.inference_` call with pinned
+HOST inputs (H2D of the features and D2H of the segment slots inside the timed region).
+`--impl reference` times the reference algorithm's CPU path (the oracle port; the reference is pure
+Python/PyTorch and cannot travel to the GPU box) on the host cores.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BATCH = 32
+SEQ = 1801
+WORKLOAD = "Repurpose.yaml MMCTransformer (16L, d512, 8 heads), batch 32 x T=1801 full-length synthetic videos per GPU, fwd + decode + Soft-NMS"
+CPU_SAMPLE_B = 2
+
+
+def algorithmic_flops_per_video(T: int) -> float:
+    return 104_989_696.0 * T + 32_768.0 * T * T
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting",
+               0x10: "sync_boost", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self._nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": float(d["hbm_gbs"]), "tflops_burst": float(d["bf16_tflops"]),
+                "tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+def cpu_reference_run(steps: int, warmup: int):
+    """The reference algorithm on the host cores: oracle port of forward + decode + Soft-NMS on a
+    bounded sample (batch 2 at T=1801, BASELINE.json configs[0]) per step."""
+    from oracle import mmct, synth
+    from repurpose_b200.models.MMCTransformer import MMCTransformer
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    sd = {k: v.clone() for k, v in MMCTransformer(**synth.MODEL_CFG).state_dict().items()}
+    sd = synth.bias_reg_head(sd)
+    batch = synth.make_batch([SEQ] * CPU_SAMPLE_B, seed=0)
+    for _ in range(warmup):
+        mmct.inference(sd, batch, synth.TEST_CFG)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        mmct.inference(sd, batch, synth.TEST_CFG)
+    dt = time.perf_counter() - t0
+    return {"value": CPU_SAMPLE_B * steps / dt, "unit": "videos/s", "cores": torch.get_num_threads(),
+            "kind": "port",
+            "sample": f"{steps} step(s) of batch {CPU_SAMPLE_B} x T={SEQ} (oracle port of the reference, "
+                      f"fp32 torch CPU, {warmup} warm-up)"}, dt / max(1, steps) * 1e3
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 40))
+    base, ms = cpu_reference_run(steps, max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": "videos/s", "value": base["value"], "unit": "videos/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "cpu_sample": base["sample"]},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "videos/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from oracle import synth  # synthetic inputs only; the oracle compute is used for cpu_baseline below
+    from repurpose_b200 import _lib
+    from repurpose_b200.models.MMCTransformer import MMCTransformer
+    from repurpose_b200.scheduler import pack_slots
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    model = MMCTransformer(**synth.MODEL_CFG)
+    model.load_state_dict(synth.bias_reg_head({k: v.clone() for k, v in model.state_dict().items()}))
+    model = model.to(dev).eval()
+    cfg = synth.TEST_CFG
+    host = synth.make_batch([SEQ] * BATCH, seed=1000 + rank, pin=True)
+    devb = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
+    kcap = synth.max_seg_num(SEQ, cfg["max_seg_per_min"])
+    slot = 1 + 4 * kcap
+    gathered = torch.empty(world * BATCH, slot, dtype=torch.float32, device=dev)
+
+    def step_device():
+        r = model.inference_device(devb, cfg)
+        slots = pack_slots(r["segments"], r["scores"], r["labels"], r["counts"])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, slots)
+        return slots
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * BATCH * args.steps / (ms_total / 1e3)
+
+    # ---- per-kernel device times, measured in situ with CUDA events on the launch stream ----------
+    model.profile_begin()
+    prof_steps = min(args.steps, 5)
+    for _ in range(prof_steps):
+        step_device()
+    prof = model.profile_end()
+    peaks = measured_peaks()
+    M = BATCH * SEQ
+    kern = {}
+    tot_ms = sum(ms for ms, _ in prof.values())
+    for tag, (ms, n) in prof.items():
+        if n:
+            kern[tag] = {"ms_per_step": ms / prof_steps, "launches_per_step": n // prof_steps,
+                         "share": ms / tot_ms}
+    fm_ms, fm_n = prof["fmha"]
+    fmha_flops = 4.0 * BATCH * 8 * SEQ * SEQ * 64  # per launch: QK^T + PV over all heads
+    fm_tflops = fmha_flops / (fm_ms / fm_n * 1e-3) / 1e12
+    roofline = {"kernel": "fmha_fwd_kernel<0>", "bound": "tensor", "achieved": fm_tflops,
+                "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": fm_tflops / peaks["tflops_sustained"], "traffic": None,
+                "peak_source": peaks["source"] + ", sustained figure (kernel timed inside the step)",
+                "share_of_step": kern["fmha"]["share"]}
+    ln_ms, ln_n = prof["layernorm"]
+    # 31 of the 34 LayerNorm launches are mode 0 (read fp32 2048 B + write bf16 1024 B per row)
+    gemm_flops = {"gemm_in": 2.0 * M * 512 * 2944, "gemm_qkv": 2.0 * M * 1536 * 512, "gemm_out": 2.0 * M * 512 * 512,
+                  "gemm_ff1": 2.0 * M * 2048 * 512, "gemm_ff2": 2.0 * M * 512 * 2048}
+    for tag, fl in gemm_flops.items():
+        ms, n = prof[tag]
+        kern[tag]["tflops"] = fl / (ms / n * 1e-3) / 1e12
+    kern["fmha"]["tflops"] = fm_tflops
+    kern["layernorm"]["gbs_lower_bound"] = (M * 3072.0) / (ln_ms / ln_n * 1e-3) / 1e9
+    kern["layernorm"]["hbm_peak_gbs"] = peaks["hbm_gbs"]
+
+    # ---- end to end through the public API with HOST inputs ----------------------------------------
+    def step_e2e():
+        return model.inference_(host, cfg, to_host=True)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        res = step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    h2d = sum(v.numel() * v.element_size() for k, v in host.items()
+              if torch.is_tensor(v) and k in ("visual_feats", "audio_feats", "text_feats", "masks"))
+    e2e = {"value": world * BATCH * args.steps / (ms_e2e / 1e3), "unit": "videos/s",
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(BATCH * slot * 4),
+           "ms_per_step": ms_e2e / args.steps, "segments_last_step": int(sum(len(r["scores"]) for r in res))}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base, _ = cpu_reference_run(steps=2, warmup=1)
+
+    if rank == 0:
+        flops_step = BATCH * algorithmic_flops_per_video(SEQ)
+        line = {"metric": "videos/s", "value": value, "unit": "videos/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "seq_len": SEQ,
+                           "parallelism": f"per-video sharding x{world}, one all-gather of segment slots",
+                           "l2": "inputs (680 MB/step) and activations (650 MB) exceed the 126 MB L2",
+                           "weights": "random init (manual_seed 0), reg_head.7 scaled/biased so Soft-NMS sees candidates"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu_base,
+                "model_tflops": flops_step / (ms_step * 1e-3) / 1e12, "kernels": kern}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

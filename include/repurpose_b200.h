@@ -84,6 +84,17 @@ int32_t rp_forward(rp_handle* h, const float* vis, const float* aud, const float
                    const int32_t* lens, int32_t B, int32_t T, float* out_logits, float* out_offsets,
                    float* out_feats, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Optional in-situ profiler: between begin and end every kernel rp_forward launches is bracketed
+ * by CUDA events on the caller's stream; end() returns the summed device time (ms) and launch count
+ * per kernel class.  Arrays must hold RP_NUM_TAGS entries. */
+enum {
+  RP_TAG_CAST = 0, RP_TAG_GEMM_IN = 1, RP_TAG_LAYERNORM = 2, RP_TAG_GEMM_QKV = 3, RP_TAG_FMHA = 4,
+  RP_TAG_GEMM_OUT = 5, RP_TAG_GEMM_FF1 = 6, RP_TAG_GEMM_FF2 = 7, RP_TAG_GEMM_FMAP = 8,
+  RP_TAG_GEMM_HEAD = 9, RP_TAG_HEAD_OUT = 10, RP_NUM_TAGS = 11
+};
+int32_t rp_profile_begin(rp_handle* h);
+int32_t rp_profile_end(rp_handle* h, float* ms_by_tag, int32_t* launches_by_tag);
+
 /* ---- decode + Soft-NMS ------------------------------------------------------------------------ */
 /* logits [B,T], offsets [B,T,2], lens [B], max_seg [B] ->
  * segs [B,Kcap,2] f32, scores [B,Kcap] f32 (probability of the kept candidate), dscores [B,Kcap]

@@ -36,6 +36,8 @@ SIGNATURES = {
     "rp_workspace_bytes": (c_i64, [c_vp, c_i32, c_i32]),
     "rp_forward": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
                            c_i64, c_vp]),
+    "rp_profile_begin": (c_i32, [c_vp]),
+    "rp_profile_end": (c_i32, [c_vp, c_vp, c_vp]),
     "rp_decode_nms": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, C.POINTER(RpDecodeCfg), c_i32,
                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "rp_soft_nms": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_f32, c_i32, c_vp, c_vp,
@@ -50,6 +52,10 @@ SIGNATURES = {
                                 c_vp, c_vp, c_vp, c_vp]),
     "rp_head_out": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
 }
+
+
+PROFILE_TAGS = ("cast", "gemm_in", "layernorm", "gemm_qkv", "fmha", "gemm_out", "gemm_ff1", "gemm_ff2",
+                "gemm_fmap", "gemm_head", "head_out")
 
 
 class RepurposeError(RuntimeError):

@@ -46,6 +46,20 @@ struct rp_handle {
   float *r0_g, *r0_b, *b_r1, *b_r4, *w_r7, *b_r7;
   float* pe;
   int64_t pe_rows_loaded = 0;
+  // optional per-kernel-class CUDA-event profiler (rp_profile_begin / rp_profile_end)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_pool;
+  size_t prof_used = 0;
+  struct ProfRec { int tag; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_recs;
+  cudaEvent_t prof_event() {
+    if (prof_used == prof_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      prof_pool.push_back(e);
+    }
+    return prof_pool[prof_used++];
+  }
 };
 
 namespace {
@@ -210,6 +224,7 @@ void rp_destroy(rp_handle* h) {
   if (h == nullptr) return;
   for (auto& kv : h->slots)
     if (kv.second.dev) cudaFree(kv.second.dev);
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   delete h;
 }
 
@@ -294,70 +309,108 @@ int32_t rp_forward(rp_handle* h, const float* vis, const float* aud, const float
   const int D = c.d_model, F = c.d_ff, Hh = c.head_hidden, H = c.num_heads;
   const int Cin = c.vis_dim + c.aud_dim + c.text_dim;
   const float eps = 1e-5f;
-#define RUN(expr)            \
-  do {                       \
-    rc = (expr);             \
-    if (rc) return rc;       \
+#define RUN(tag, expr)                                         \
+  do {                                                         \
+    cudaEvent_t _e0 = nullptr, _e1 = nullptr;                  \
+    if (h->prof_on) {                                          \
+      _e0 = h->prof_event();                                   \
+      _e1 = h->prof_event();                                   \
+      cudaEventRecord(_e0, st);                                \
+    }                                                          \
+    rc = (expr);                                               \
+    if (rc) return rc;                                         \
+    if (h->prof_on) {                                          \
+      cudaEventRecord(_e1, st);                                \
+      h->prof_recs.push_back({(tag), _e0, _e1});               \
+    }                                                          \
   } while (0)
 
   // (1) concat + cast, input projection (fp32 out), input_norm + PE -> h, layers[0].norm1 -> u
   __nv_bfloat16* xcat = w.qkv;
-  RUN(launch_concat_cast(vis, aud, txt, c.vis_dim, c.aud_dim, c.text_dim, xcat, M, st));
-  RUN(launch_gemm(EPI_BIAS_F32, xcat, Cin, h->w_in, Cin, w.h, D, h->b_in, nullptr, 0, M, D, Cin, st));
+  RUN(RP_TAG_CAST, launch_concat_cast(vis, aud, txt, c.vis_dim, c.aud_dim, c.text_dim, xcat, M, st));
+  RUN(RP_TAG_GEMM_IN, launch_gemm(EPI_BIAS_F32, xcat, Cin, h->w_in, Cin, w.h, D, h->b_in, nullptr, 0, M, D, Cin, st));
   {
     LnArgs a{};
     a.x = w.h; a.M = M; a.T = T; a.eps = eps;
     a.g0 = h->in_g; a.b0 = h->in_b; a.pe = h->pe;
     a.g1 = h->layers[0].n1_g; a.b1 = h->layers[0].n1_b;
     a.out_f32 = w.h; a.y_bf16 = w.u;
-    RUN(launch_layernorm512(1, a, st));
+    RUN(RP_TAG_LAYERNORM, launch_layernorm512(1, a, st));
   }
   // (2) encoder layers (pre-LN): h += MHA(LN1(h)); h += FFN(LN2(h))
   for (int l = 0; l < c.num_layers; ++l) {
     const LayerW& L = h->layers[l];
-    RUN(launch_gemm(EPI_BIAS_BF16, w.u, D, L.w_qkv, D, w.qkv, 3 * D, L.b_qkv, nullptr, 0, M, 3 * D, D, st));
+    RUN(RP_TAG_GEMM_QKV, launch_gemm(EPI_BIAS_BF16, w.u, D, L.w_qkv, D, w.qkv, 3 * D, L.b_qkv, nullptr, 0, M, 3 * D, D, st));
     FmhaArgs fa{};
     fa.q = w.qkv; fa.k = w.qkv + D; fa.v = w.qkv + 2 * D; fa.o = w.attn;
     fa.ldq = fa.ldk = fa.ldv = 3 * D; fa.ldo = D;
     fa.bsq = fa.bsk = fa.bsv = int64_t(T) * 3 * D; fa.bso = int64_t(T) * D;
     fa.B = B; fa.H = H; fa.Tq = T; fa.Tk = T; fa.kv_lens = lens; fa.mask_mode = 0;
-    RUN(launch_fmha(fa, st));
-    RUN(launch_gemm(EPI_BIAS_RESID_F32, w.attn, D, L.w_out, D, w.h, D, L.b_out, w.h, D, M, D, D, st));
+    RUN(RP_TAG_FMHA, launch_fmha(fa, st));
+    RUN(RP_TAG_GEMM_OUT, launch_gemm(EPI_BIAS_RESID_F32, w.attn, D, L.w_out, D, w.h, D, L.b_out, w.h, D, M, D, D, st));
     {
       LnArgs a{};
       a.x = w.h; a.M = M; a.T = T; a.eps = eps; a.g0 = L.n2_g; a.b0 = L.n2_b; a.y_bf16 = w.u;
-      RUN(launch_layernorm512(0, a, st));
+      RUN(RP_TAG_LAYERNORM, launch_layernorm512(0, a, st));
     }
-    RUN(launch_gemm(EPI_BIAS_RELU_BF16, w.u, D, L.w_ff1, D, w.ffn, F, L.b_ff1, nullptr, 0, M, F, D, st));
-    RUN(launch_gemm(EPI_BIAS_RESID_F32, w.ffn, F, L.w_ff2, F, w.h, D, L.b_ff2, w.h, D, M, D, F, st));
+    RUN(RP_TAG_GEMM_FF1, launch_gemm(EPI_BIAS_RELU_BF16, w.u, D, L.w_ff1, D, w.ffn, F, L.b_ff1, nullptr, 0, M, F, D, st));
+    RUN(RP_TAG_GEMM_FF2, launch_gemm(EPI_BIAS_RESID_F32, w.ffn, F, L.w_ff2, F, w.h, D, L.b_ff2, w.h, D, M, D, F, st));
     {
       LnArgs a{};
       a.x = w.h; a.M = M; a.T = T; a.eps = eps; a.y_bf16 = w.u;
       if (l + 1 < c.num_layers) { a.g0 = h->layers[l + 1].n1_g; a.b0 = h->layers[l + 1].n1_b; }
       else { a.g0 = h->enc_g; a.b0 = h->enc_b; }  // encoder_norm feeds feature_map
-      RUN(launch_layernorm512(0, a, st));
+      RUN(RP_TAG_LAYERNORM, launch_layernorm512(0, a, st));
     }
   }
   // (3) feature_map: Linear -> LN -> ReLU = feats (returned); head LayerNorms
-  RUN(launch_gemm(EPI_BIAS_F32, w.u, D, h->w_fm, D, w.h, D, h->b_fm, nullptr, 0, M, D, D, st));
+  RUN(RP_TAG_GEMM_FMAP, launch_gemm(EPI_BIAS_F32, w.u, D, h->w_fm, D, w.h, D, h->b_fm, nullptr, 0, M, D, D, st));
   {
     LnArgs a{};
     a.x = w.h; a.M = M; a.T = T; a.eps = eps;
     a.g0 = h->fm_g; a.b0 = h->fm_b; a.g1 = h->c0_g; a.b1 = h->c0_b; a.g2 = h->r0_g; a.b2 = h->r0_b;
     a.out_f32 = out_feats; a.y_bf16 = w.u; a.y2_bf16 = w.attn;
-    RUN(launch_layernorm512(2, a, st));
+    RUN(RP_TAG_LAYERNORM, launch_layernorm512(2, a, st));
   }
   // (4) heads: 512->256 ReLU -> 256->256 ReLU -> {1, 2 (+ReLU)}
   __nv_bfloat16* a1c = w.qkv;
   __nv_bfloat16* a2c = a1c + int64_t(M) * Hh;
   __nv_bfloat16* a1r = a2c + int64_t(M) * Hh;
   __nv_bfloat16* a2r = a1r + int64_t(M) * Hh;
-  RUN(launch_gemm(EPI_BIAS_RELU_BF16, w.u, D, h->w_c1, D, a1c, Hh, h->b_c1, nullptr, 0, M, Hh, D, st));
-  RUN(launch_gemm(EPI_BIAS_RELU_BF16, a1c, Hh, h->w_c4, Hh, a2c, Hh, h->b_c4, nullptr, 0, M, Hh, Hh, st));
-  RUN(launch_gemm(EPI_BIAS_RELU_BF16, w.attn, D, h->w_r1, D, a1r, Hh, h->b_r1, nullptr, 0, M, Hh, D, st));
-  RUN(launch_gemm(EPI_BIAS_RELU_BF16, a1r, Hh, h->w_r4, Hh, a2r, Hh, h->b_r4, nullptr, 0, M, Hh, Hh, st));
-  RUN(launch_head_out(a2c, a2r, h->w_c7, h->b_c7, h->w_r7, h->b_r7, out_logits, out_offsets, M, st));
+  RUN(RP_TAG_GEMM_HEAD, launch_gemm(EPI_BIAS_RELU_BF16, w.u, D, h->w_c1, D, a1c, Hh, h->b_c1, nullptr, 0, M, Hh, D, st));
+  RUN(RP_TAG_GEMM_HEAD, launch_gemm(EPI_BIAS_RELU_BF16, a1c, Hh, h->w_c4, Hh, a2c, Hh, h->b_c4, nullptr, 0, M, Hh, Hh, st));
+  RUN(RP_TAG_GEMM_HEAD, launch_gemm(EPI_BIAS_RELU_BF16, w.attn, D, h->w_r1, D, a1r, Hh, h->b_r1, nullptr, 0, M, Hh, D, st));
+  RUN(RP_TAG_GEMM_HEAD, launch_gemm(EPI_BIAS_RELU_BF16, a1r, Hh, h->w_r4, Hh, a2r, Hh, h->b_r4, nullptr, 0, M, Hh, Hh, st));
+  RUN(RP_TAG_HEAD_OUT, launch_head_out(a2c, a2r, h->w_c7, h->b_c7, h->w_r7, h->b_r7, out_logits, out_offsets, M, st));
 #undef RUN
+  return RP_OK;
+}
+
+int32_t rp_profile_begin(rp_handle* h) {
+  RP_CHECK(h != nullptr, "rp_profile_begin: null handle");
+  h->prof_on = true;
+  h->prof_used = 0;
+  h->prof_recs.clear();
+  return RP_OK;
+}
+
+int32_t rp_profile_end(rp_handle* h, float* ms_by_tag, int32_t* launches_by_tag) {
+  RP_CHECK(h != nullptr && ms_by_tag != nullptr && launches_by_tag != nullptr,
+           "rp_profile_end: null argument");
+  h->prof_on = false;
+  for (int i = 0; i < RP_NUM_TAGS; ++i) {
+    ms_by_tag[i] = 0.f;
+    launches_by_tag[i] = 0;
+  }
+  for (const auto& r : h->prof_recs) {
+    RP_CUDA_CHECK(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    RP_CUDA_CHECK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ms_by_tag[r.tag] += ms;
+    launches_by_tag[r.tag] += 1;
+  }
+  h->prof_recs.clear();
+  h->prof_used = 0;
   return RP_OK;
 }
 

@@ -160,7 +160,7 @@ class MMCTransformer(nn.Module):
 
     @staticmethod
     def _as_f32(t, dev):
-        return t.to(device=dev, dtype=torch.float32).contiguous()
+        return t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
 
     # -------------------------------------------------------------------------------- forward
     def forward(self, batch):
@@ -175,7 +175,7 @@ class MMCTransformer(nn.Module):
         txt = self._as_f32(batch["text_feats"], dev)
         masks = batch["masks"]
         B, T = vis.shape[0], vis.shape[1]
-        lens = masks.to(dev).reshape(B, -1).ne(0).sum(dim=1, dtype=torch.int32).contiguous()
+        lens = masks.to(dev, non_blocking=True).reshape(B, -1).ne(0).sum(dim=1, dtype=torch.int32).contiguous()
         logits = torch.empty(B, T, 1, dtype=torch.float32, device=dev)
         offsets = torch.empty(B, T, 2, dtype=torch.float32, device=dev)
         feats = torch.empty(B, T, self._cfg["d_model"], dtype=torch.float32, device=dev)
@@ -186,6 +186,19 @@ class MMCTransformer(nn.Module):
                                          cur_stream()), "rp_forward")
         self._last_lens = lens
         return masks, logits, offsets, batch.get("labels"), batch.get("segments"), feats
+
+    def profile_begin(self):
+        """Bracket every kernel of the following forward passes with CUDA events (bench.py)."""
+        self._ensure_ready()
+        check(_lib.load().rp_profile_begin(self._handle), "rp_profile_begin")
+
+    def profile_end(self):
+        """-> {kernel class: (total device ms, launches)} since profile_begin(); synchronises."""
+        n = len(_lib.PROFILE_TAGS)
+        ms = (C.c_float * n)()
+        cnt = (C.c_int32 * n)()
+        check(_lib.load().rp_profile_end(self._handle, ms, cnt), "rp_profile_end")
+        return {t: (float(ms[i]), int(cnt[i])) for i, t in enumerate(_lib.PROFILE_TAGS)}
 
     def losses(self, masks, out_cls_logits, out_offsets, gt_cls_labels, gt_offsets, feats):
         raise NotImplementedError(
@@ -242,22 +255,38 @@ class MMCTransformer(nn.Module):
                 "labels": r["cand_labels"][0, :n].to(torch.int64)}
 
     @torch.no_grad()
-    def inference_(self, batch, inference_settings):
+    def inference_device(self, batch, inference_settings):
+        """forward + decode + Soft-NMS with no host synchronisation: returns the fixed-slot device
+        tensors of `_run_decode` (segments [B,K,2], scores, dscores, labels [B,K], counts [B])."""
+        _, logits, offsets, _, _, _ = self.forward(batch)
+        max_seg = [int(np.ceil((int(v) // 60) * inference_settings["max_seg_per_min"]))
+                   for v in batch["duration"]]
+        B, T = logits.shape[0], logits.shape[1]
+        return self._run_decode(logits.view(B, T), offsets, self._last_lens, max_seg,
+                                inference_settings)
+
+    @torch.no_grad()
+    def inference_(self, batch, inference_settings, to_host=False):
         """forward -> per-video decode -> Soft-NMS, all on the device (reference :231-275).
         Returns one dict per video: segments [K,2] f32 (feature-grid seconds), scores [K] f32
         (the candidate's probability, i.e. the reference's CUDA semantics),
-        labels [K] int64, video_id, duration — in Soft-NMS selection order."""
-        masks, logits, offsets, _, _, _ = self.forward(batch)
+        labels [K] int64, video_id, duration — in Soft-NMS selection order.
+        Tensors live on the model's device like the reference's; `to_host=True` (extension) returns
+        CPU tensors taken from one packed device->host copy, which is what callers that immediately
+        do `.tolist()` (inference.py:47, main.py:689) want."""
+        r = self.inference_device(batch, inference_settings)
         vid_idxs = batch["video_id"]
         vid_lens = batch["duration"]
-        max_seg = [int(np.ceil((int(v) // 60) * inference_settings["max_seg_per_min"]))
-                   for v in vid_lens]
-        B, T = logits.shape[0], logits.shape[1]
-        r = self._run_decode(logits.view(B, T), offsets, self._last_lens, max_seg,
-                             inference_settings)
+        results = []
+        if to_host:
+            from ..scheduler import pack_slots, unpack_slots
+            slots = pack_slots(r["segments"], r["scores"], r["labels"], r["counts"])
+            for o, vidx, vlen in zip(unpack_slots(slots), vid_idxs, vid_lens):
+                o["video_id"], o["duration"] = vidx, vlen
+                results.append(o)
+            return results
         counts = r["counts"].tolist()  # the single device->host sync of the whole batch
         labels64 = r["labels"].to(torch.int64)
-        results = []
         for i, (vidx, vlen) in enumerate(zip(vid_idxs, vid_lens)):
             k = counts[i]
             results.append({"segments": r["segments"][i, :k], "scores": r["scores"][i, :k],

@@ -1,0 +1,137 @@
+"""Batch scheduling for the inference path: whole videos are sharded across ranks (one process per
+GPU), each rank runs length-bucketed batches through `MMCTransformer.inference_device`, and the
+per-rank fixed-slot segment lists are combined with ONE all-gather (NCCL over NVLink on the GPU
+box; gloo in the CPU tests).  Nothing here has a counterpart in the reference — its inference is
+single-process, batch_size=1 (inference.py:29-31) and its DDP eval never gathers (main.py:696-716).
+SURVEY.md §8(e).
+
+Slot layout per video (float32, SLOT = 1 + 4*K values):
+    [count, (start, end, score, label) * K]      K = kcap, identical on every rank
+"""
+from __future__ import annotations
+
+from typing import Iterable, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def video_cost(T: int) -> float:
+    """Algorithmic FLOPs of one video of T valid steps."""
+    return 104_989_696.0 * T + 32_768.0 * T * T
+
+
+def shard_videos(lengths: Sequence[int], world_size: int) -> list[list[int]]:
+    """Greedy longest-processing-time assignment of whole videos to ranks; deterministic (ties by
+    video index).  Returns, per rank, the global video indices it owns (sorted by length, longest
+    first, so consecutive videos make low-padding batches)."""
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    load = [0.0] * world_size
+    shards: list[list[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        shards[r].append(i)
+        load[r] += video_cost(int(lengths[i]))
+    return shards
+
+
+def make_batches(indices: Sequence[int], batch_size: int) -> list[list[int]]:
+    """Chunk a (length-sorted) shard into batches of at most batch_size videos."""
+    return [list(indices[i:i + batch_size]) for i in range(0, len(indices), batch_size)]
+
+
+def pack_slots(segments, scores, labels, counts) -> torch.Tensor:
+    """[B,K,2], [B,K], [B,K] (int), [B] (int) -> [B, 1+4K] float32 slots (device op, no sync)."""
+    B, K = scores.shape
+    body = torch.cat([segments.float(), scores.float().unsqueeze(-1),
+                      labels.float().unsqueeze(-1)], dim=-1).reshape(B, 4 * K)
+    return torch.cat([counts.float().unsqueeze(-1), body], dim=1).contiguous()
+
+
+def unpack_slots(slots: torch.Tensor) -> list[dict]:
+    """Inverse of pack_slots on a host or device tensor -> list of dicts with tensors trimmed to count."""
+    slots = slots.cpu()
+    out = []
+    K = (slots.shape[1] - 1) // 4
+    for row in slots:
+        k = int(row[0].item())
+        body = row[1:].reshape(K, 4)[:k]
+        out.append({"segments": body[:, :2].clone(), "scores": body[:, 2].clone(),
+                    "labels": body[:, 3].to(torch.int64)})
+    return out
+
+
+def gather_slots(local_slots: torch.Tensor, owned: Sequence[int], shards: Sequence[Sequence[int]],
+                 group=None) -> torch.Tensor:
+    """One all-gather of equal-sized per-rank slot blocks; returns [n_videos, SLOT] in GLOBAL video
+    order on every rank.  `local_slots[i]` belongs to global video `owned[i]`; `shards` is the
+    deterministic shard map every rank computed from the same lengths."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    n_max = max(len(s) for s in shards)
+    slot = local_slots.shape[1]
+    block = torch.zeros(n_max, slot, dtype=torch.float32, device=local_slots.device)
+    block[:len(owned)] = local_slots
+    if world == 1:
+        gathered = block.unsqueeze(0)
+    else:
+        gathered = torch.empty(world, n_max, slot, dtype=torch.float32, device=local_slots.device)
+        dist.all_gather_into_tensor(gathered.view(world * n_max, slot), block, group=group)
+    n_total = sum(len(s) for s in shards)
+    out = torch.zeros(n_total, slot, dtype=torch.float32, device=local_slots.device)
+    for r, idxs in enumerate(shards):
+        if len(idxs):
+            out[torch.as_tensor(list(idxs), device=out.device)] = gathered[r, :len(idxs)]
+    return out
+
+
+def collate(videos: Sequence[dict], pin: bool = False) -> dict:
+    """Pad per-video host features to the batch maximum and build the left-aligned mask — the batch
+    dict contract of dataset/RepurposeClip.py:450-533 (preprocessing) / :997-1038 (collate_fn_test)."""
+    lens = [int(v["visual_feats"].shape[0]) for v in videos]
+    T = max(lens)
+    batch = {}
+    for key in ("visual_feats", "audio_feats", "text_feats"):
+        dim = videos[0][key].shape[1]
+        x = torch.zeros(len(videos), T, dim, dtype=torch.float32)
+        if pin:
+            x = x.pin_memory()
+        for i, v in enumerate(videos):
+            x[i, :lens[i]] = torch.as_tensor(v[key], dtype=torch.float32)
+        batch[key] = x
+    batch["masks"] = (torch.arange(T)[None, :] < torch.tensor(lens)[:, None])[:, None, :]
+    batch["labels"] = torch.zeros(len(videos), T)
+    batch["segments"] = torch.zeros(len(videos), T, 2)
+    batch["video_id"] = [v.get("video_id", i) for i, v in enumerate(videos)]
+    batch["duration"] = lens
+    return batch
+
+
+def run_sharded_inference(model, videos: Sequence[dict], test_cfg: dict, batch_size: int = 32,
+                          kcap: int | None = None, group=None) -> list[dict]:
+    """Shard `videos` (list of per-video host dicts with visual_feats/audio_feats/text_feats [T,C])
+    across the ranks of `group`, run inference on this rank's share, all-gather, and return one
+    result dict per video in the caller's order (identical on every rank)."""
+    import numpy as np
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    lengths = [int(v["visual_feats"].shape[0]) for v in videos]
+    if kcap is None:
+        kcap = max(1, max(int(np.ceil((l // 60) * test_cfg["max_seg_per_min"])) for l in lengths))
+    shards = shard_videos(lengths, world)
+    owned = shards[rank]
+    dev = model.device
+    local = torch.zeros(len(owned), 1 + 4 * kcap, dtype=torch.float32, device=dev)
+    pos = 0
+    for idxs in make_batches(owned, batch_size):
+        batch = collate([videos[i] for i in idxs])
+        r = model.inference_device(batch, test_cfg)
+        k = r["scores"].shape[1]
+        slots = pack_slots(r["segments"], r["scores"], r["labels"], r["counts"])
+        local[pos:pos + len(idxs), :1 + 4 * k] = slots
+        pos += len(idxs)
+    merged = gather_slots(local, owned, shards, group)
+    out = unpack_slots(merged)
+    for i, o in enumerate(out):
+        o["video_id"] = videos[i].get("video_id", i)
+        o["duration"] = lengths[i]
+    return out
