@@ -29,6 +29,9 @@ NVCC_FLAGS = [
 ]
 
 
+NVCC_FLAGS += os.environ.get("RP_EXTRA_NVCC_FLAGS", "").split()
+
+
 def _nvcc() -> str:
     cand = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
     return cand if Path(cand).exists() else "nvcc"

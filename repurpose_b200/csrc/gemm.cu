@@ -90,7 +90,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -98,18 +98,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n_blk = tile - m_blk * n_tiles;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
-          tma_load_2d(base + SMEM_A_OFF + stage * A_BYTES, &tmA, full_bar(stage), kb * BK,
-                      m_blk * BM);
-          tma_load_2d(base + SMEM_B_OFF + stage * B_BYTES, &tmB, full_bar(stage), kb * BK,
-                      n_blk * BN);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
+            tma_load_2d(base + SMEM_A_OFF + stage * A_BYTES, &tmA, full_bar(stage), kb * BK,
+                        m_blk * BM);
+            tma_load_2d(base + SMEM_B_OFF + stage * B_BYTES, &tmB, full_bar(stage), kb * BK,
+                        n_blk * BN);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the pipeline (converged control flow keeps descriptors in uniform
+    // registers); one elected lane issues the tcgen05 instructions.
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
       int stage = 0;
       uint32_t phase = 0;
@@ -123,18 +128,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_addr = base + SMEM_A_OFF + stage * A_BYTES;
-          const uint32_t b_addr = base + SMEM_B_OFF + stage * B_BYTES;
+          if (elect_one()) {
+            const uint64_t da = make_smem_desc_sw128(base + SMEM_A_OFF + stage * A_BYTES, 1024, 16);
+            const uint64_t db = make_smem_desc_sw128(base + SMEM_B_OFF + stage * B_BYTES, 1024, 16);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 1024, 16);
-            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 1024, 16);
-            mma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)  // +32 bytes along K per step = +2 in the address field
+              mma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_commit(empty_bar(stage));  // smem slot free once these MMAs retire
+            if (kb == k_blocks - 1) tc_commit(tfull_bar(buf));  // accumulator complete
           }
-          tc_commit(empty_bar(stage));  // smem slot free once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(tfull_bar(buf));  // accumulator complete
       }
     }
   } else {
@@ -149,12 +154,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n_blk = tile - m_blk * n_tiles;
       const int buf = it & 1;
       const uint32_t use_parity = (uint32_t(it) >> 1) & 1u;
-      mbar_wait(tfull_bar(buf), use_parity);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN);
       const int row0 = m_blk * BM + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < g.M;
+      // Residual rows are fetched one chunk ahead (and the first chunk before the accumulator is
+      // even ready), so the global-load latency is off the TMEM -> smem -> TMA-store critical path.
+      float4 rnext[8];
+      [[maybe_unused]] const float* rrow = nullptr;
+      if constexpr (EPI == EPI_BIAS_RESID_F32) {
+        rrow = g.resid + int64_t(row_ok ? row : 0) * g.ldr + n_blk * BN;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rnext[i] = row_ok ? reinterpret_cast<const float4*>(rrow)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      mbar_wait(tfull_bar(buf), use_parity);
+      tc_fence_after();
 
 #pragma unroll 1
       for (int c = 0; c < BN / CPC; ++c, ++chunk_ctr) {
@@ -180,17 +195,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if constexpr (EPI == EPI_BIAS_RESID_F32) {
-            if (row_ok) {
-              const float4* rp4 =
-                  reinterpret_cast<const float4*>(g.resid + int64_t(row) * g.ldr + col0);
+            float4 rcur[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 r4 = rp4[i];
-                v[4 * i + 0] = __float_as_uint(__uint_as_float(v[4 * i + 0]) + r4.x);
-                v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + r4.y);
-                v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + r4.z);
-                v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + r4.w);
-              }
+            for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+            if (c + 1 < BN / CPC && row_ok) {
+              const float4* rp4 = reinterpret_cast<const float4*>(rrow + (c + 1) * CPC);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) rnext[i] = rp4[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[4 * i + 0] = __float_as_uint(__uint_as_float(v[4 * i + 0]) + rcur[i].x);
+              v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + rcur[i].y);
+              v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + rcur[i].z);
+              v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + rcur[i].w);
             }
           }
           if constexpr (EPI == EPI_BIAS_RELU_BF16) {
