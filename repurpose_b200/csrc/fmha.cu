@@ -40,19 +40,29 @@ namespace {
 constexpr int QT = 128;
 constexpr int KT = 128;
 constexpr int HD = 64;
-constexpr int KV_STAGES = 3;
 constexpr int TILE_BYTES = QT * HD * 2;  // 16 KB (Q, K and V tiles are all 128 x 64 bf16)
-constexpr int SMEM_Q_OFF = 0;
-constexpr int SMEM_K_OFF = 2 * TILE_BYTES;
-constexpr int SMEM_V_OFF = SMEM_K_OFF + KV_STAGES * TILE_BYTES;
-constexpr int SMEM_X_OFF = SMEM_V_OFF + KV_STAGES * TILE_BYTES;   // 131072: row-stat exchange, 2x2x2x128 f32
-constexpr int SMEM_BAR_OFF = SMEM_X_OFF + 2 * 2 * 2 * 128 * 4;    // +4 KB
-constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 256 + 1024;
-constexpr int NUM_THREADS = 576;
-constexpr int TMEM_COLS = 512;
-constexpr int TM_S = 0;     // + q*128
-constexpr int TM_P = 256;   // + q*64
-constexpr int TM_O = 384;   // + q*64
+
+// NQ = query tiles per CTA.  NQ = 2: one CTA per SM (512 TMEM columns, 18 warps).  NQ = 1: two
+// independent CTAs per SM (256 TMEM columns and 10 warps each) whose softmax / MMA phases drift
+// against each other instead of running in lockstep.
+template <int NQ>
+struct Cfg {
+  static constexpr int KV_STAGES = NQ == 2 ? 3 : 2;
+  static constexpr int SMEM_Q_OFF = 0;
+  static constexpr int SMEM_K_OFF = NQ * TILE_BYTES;
+  static constexpr int SMEM_V_OFF = SMEM_K_OFF + KV_STAGES * TILE_BYTES;
+  static constexpr int SMEM_X_OFF = SMEM_V_OFF + KV_STAGES * TILE_BYTES;  // row-stat exchange [2][NQ][2][128] f32
+  static constexpr int SMEM_BAR_OFF = SMEM_X_OFF + 2 * NQ * 2 * 128 * 4;
+  static constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 256 + 1024;
+  static constexpr int PRODUCER_WARP = 8 * NQ;
+  static constexpr int MMA_WARP = 8 * NQ + 1;
+  static constexpr int NUM_THREADS = (8 * NQ + 2) * 32;
+  static constexpr int MIN_CTAS = NQ == 2 ? 1 : 2;
+  static constexpr int TMEM_COLS = 256 * NQ;
+  static constexpr int TM_S = 0;         // + q*128
+  static constexpr int TM_P = 128 * NQ;  // + q*64
+  static constexpr int TM_O = 192 * NQ;  // + q*64
+};
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units; stale max keeps p <= 2^8
 constexpr float MASK_FILL_LOG2 = -1.0e9f * 1.4426950408889634f;
 
@@ -119,11 +129,16 @@ __device__ __forceinline__ void exp2_emulated2(unsigned long long x2, float& p0,
   p1 = __uint_as_float((__float_as_uint(t1) << 23) + __float_as_uint(q1));
 }
 
-template <int MASK_MODE, int EMU_PAIRS, int PINGPONG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int MASK_MODE, int EMU_PAIRS, int NQ>
+__global__ void __launch_bounds__(Cfg<NQ>::NUM_THREADS, Cfg<NQ>::MIN_CTAS)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                 const FmhaParams p) {
+  using C = Cfg<NQ>;
+  constexpr int KV_STAGES = C::KV_STAGES;
+  constexpr int SMEM_Q_OFF = C::SMEM_Q_OFF, SMEM_K_OFF = C::SMEM_K_OFF, SMEM_V_OFF = C::SMEM_V_OFF;
+  constexpr int SMEM_X_OFF = C::SMEM_X_OFF, SMEM_BAR_OFF = C::SMEM_BAR_OFF;
+  constexpr int TM_S = C::TM_S, TM_P = C::TM_P, TM_O = C::TM_O, TMEM_COLS = C::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -147,8 +162,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int head = blockIdx.y;
   const int b = blockIdx.z;
 
-  const int q_start0 = pair * (2 * QT);
-  const bool q1_active = (q_start0 + QT) < p.Tq;
+  const int q_start0 = pair * (NQ * QT);
+  const bool q1_active = NQ == 2 && (q_start0 + QT) < p.Tq;
   const int nq = q1_active ? 2 : 1;
   int kv_len = p.Tk;
   if (MASK_MODE == 0 && p.kv_lens != nullptr) {
@@ -157,7 +172,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   const int n_kv = (kv_len + KT - 1) / KT;
 
-  if (warp == 16 && lane == 0) {
+  if (warp == C::PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -177,13 +192,13 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     fence_mbar_init();
   }
-  if (warp == 17) tmem_alloc<TMEM_COLS>(base + SMEM_BAR_OFF + 176);
+  if (warp == C::MMA_WARP) tmem_alloc<TMEM_COLS>(base + SMEM_BAR_OFF + 176);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 16) {
+  if (warp == C::PRODUCER_WARP) {
     // ---------------------------------------------------------------- TMA producer
     // (whole warp walks the loop; one elected lane issues)
     if (n_kv > 0) {
@@ -215,7 +230,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (++st == KV_STAGES) { st = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 17) {
+  } else if (warp == C::MMA_WARP) {
     // ---------------------------------------------------------------- MMA issuer
     // Converged warp, one elected lane per issue group: descriptors stay in uniform registers and
     // each tcgen05.mma costs a handful of issue cycles (a divergent single-thread loop costs ~100).
@@ -284,7 +299,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-  } else if (warp < 16) {
+  } else if (warp < 8 * NQ) {
     // ---------------------------------------------------------------- softmax warps
     // 16 warps: (query tile q, column half h, lane quarter wl).  Thread (q,h,wl,lane) owns row
     // wl*32+lane of S_q and the 64 score columns [64h, 64h+64); the two threads of a row exchange
@@ -312,12 +327,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mrow = p.mask + int64_t(b) * p.mask_b_stride + int64_t(qrow) * p.mask_q_stride;
       }
 
-      // Ping-pong token between the two query tiles: their exp phases (the MUFU-bound part)
-      // strictly alternate, so the TMEM-load / row-max / barrier phases of one tile hide under the
-      // exp phase of the other.  Named barriers 11 (tile 0's turn) and 12 (tile 1's turn), 512 threads.
-      const bool pingpong = (nq == 2) && (PINGPONG != 0);
       const bool opaque_true = (p.H != 0);  // always true; unknown to the compiler
-      if (pingpong && q == 1) named_bar_arrive(11, 512);
       for (int j = 0; j < n_kv; ++j) {
         if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 0);
         mbar_wait(s_full(q), uint32_t(j) & 1u);
@@ -353,7 +363,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (c + 2 < 64) mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])));
         }
         const float mxh = fmaxf(mx0, mx1);
-        float* xrow = xch + (((j & 1) * 2 + q) * 2) * 128 + row_in_tile;
+        float* xrow = xch + (((j & 1) * NQ + q) * 2) * 128 + row_in_tile;
         xrow[h * 128] = mxh;
         named_bar_sync(pair_bar, 64);
         const float m_new = fmaxf(m, fmaxf(mxh, xrow[(h ^ 1) * 128]));
@@ -388,9 +398,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 3);
 
-        if (pingpong) {  // wait for my tile's turn on the MUFU
-          if (q == 0) named_bar_sync(11, 512); else named_bar_sync(12, 512);
-        }
         if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 4);
         // Block A: every exp2 of my 64 scores, results overwrite the score registers.  All 64
         // evaluations are independent, so the MUFU queue stays full; the consumers (row sum, bf16
@@ -432,9 +439,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           lsum2 = add2(lsum2, add2(sumA, sumB));
         }
         if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 5);
-        if (pingpong && !(q == 1 && j == n_kv - 1)) {  // hand the MUFU to the other tile
-          if (q == 0) named_bar_arrive(12, 512); else named_bar_arrive(11, 512);
-        }
         if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 6);
         tmem_st_wait();
         tc_fence_before();
@@ -449,7 +453,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float l0, l1;
         unpack2(lsum2, l0, l1);
         const float lh = l0 + l1;
-        float* lrow = xch + ((n_kv & 1) * 2 + q) * 2 * 128 + row_in_tile;  // buffer not used by the last tile
+        float* lrow = xch + ((n_kv & 1) * NQ + q) * 2 * 128 + row_in_tile;  // buffer not used by the last tile
         lrow[h * 128] = lh;
         mbar_wait(pv_done(q), uint32_t(n_kv - 1) & 1u);
         tc_fence_after();
@@ -485,22 +489,24 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 17) {
+  if (warp == C::MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
-template <int MASK_MODE, int EMU_PAIRS, int PINGPONG>
+template <int MASK_MODE, int EMU_PAIRS, int NQ>
 int launch_variant(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                   const CUtensorMap& tmO, const FmhaParams& p, dim3 grid, cudaStream_t stream) {
+                   const CUtensorMap& tmO, const FmhaParams& p, cudaStream_t stream) {
+  using C = Cfg<NQ>;
   static bool configured = false;
   if (!configured) {
-    RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, PINGPONG>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));
     configured = true;
   }
-  fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, PINGPONG><<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(tmQ, tmK, tmV, tmO, p);
+  dim3 grid((p.Tq + NQ * QT - 1) / (NQ * QT), p.H, p.B);
+  fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ><<<grid, C::NUM_THREADS, C::SMEM_TOTAL, stream>>>(tmQ, tmK, tmV, tmO, p);
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;
@@ -547,18 +553,16 @@ int launch_fmha(const FmhaArgs& a, cudaStream_t stream) {
   if ((rc = make_tmap_3d(&tmO, bf, a.o, cols, a.Tq, a.B, a.ldo * 2, a.bso * 2, HD, QT))) return rc;
 
   FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride};
-  dim3 grid((a.Tq + 2 * QT - 1) / (2 * QT), a.H, a.B);
-  if (a.mask_mode == 1) return launch_variant<1, 1, 1>(tmQ, tmK, tmV, tmO, p, grid, stream);
-  static const bool pp = getenv("RP_FMHA_PINGPONG") ? atoi(getenv("RP_FMHA_PINGPONG")) != 0 : false;
-  switch (emu_pairs_setting() * 2 + (pp ? 1 : 0)) {
-    case 0: return launch_variant<0, 0, 0>(tmQ, tmK, tmV, tmO, p, grid, stream);
-    case 1: return launch_variant<0, 0, 1>(tmQ, tmK, tmV, tmO, p, grid, stream);
-    case 2: return launch_variant<0, 1, 0>(tmQ, tmK, tmV, tmO, p, grid, stream);
-    case 4: return launch_variant<0, 2, 0>(tmQ, tmK, tmV, tmO, p, grid, stream);
-    case 5: return launch_variant<0, 2, 1>(tmQ, tmK, tmV, tmO, p, grid, stream);
-    case 6: return launch_variant<0, 3, 0>(tmQ, tmK, tmV, tmO, p, grid, stream);
-    case 7: return launch_variant<0, 3, 1>(tmQ, tmK, tmV, tmO, p, grid, stream);
-    default: return launch_variant<0, 1, 1>(tmQ, tmK, tmV, tmO, p, grid, stream);
+  // RP_FMHA_NQ: query tiles per CTA (2 = one big CTA per SM, 1 = two independent CTAs per SM)
+  static const int nq_cfg = getenv("RP_FMHA_NQ") ? atoi(getenv("RP_FMHA_NQ")) : 1;
+  if (a.mask_mode == 1) return launch_variant<1, 1, 1>(tmQ, tmK, tmV, tmO, p, stream);
+  switch (emu_pairs_setting() * 2 + (nq_cfg == 2 ? 1 : 0)) {
+    case 0: return launch_variant<0, 0, 1>(tmQ, tmK, tmV, tmO, p, stream);
+    case 1: return launch_variant<0, 0, 2>(tmQ, tmK, tmV, tmO, p, stream);
+    case 3: return launch_variant<0, 1, 2>(tmQ, tmK, tmV, tmO, p, stream);
+    case 4: return launch_variant<0, 2, 1>(tmQ, tmK, tmV, tmO, p, stream);
+    case 5: return launch_variant<0, 2, 2>(tmQ, tmK, tmV, tmO, p, stream);
+    default: return launch_variant<0, 1, 1>(tmQ, tmK, tmV, tmO, p, stream);
   }
 }
 

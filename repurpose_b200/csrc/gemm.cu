@@ -1,10 +1,17 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T (+ epilogue).
 //
-//   warp 0      : TMA producer   (A 128x64 and W 256x64 bf16 tiles, SWIZZLE_128B, 4-stage ring)
-//   warp 1      : tcgen05.mma issuer (one thread; UMMA 128x256x16, fp32 accumulators in TMEM,
-//                 two 256-column accumulator buffers so the epilogue of tile i overlaps the
-//                 main loop of tile i+1); also owns TMEM alloc/dealloc
-//   warps 2..5  : epilogue: tcgen05.ld -> bias / ReLU / residual -> swizzled smem slab -> TMA store
+//   warp 0      : TMA producer   (A 128x64 and W 256x64 bf16 tiles, SWIZZLE_128B, multi-stage ring)
+//   warp 1      : tcgen05.mma issuer (converged warp, one elected lane; UMMA 128x256x16, fp32
+//                 accumulators in TMEM, two 256-column accumulator buffers so the epilogue of tile i
+//                 overlaps the main loop of tile i+1); also owns TMEM alloc/dealloc
+//   warps 2..5  : epilogue: tcgen05.ld -> bias / ReLU / residual -> swizzled smem slab -> TMA store.
+//                 Each warp owns 32 accumulator rows and a private ring of 4 KB slabs.
+//
+// Residual epilogue (h += acc + bias, in place): the residual chunk is TMA-LOADED into the slab a few
+// chunks ahead (mbarrier per slab), updated in shared memory, and TMA-stored from the same slab.
+// Both directions are therefore full-line bulk copies with several in flight per warp, which is what
+// a ~1.5 us DRAM round trip needs; a register prefetch of depth one left the warps stalled on the
+// loads (profiles/r01_notes.md).
 //
 // This kernel implements the Linear layers of the reference hot path
 // (models/MMCTransformer.py:121 input_projection, :135-138 in_proj/out_proj/linear1/linear2 inside
@@ -20,43 +27,57 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;                // 16 KB
-constexpr int B_BYTES = BN * BK * 2;                // 32 KB
-constexpr int SLAB_BYTES = 32 * 128;                // 32 rows x 128 B, one TMA-store box
-constexpr int SMEM_A_OFF = 0;
-constexpr int SMEM_B_OFF = STAGES * A_BYTES;        // 65536
-constexpr int SMEM_D_OFF = SMEM_B_OFF + STAGES * B_BYTES;  // 196608
-constexpr int SMEM_BAR_OFF = SMEM_D_OFF + 4 * 2 * SLAB_BYTES;  // 229376
-constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 128 + 1024;  // barriers + alignment slack
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_BYTES = BN * BK * 2;   // 32 KB
+constexpr int SLAB_BYTES = 32 * 128;   // 32 rows x 128 B: one TMA box of the output / residual
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
+constexpr int MAX_SLABS = 5;
+
+// Shared-memory budget per epilogue kind: the residual epilogue trades one operand stage for a
+// deeper slab ring (loads and stores both live there).
+template <int EPI>
+struct Cfg {
+  static constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32);
+  static constexpr int STAGES = RESID ? 3 : 4;
+  static constexpr int SLABS = RESID ? 5 : 2;          // per epilogue warp
+  static constexpr int LOOKAHEAD = 3;                  // residual chunks in flight per warp
+  static constexpr int SMEM_A_OFF = 0;
+  static constexpr int SMEM_B_OFF = STAGES * A_BYTES;
+  static constexpr int SMEM_D_OFF = SMEM_B_OFF + STAGES * B_BYTES;
+  static constexpr int SMEM_BAR_OFF = SMEM_D_OFF + 4 * SLABS * SLAB_BYTES;  // 229376 either way
+  static constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 512 + 1024;  // barriers + alignment slack
+};
 
 struct GemmArgs {
   int M, N, K;
   const float* bias;
-  const float* resid;
-  int64_t ldr;
 };
 
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmD, const GemmArgs g) {
+                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
+                 const GemmArgs g) {
+  using C = Cfg<EPI>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int SLABS = C::SLABS;
   constexpr bool OUT_F32 = (EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_RESID_F32);
   constexpr int CPC = OUT_F32 ? 32 : 64;  // output columns per 128-byte slab row
+  constexpr int CHUNKS = BN / CPC;        // slab-sized chunks per tile and warp
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
 
-  const uint32_t bar_base = base + SMEM_BAR_OFF;
+  const uint32_t bar_base = base + C::SMEM_BAR_OFF;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
   auto tfull_bar = [&](int b) { return bar_base + 64u + 8u * b; };
   auto tempty_bar = [&](int b) { return bar_base + 80u + 8u * b; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR_OFF + 96);
+  auto resid_bar = [&](int ew, int s) { return bar_base + 128u + 8u * (ew * MAX_SLABS + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::SMEM_BAR_OFF + 96);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -70,6 +91,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
+    if (C::RESID) tma_prefetch_desc(&tmR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -78,10 +100,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), 4);
     }
+    for (int i = 0; i < 4 * MAX_SLABS; ++i) mbar_init(bar_base + 128u + 8u * i, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc<TMEM_COLS>(base + SMEM_BAR_OFF + 96);
+    tmem_alloc<TMEM_COLS>(base + C::SMEM_BAR_OFF + 96);
   }
   tc_fence_before();
   __syncthreads();
@@ -90,65 +113,81 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles;
-        const int n_blk = tile - m_blk * n_tiles;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          if (elect_one()) {
-            mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
-            tma_load_2d(base + SMEM_A_OFF + stage * A_BYTES, &tmA, full_bar(stage), kb * BK,
-                        m_blk * BM);
-            tma_load_2d(base + SMEM_B_OFF + stage * B_BYTES, &tmB, full_bar(stage), kb * BK,
-                        n_blk * BN);
-          }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    // (the whole warp walks the loop; one elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles;
+      const int n_blk = tile - m_blk * n_tiles;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
+          tma_load_2d(base + C::SMEM_A_OFF + stage * A_BYTES, &tmA, full_bar(stage), kb * BK,
+                      m_blk * BM);
+          tma_load_2d(base + C::SMEM_B_OFF + stage * B_BYTES, &tmB, full_bar(stage), kb * BK,
+                      n_blk * BN);
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    // The whole warp walks the pipeline (converged control flow keeps descriptors in uniform
-    // registers); one elected lane issues the tcgen05 instructions.
-    {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t use_parity = (uint32_t(it) >> 1) & 1u;
-        mbar_wait(tempty_bar(buf), use_parity ^ 1u);
+    // Converged control flow keeps the descriptors in uniform registers; a divergent
+    // single-thread loop costs ~100 cycles per tcgen05.mma issue.
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use_parity = (uint32_t(it) >> 1) & 1u;
+      mbar_wait(tempty_bar(buf), use_parity ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(buf * BN);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(buf * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t da = make_smem_desc_sw128(base + SMEM_A_OFF + stage * A_BYTES, 1024, 16);
-            const uint64_t db = make_smem_desc_sw128(base + SMEM_B_OFF + stage * B_BYTES, 1024, 16);
+        if (elect_one()) {
+          const uint64_t da = make_smem_desc_sw128(base + C::SMEM_A_OFF + stage * A_BYTES, 1024, 16);
+          const uint64_t db = make_smem_desc_sw128(base + C::SMEM_B_OFF + stage * B_BYTES, 1024, 16);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)  // +32 bytes along K per step = +2 in the address field
-              mma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-            tc_commit(empty_bar(stage));  // smem slot free once these MMAs retire
-            if (kb == k_blocks - 1) tc_commit(tfull_bar(buf));  // accumulator complete
-          }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          for (int k = 0; k < BK / 16; ++k)  // +32 bytes along K per step = +2 in the address field
+            mma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(empty_bar(stage));  // smem slot free once these MMAs retire
+          if (kb == k_blocks - 1) tc_commit(tfull_bar(buf));  // accumulator complete
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int ew = warp - 2; // staging slot
-    const uint32_t slab0 = base + SMEM_D_OFF + ew * 2 * SLAB_BYTES;
+    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    const int ew = warp - 2;  // slab ring / barrier set of this warp
+    const uint32_t slab0 = base + C::SMEM_D_OFF + ew * SLABS * SLAB_BYTES;
+    const int my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int total_chunks = my_tiles * CHUNKS;
+
+    // residual chunk gc (global per-warp chunk counter) -> issue its TMA load into slab gc % SLABS
+    auto issue_resid_load = [&](int gc) {
+      const int tile = blockIdx.x + (gc / CHUNKS) * gridDim.x;
+      const int c = gc % CHUNKS;
+      const int m_blk = tile / n_tiles;
+      const int n_blk = tile - m_blk * n_tiles;
+      const int s = gc % SLABS;
+      mbar_expect_tx(resid_bar(ew, s), SLAB_BYTES);
+      tma_load_2d(slab0 + s * SLAB_BYTES, &tmR, resid_bar(ew, s), n_blk * BN + c * CPC,
+                  m_blk * BM + q * 32);
+    };
+    if constexpr (C::RESID) {
+      if (lane == 0)
+        for (int gc = 0; gc < C::LOOKAHEAD && gc < total_chunks; ++gc) issue_resid_load(gc);
+    }
+
     int it = 0;
-    int chunk_ctr = 0;
+    int gc = 0;  // chunks processed so far by this warp
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles;
       const int n_blk = tile - m_blk * n_tiles;
@@ -156,27 +195,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t use_parity = (uint32_t(it) >> 1) & 1u;
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN);
       const int row0 = m_blk * BM + q * 32;
-      const int row = row0 + lane;
-      const bool row_ok = row < g.M;
-      // Residual rows are fetched one chunk ahead (and the first chunk before the accumulator is
-      // even ready), so the global-load latency is off the TMEM -> smem -> TMA-store critical path.
-      float4 rnext[8];
-      [[maybe_unused]] const float* rrow = nullptr;
-      if constexpr (EPI == EPI_BIAS_RESID_F32) {
-        rrow = g.resid + int64_t(row_ok ? row : 0) * g.ldr + n_blk * BN;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          rnext[i] = row_ok ? reinterpret_cast<const float4*>(rrow)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
       mbar_wait(tfull_bar(buf), use_parity);
       tc_fence_after();
 
 #pragma unroll 1
-      for (int c = 0; c < BN / CPC; ++c, ++chunk_ctr) {
-        const uint32_t slab = slab0 + (chunk_ctr & 1) * SLAB_BYTES;
-        // the TMA store that last read this slab (two chunks ago) must have drained it
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
+      for (int c = 0; c < CHUNKS; ++c, ++gc) {
+        const int s = gc % SLABS;
+        const uint32_t slab = slab0 + s * SLAB_BYTES;
+        if constexpr (C::RESID) {
+          // keep LOOKAHEAD residual loads in flight: chunk gc+LOOKAHEAD lands in the slab chunk gc-2
+          // was stored from, so all but the most recent store must have finished reading smem
+          if (lane == 0 && gc + C::LOOKAHEAD < total_chunks) {
+            tma_store_wait_read<1>();
+            issue_resid_load(gc + C::LOOKAHEAD);
+          }
+          mbar_wait(resid_bar(ew, s), uint32_t(gc / SLABS) & 1u);
+        } else {
+          // the TMA store that last read this slab (SLABS chunks ago) must have drained it
+          if (lane == 0) tma_store_wait_read<SLABS - 1>();
+          __syncwarp();
+        }
 #pragma unroll
         for (int half = 0; half < CPC / 32; ++half) {
           uint32_t v[32];
@@ -194,23 +232,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + b4.w);
             }
           }
-          if constexpr (EPI == EPI_BIAS_RESID_F32) {
-            float4 rcur[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
-            if (c + 1 < BN / CPC && row_ok) {
-              const float4* rp4 = reinterpret_cast<const float4*>(rrow + (c + 1) * CPC);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) rnext[i] = rp4[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[4 * i + 0] = __float_as_uint(__uint_as_float(v[4 * i + 0]) + rcur[i].x);
-              v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + rcur[i].y);
-              v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + rcur[i].z);
-              v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + rcur[i].w);
-            }
-          }
           if constexpr (EPI == EPI_BIAS_RELU_BF16) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
@@ -221,6 +242,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const uint32_t dst = row_addr + (uint32_t(i ^ (lane & 7)) << 4);
+              if constexpr (C::RESID) {  // slab currently holds the residual: update in place
+                uint32_t r0, r1, r2, r3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                             : "r"(dst)
+                             : "memory");
+                v[4 * i + 0] = __float_as_uint(__uint_as_float(v[4 * i + 0]) + __uint_as_float(r0));
+                v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + __uint_as_float(r1));
+                v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + __uint_as_float(r2));
+                v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + __uint_as_float(r3));
+              }
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[4 * i]),
                            "r"(v[4 * i + 1]), "r"(v[4 * i + 2]), "r"(v[4 * i + 3])
                            : "memory");
@@ -265,14 +297,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int EPI>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
-               const GemmArgs& g, int grid, cudaStream_t stream) {
+               const CUtensorMap& tmR, const GemmArgs& g, int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     RP_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg<EPI>::SMEM_TOTAL));
     configured = true;
   }
-  gemm_bf16_kernel<EPI><<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(tmA, tmB, tmD, g);
+  gemm_bf16_kernel<EPI><<<grid, NUM_THREADS, Cfg<EPI>::SMEM_TOTAL, stream>>>(tmA, tmB, tmD, tmR, g);
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;
@@ -296,7 +329,7 @@ int launch_gemm(int epilogue, const void* A, int64_t lda, const void* W, int64_t
             reinterpret_cast<uintptr_t>(resid)) % 16 == 0,
            "gemm: pointers must be 16-byte aligned");
 
-  CUtensorMap tmA, tmB, tmD;
+  CUtensorMap tmA, tmB, tmD, tmR;
   int rc;
   if ((rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, A, K, M, lda * 2, BK, BM))) return rc;
   if ((rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, W, K, N, ldw * 2, BK, BN))) return rc;
@@ -305,17 +338,21 @@ int launch_gemm(int epilogue, const void* A, int64_t lda, const void* W, int64_t
   else
     rc = make_tmap_2d(&tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, D, N, M, ldd * 2, 64, 32);
   if (rc) return rc;
+  tmR = tmD;
+  if (epilogue == EPI_BIAS_RESID_F32 &&
+      (rc = make_tmap_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, resid, N, M, ldr * 4, 32, 32)))
+    return rc;
 
-  GemmArgs g{M, N, K, bias, resid, ldr};
+  GemmArgs g{M, N, K, bias};
   const int total_tiles = ((M + BM - 1) / BM) * (N / BN);
   const int sms = num_sms();
   if (sms <= 0) return RP_ERR_NO_DEVICE;
   const int grid = total_tiles < sms ? total_tiles : sms;
   switch (epilogue) {
-    case EPI_BIAS_BF16: return launch_one<EPI_BIAS_BF16>(tmA, tmB, tmD, g, grid, stream);
-    case EPI_BIAS_RELU_BF16: return launch_one<EPI_BIAS_RELU_BF16>(tmA, tmB, tmD, g, grid, stream);
-    case EPI_BIAS_F32: return launch_one<EPI_BIAS_F32>(tmA, tmB, tmD, g, grid, stream);
-    case EPI_BIAS_RESID_F32: return launch_one<EPI_BIAS_RESID_F32>(tmA, tmB, tmD, g, grid, stream);
+    case EPI_BIAS_BF16: return launch_one<EPI_BIAS_BF16>(tmA, tmB, tmD, tmR, g, grid, stream);
+    case EPI_BIAS_RELU_BF16: return launch_one<EPI_BIAS_RELU_BF16>(tmA, tmB, tmD, tmR, g, grid, stream);
+    case EPI_BIAS_F32: return launch_one<EPI_BIAS_F32>(tmA, tmB, tmD, tmR, g, grid, stream);
+    case EPI_BIAS_RESID_F32: return launch_one<EPI_BIAS_RESID_F32>(tmA, tmB, tmD, tmR, g, grid, stream);
     default: set_last_error("gemm: unknown epilogue %d", epilogue); return RP_ERR_INVALID;
   }
 }
