@@ -106,6 +106,89 @@ def collate(videos: Sequence[dict], pin: bool = False) -> dict:
     return batch
 
 
+class InferencePipeline:
+    """Double-buffered host->device->host inference over a stream of collated HOST batches (the
+    batched replacement of the reference's `for batch in loader: .to('cuda'); inference_()` loop,
+    inference.py:39-47).  The H2D copy of batch i+1 runs on a side stream while batch i computes;
+    each batch's fixed-slot result block comes back with one async D2H copy into pinned memory.
+    Host tensors should be pinned (`collate(..., pin=True)`) for the copies to overlap."""
+
+    FEATS = ("visual_feats", "audio_feats", "text_feats", "masks")
+
+    def __init__(self, model, test_cfg: dict, depth: int = 2):
+        self.model, self.cfg, self.depth = model, test_cfg, max(2, depth)
+        self.dev = model.device
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self._bufs = [dict() for _ in range(self.depth)]     # device staging, reused per slot
+        self._free = [None] * self.depth                      # event: compute that read slot is done
+        self._host_out = [None] * self.depth
+
+    def _stage(self, slot: int, batch: dict) -> dict:
+        """enqueue the H2D copies of `batch` into staging slot `slot` on the copy stream"""
+        bufs = self._bufs[slot]
+        dbatch = dict(batch)
+        with torch.cuda.stream(self.copy_stream):
+            if self._free[slot] is not None:
+                self.copy_stream.wait_event(self._free[slot])
+            for k in self.FEATS:
+                src = batch[k]
+                dst = bufs.get(k)
+                if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:
+                    dst = bufs[k] = torch.empty(src.shape, dtype=src.dtype, device=self.dev)
+                dst.copy_(src, non_blocking=True)
+                dbatch[k] = dst
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        return dbatch, ready
+
+    def run(self, batches):
+        """yields, per input batch and in order, the list of per-video result dicts (CPU tensors)"""
+        main = torch.cuda.current_stream(self.dev)
+        it = iter(batches)
+        pending = []        # (slot, batch, host_slots, done_event)
+        staged = []         # (slot, dbatch, ready_event, batch)
+        slot = 0
+
+        def stage_next():
+            nonlocal slot
+            try:
+                b = next(it)
+            except StopIteration:
+                return False
+            dbatch, ready = self._stage(slot, b)
+            staged.append((slot, dbatch, ready, b))
+            slot = (slot + 1) % self.depth
+            return True
+
+        stage_next()
+        while staged:
+            s, dbatch, ready, b = staged.pop(0)
+            stage_next()                                   # H2D of the next batch overlaps this compute
+            main.wait_event(ready)
+            r = self.model.inference_device(dbatch, self.cfg)
+            slots = pack_slots(r["segments"], r["scores"], r["labels"], r["counts"])
+            host = self._host_out[s]
+            if host is None or host.shape != slots.shape:
+                host = self._host_out[s] = torch.empty(slots.shape, dtype=slots.dtype).pin_memory()
+            host.copy_(slots, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            self._free[s] = done
+            pending.append((b, host, done))
+            if len(pending) >= self.depth:                 # retire the oldest while the GPU works
+                yield self._finish(*pending.pop(0))
+        while pending:
+            yield self._finish(*pending.pop(0))
+
+    @staticmethod
+    def _finish(batch, host, done):
+        done.synchronize()
+        out = unpack_slots(host)
+        for o, vid, dur in zip(out, batch["video_id"], batch["duration"]):
+            o["video_id"], o["duration"] = vid, dur
+        return out
+
+
 def run_sharded_inference(model, videos: Sequence[dict], test_cfg: dict, batch_size: int = 32,
                           kcap: int | None = None, group=None) -> list[dict]:
     """Shard `videos` (list of per-video host dicts with visual_feats/audio_feats/text_feats [T,C])

@@ -257,3 +257,30 @@ def test_multi_head_attention_module(kind):
     got = mha(q.to(DEV), k_in.to(DEV), v_in.to(DEV), None if mask is None else mask.to(DEV))
     assert got.shape == ref.shape
     assert _rel_err(got, ref) < REL_TOL, f"{kind}: {_rel_err(got, ref)}"
+
+
+# ------------------------------------------------------------------------------------ pipeline (f1)
+def test_inference_pipeline_matches_inference_():
+    from repurpose_b200.scheduler import InferencePipeline, collate
+    torch.manual_seed(11)
+    m = MMCTransformer(512, 2048, 384, 512, 2, 3, 3, 8)
+    m.load_state_dict(synth.bias_reg_head({k: v.clone() for k, v in m.state_dict().items()}))
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(3)
+    batches = []
+    for lens in ([300, 250], [128, 127, 64], [400]):
+        vids = [{"visual_feats": torch.randn(t, 512, generator=g), "audio_feats": torch.randn(t, 2048, generator=g),
+                 "text_feats": torch.randn(t, 384, generator=g), "video_id": f"v{t}"} for t in lens]
+        batches.append(collate(vids, pin=True))
+    want = []
+    for b in batches:
+        db = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in b.items()}
+        want.append(m.inference_(db, synth.TEST_CFG))
+    got = list(InferencePipeline(m, synth.TEST_CFG).run(iter(batches)))
+    assert len(got) == len(want)
+    for gb, wb in zip(got, want):
+        assert [r["video_id"] for r in gb] == [r["video_id"] for r in wb]
+        for r, w in zip(gb, wb):
+            assert torch.equal(r["labels"], w["labels"].cpu())
+            assert torch.allclose(r["segments"], w["segments"].cpu()) and torch.allclose(r["scores"], w["scores"].cpu())
+            assert not r["segments"].is_cuda
