@@ -1,21 +1,30 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T (+ epilogue).
 //
-//   warp 0      : TMA producer   (A 128x64 and W 256x64 bf16 tiles, SWIZZLE_128B, multi-stage ring)
-//   warp 1      : tcgen05.mma issuer (converged warp, one elected lane; UMMA 128x256x16, fp32
-//                 accumulators in TMEM, two 256-column accumulator buffers so the epilogue of tile i
-//                 overlaps the main loop of tile i+1); also owns TMEM alloc/dealloc
+// Two instantiations of one kernel:
+//   CG = 2 (default): CTA PAIRS (`tcgen05.mma.cta_group::2`, thread-block cluster of 2).  A pair computes
+//           a 256x256 tile: each CTA stages its own 128 rows of A and its own 128 rows (half of N) of W
+//           and holds the accumulator rows of its 128 A rows in its own TMEM.  Per CTA and k-block only
+//           32 KB enter shared memory (vs 48 KB) and the tensor core of each SM reads half of W from the
+//           peer — this is what relieves the shared-memory port that bounds the 1-CTA version.
+//   CG = 1: single-CTA 128x256 tile (kept for A/B comparison and small problems).
+//
+//   warp 0      : TMA producer   (SWIZZLE_128B boxes into a multi-stage ring)
+//   warp 1      : tcgen05.mma issuer (converged warp, one elected lane; only the leader CTA of a pair
+//                 issues), fp32 accumulators in TMEM, two 256-column accumulator buffers so the epilogue
+//                 of tile i overlaps the main loop of tile i+1; also owns TMEM alloc/dealloc
 //   warps 2..5  : epilogue: tcgen05.ld -> bias / ReLU / residual -> swizzled smem slab -> TMA store.
 //                 Each warp owns 32 accumulator rows and a private ring of 4 KB slabs.
 //
 // Residual epilogue (h += acc + bias, in place): the residual chunk is TMA-LOADED into the slab a few
 // chunks ahead (mbarrier per slab), updated in shared memory, and TMA-stored from the same slab.
 // Both directions are therefore full-line bulk copies with several in flight per warp, which is what
-// a ~1.5 us DRAM round trip needs; a register prefetch of depth one left the warps stalled on the
-// loads (profiles/r01_notes.md).
+// a ~1.5 us DRAM round trip needs (profiles/r01_notes.md).
 //
 // This kernel implements the Linear layers of the reference hot path
 // (models/MMCTransformer.py:121 input_projection, :135-138 in_proj/out_proj/linear1/linear2 inside
 // nn.TransformerEncoderLayer, :144 feature_map[0], :147-149 head Linear layers).
+#include <stdlib.h>
+
 #include "ptx.cuh"
 #include "host_util.h"
 #include "kernels.h"
@@ -24,29 +33,33 @@ namespace rp {
 
 namespace {
 
-constexpr int BM = 128;
-constexpr int BN = 256;
+constexpr int BM = 128;                // accumulator rows per CTA
+constexpr int BN = 256;                // accumulator columns per tile
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_BYTES = BN * BK * 2;   // 32 KB
 constexpr int SLAB_BYTES = 32 * 128;   // 32 rows x 128 B: one TMA box of the output / residual
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_SLABS = 5;
 
-// Shared-memory budget per epilogue kind: the residual epilogue trades one operand stage for a
-// deeper slab ring (loads and stores both live there).
-template <int EPI>
+// Shared-memory budget per (epilogue kind, CTA-group size): the residual epilogue trades operand
+// stages for a deeper slab ring (loads and stores both live there).
+template <int EPI, int CG>
 struct Cfg {
   static constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32);
-  static constexpr int STAGES = RESID ? 3 : 4;
+  static constexpr int B_ROWS = BN / CG;               // rows of W staged by each CTA
+  static constexpr int B_BYTES = B_ROWS * BK * 2;      // 32 KB (CG=1) / 16 KB (CG=2)
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SLABS = RESID ? 5 : 2;          // per epilogue warp
   static constexpr int LOOKAHEAD = 3;                  // residual chunks in flight per warp
+  static constexpr int STAGES = (229376 - 4 * SLABS * SLAB_BYTES) / STAGE_BYTES;  // CG1: 4/3, CG2: 6/4
   static constexpr int SMEM_A_OFF = 0;
   static constexpr int SMEM_B_OFF = STAGES * A_BYTES;
   static constexpr int SMEM_D_OFF = SMEM_B_OFF + STAGES * B_BYTES;
-  static constexpr int SMEM_BAR_OFF = SMEM_D_OFF + 4 * SLABS * SLAB_BYTES;  // 229376 either way
+  static constexpr int SMEM_BAR_OFF = SMEM_D_OFF + 4 * SLABS * SLAB_BYTES;
   static constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 512 + 1024;  // barriers + alignment slack
+  static_assert(STAGES >= 3 && STAGES <= 8, "stage count");
+  static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 };
 
 struct GemmArgs {
@@ -54,12 +67,12 @@ struct GemmArgs {
   const float* bias;
 };
 
-template <int EPI>
+template <int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                  const GemmArgs g) {
-  using C = Cfg<EPI>;
+  using C = Cfg<EPI, CG>;
   constexpr int STAGES = C::STAGES;
   constexpr int SLABS = C::SLABS;
   constexpr bool OUT_F32 = (EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_RESID_F32);
@@ -71,18 +84,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
 
+  // barrier map (bytes from bar_base): full[8] @0, empty[8] @64, tfull[2] @128, tempty[2] @144,
+  // tmem slot @160, resid[4][5] @192
   const uint32_t bar_base = base + C::SMEM_BAR_OFF;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
-  auto tfull_bar = [&](int b) { return bar_base + 64u + 8u * b; };
-  auto tempty_bar = [&](int b) { return bar_base + 80u + 8u * b; };
-  auto resid_bar = [&](int ew, int s) { return bar_base + 128u + 8u * (ew * MAX_SLABS + s); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::SMEM_BAR_OFF + 96);
+  auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+  auto tfull_bar = [&](int b) { return bar_base + 128u + 8u * b; };
+  auto tempty_bar = [&](int b) { return bar_base + 144u + 8u * b; };
+  auto resid_bar = [&](int ew, int s) { return bar_base + 192u + 8u * (ew * MAX_SLABS + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::SMEM_BAR_OFF + 160);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = CG == 2 ? int(cluster_ctarank()) : 0;   // 0 = leader of the pair
+  const int group = blockIdx.x / CG;                           // tile-scheduler slot (pair index)
+  const int num_groups = gridDim.x / CG;
 
-  const int m_tiles = (g.M + BM - 1) / BM;
+  const int m_tiles = (g.M + BM * CG - 1) / (BM * CG);
   const int n_tiles = g.N / BN;
   const int total_tiles = m_tiles * n_tiles;
   const int k_blocks = g.K / BK;
@@ -98,16 +116,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4);
+      mbar_init(tempty_bar(b), 4 * CG);
     }
-    for (int i = 0; i < 4 * MAX_SLABS; ++i) mbar_init(bar_base + 128u + 8u * i, 1);
+    for (int i = 0; i < 4 * MAX_SLABS; ++i) mbar_init(bar_base + 192u + 8u * i, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc<TMEM_COLS>(base + C::SMEM_BAR_OFF + 96);
+    if constexpr (CG == 2) tmem_alloc_cg2<TMEM_COLS>(base + C::SMEM_BAR_OFF + 160);
+    else tmem_alloc<TMEM_COLS>(base + C::SMEM_BAR_OFF + 160);
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // peer barriers initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -116,50 +136,70 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // (the whole warp walks the loop; one elected lane issues)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = group; tile < total_tiles; tile += num_groups) {
       const int m_blk = tile / n_tiles;
       const int n_blk = tile - m_blk * n_tiles;
+      const int a_row = (m_blk * CG + cta_rank) * BM;
+      const int b_row = n_blk * BN + cta_rank * C::B_ROWS;
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         if (elect_one()) {
-          mbar_expect_tx(full_bar(stage), A_BYTES + B_BYTES);
-          tma_load_2d(base + C::SMEM_A_OFF + stage * A_BYTES, &tmA, full_bar(stage), kb * BK,
-                      m_blk * BM);
-          tma_load_2d(base + C::SMEM_B_OFF + stage * B_BYTES, &tmB, full_bar(stage), kb * BK,
-                      n_blk * BN);
+          const uint32_t sa = base + C::SMEM_A_OFF + stage * A_BYTES;
+          const uint32_t sb = base + C::SMEM_B_OFF + stage * C::B_BYTES;
+          if constexpr (CG == 2) {
+            // both CTAs' bytes are credited to the leader's barrier, which the leader arms
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+            tma_load_2d_cg2(sa, &tmA, full_bar(stage), kb * BK, a_row);
+            tma_load_2d_cg2(sb, &tmB, full_bar(stage), kb * BK, b_row);
+          } else {
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, a_row);
+            tma_load_2d(sb, &tmB, full_bar(stage), kb * BK, b_row);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     // Converged control flow keeps the descriptors in uniform registers; a divergent
     // single-thread loop costs ~100 cycles per tcgen05.mma issue.
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t use_parity = (uint32_t(it) >> 1) & 1u;
-      mbar_wait(tempty_bar(buf), use_parity ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + uint32_t(buf * BN);
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+    if (cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = group; tile < total_tiles; tile += num_groups, ++it) {
+        const int buf = it & 1;
+        const uint32_t use_parity = (uint32_t(it) >> 1) & 1u;
+        mbar_wait(tempty_bar(buf), use_parity ^ 1u);
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t da = make_smem_desc_sw128(base + C::SMEM_A_OFF + stage * A_BYTES, 1024, 16);
-          const uint64_t db = make_smem_desc_sw128(base + C::SMEM_B_OFF + stage * B_BYTES, 1024, 16);
+        const uint32_t d_tmem = tmem_base + uint32_t(buf * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = make_smem_desc_sw128(base + C::SMEM_A_OFF + stage * A_BYTES, 1024, 16);
+            const uint64_t db = make_smem_desc_sw128(base + C::SMEM_B_OFF + stage * C::B_BYTES, 1024, 16);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // +32 bytes along K per step = +2 in the address field
-            mma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit(empty_bar(stage));  // smem slot free once these MMAs retire
-          if (kb == k_blocks - 1) tc_commit(tfull_bar(buf));  // accumulator complete
+            for (int k = 0; k < BK / 16; ++k) {  // +32 bytes along K per step = +2 in the address field
+              if constexpr (CG == 2)
+                mma_ss_cg2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              else
+                mma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if constexpr (CG == 2) {
+              tc_commit_cg2(empty_bar(stage));  // frees the slot in BOTH CTAs once these MMAs retire
+              if (kb == k_blocks - 1) tc_commit_cg2(tfull_bar(buf));
+            } else {
+              tc_commit(empty_bar(stage));
+              if (kb == k_blocks - 1) tc_commit(tfull_bar(buf));
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -167,19 +207,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;   // TMEM lane quarter this warp may access
     const int ew = warp - 2;  // slab ring / barrier set of this warp
     const uint32_t slab0 = base + C::SMEM_D_OFF + ew * SLABS * SLAB_BYTES;
-    const int my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int my_tiles = group < total_tiles ? (total_tiles - group + num_groups - 1) / num_groups : 0;
     const int total_chunks = my_tiles * CHUNKS;
+    auto tile_row0 = [&](int m_blk) { return (m_blk * CG + cta_rank) * BM + q * 32; };
 
-    // residual chunk gc (global per-warp chunk counter) -> issue its TMA load into slab gc % SLABS
+    // residual chunk gc (per-warp chunk counter) -> issue its TMA load into slab gc % SLABS
     auto issue_resid_load = [&](int gc) {
-      const int tile = blockIdx.x + (gc / CHUNKS) * gridDim.x;
+      const int tile = group + (gc / CHUNKS) * num_groups;
       const int c = gc % CHUNKS;
       const int m_blk = tile / n_tiles;
       const int n_blk = tile - m_blk * n_tiles;
       const int s = gc % SLABS;
       mbar_expect_tx(resid_bar(ew, s), SLAB_BYTES);
-      tma_load_2d(slab0 + s * SLAB_BYTES, &tmR, resid_bar(ew, s), n_blk * BN + c * CPC,
-                  m_blk * BM + q * 32);
+      tma_load_2d(slab0 + s * SLAB_BYTES, &tmR, resid_bar(ew, s), n_blk * BN + c * CPC, tile_row0(m_blk));
     };
     if constexpr (C::RESID) {
       if (lane == 0)
@@ -188,13 +228,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     int it = 0;
     int gc = 0;  // chunks processed so far by this warp
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = group; tile < total_tiles; tile += num_groups, ++it) {
       const int m_blk = tile / n_tiles;
       const int n_blk = tile - m_blk * n_tiles;
       const int buf = it & 1;
       const uint32_t use_parity = (uint32_t(it) >> 1) & 1u;
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN);
-      const int row0 = m_blk * BM + q * 32;
+      const int row0 = tile_row0(m_blk);
       mbar_wait(tfull_bar(buf), use_parity);
       tc_fence_after();
 
@@ -280,35 +320,87 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       // all TMEM reads of this accumulator buffer are complete -> hand it back to the MMA warp
+      // (of the leader CTA; both CTAs' epilogue warps report there)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_leader(tempty_bar(buf));
+        else mbar_arrive(tempty_bar(buf));
+      }
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer may still read my smem / signal my barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
-template <int EPI>
+template <int EPI, int CG>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
-               const CUtensorMap& tmR, const GemmArgs& g, int grid, cudaStream_t stream) {
+               const CUtensorMap& tmR, const GemmArgs& g, int groups, cudaStream_t stream) {
+  using C = Cfg<EPI, CG>;
   static bool configured = false;
   if (!configured) {
-    RP_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg<EPI>::SMEM_TOTAL));
+    RP_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, CG>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));
     configured = true;
   }
-  gemm_bf16_kernel<EPI><<<grid, NUM_THREADS, Cfg<EPI>::SMEM_TOTAL, stream>>>(tmA, tmB, tmD, tmR, g);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(groups * CG));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, CG>, tmA, tmB, tmD, tmR, g));
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;
+}
+
+template <int CG>
+int launch_cg(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd,
+              const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
+              cudaStream_t stream) {
+  const bool out_f32 = (epilogue == EPI_BIAS_F32 || epilogue == EPI_BIAS_RESID_F32);
+  CUtensorMap tmA, tmB, tmD, tmR;
+  int rc;
+  if ((rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, A, K, M, lda * 2, BK, BM))) return rc;
+  if ((rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, W, K, N, ldw * 2, BK, BN / CG))) return rc;
+  if (out_f32)
+    rc = make_tmap_2d(&tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, D, N, M, ldd * 4, 32, 32);
+  else
+    rc = make_tmap_2d(&tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, D, N, M, ldd * 2, 64, 32);
+  if (rc) return rc;
+  tmR = tmD;
+  if (epilogue == EPI_BIAS_RESID_F32 &&
+      (rc = make_tmap_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, resid, N, M, ldr * 4, 32, 32)))
+    return rc;
+
+  GemmArgs g{M, N, K, bias};
+  const int total_tiles = ((M + BM * CG - 1) / (BM * CG)) * (N / BN);
+  const int sms = num_sms();
+  if (sms <= 0) return RP_ERR_NO_DEVICE;
+  const int max_groups = sms / CG;
+  const int groups = total_tiles < max_groups ? total_tiles : max_groups;
+  switch (epilogue) {
+    case EPI_BIAS_BF16: return launch_one<EPI_BIAS_BF16, CG>(tmA, tmB, tmD, tmR, g, groups, stream);
+    case EPI_BIAS_RELU_BF16: return launch_one<EPI_BIAS_RELU_BF16, CG>(tmA, tmB, tmD, tmR, g, groups, stream);
+    case EPI_BIAS_F32: return launch_one<EPI_BIAS_F32, CG>(tmA, tmB, tmD, tmR, g, groups, stream);
+    case EPI_BIAS_RESID_F32: return launch_one<EPI_BIAS_RESID_F32, CG>(tmA, tmB, tmD, tmR, g, groups, stream);
+    default: set_last_error("gemm: unknown epilogue %d", epilogue); return RP_ERR_INVALID;
+  }
 }
 
 }  // namespace
@@ -328,33 +420,11 @@ int launch_gemm(int epilogue, const void* A, int64_t lda, const void* W, int64_t
             reinterpret_cast<uintptr_t>(D) | reinterpret_cast<uintptr_t>(bias) |
             reinterpret_cast<uintptr_t>(resid)) % 16 == 0,
            "gemm: pointers must be 16-byte aligned");
-
-  CUtensorMap tmA, tmB, tmD, tmR;
-  int rc;
-  if ((rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, A, K, M, lda * 2, BK, BM))) return rc;
-  if ((rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, W, K, N, ldw * 2, BK, BN))) return rc;
-  if (out_f32)
-    rc = make_tmap_2d(&tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, D, N, M, ldd * 4, 32, 32);
-  else
-    rc = make_tmap_2d(&tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, D, N, M, ldd * 2, 64, 32);
-  if (rc) return rc;
-  tmR = tmD;
-  if (epilogue == EPI_BIAS_RESID_F32 &&
-      (rc = make_tmap_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, resid, N, M, ldr * 4, 32, 32)))
-    return rc;
-
-  GemmArgs g{M, N, K, bias};
-  const int total_tiles = ((M + BM - 1) / BM) * (N / BN);
-  const int sms = num_sms();
-  if (sms <= 0) return RP_ERR_NO_DEVICE;
-  const int grid = total_tiles < sms ? total_tiles : sms;
-  switch (epilogue) {
-    case EPI_BIAS_BF16: return launch_one<EPI_BIAS_BF16>(tmA, tmB, tmD, tmR, g, grid, stream);
-    case EPI_BIAS_RELU_BF16: return launch_one<EPI_BIAS_RELU_BF16>(tmA, tmB, tmD, tmR, g, grid, stream);
-    case EPI_BIAS_F32: return launch_one<EPI_BIAS_F32>(tmA, tmB, tmD, tmR, g, grid, stream);
-    case EPI_BIAS_RESID_F32: return launch_one<EPI_BIAS_RESID_F32>(tmA, tmB, tmD, tmR, g, grid, stream);
-    default: set_last_error("gemm: unknown epilogue %d", epilogue); return RP_ERR_INVALID;
-  }
+  // RP_GEMM_CG=1 selects the single-CTA kernel (A/B experiments); the CTA-pair kernel is the default
+  static const int cg = getenv("RP_GEMM_CG") ? atoi(getenv("RP_GEMM_CG")) : 2;
+  if (cg == 1 || M <= BM)
+    return launch_cg<1>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, stream);
+  return launch_cg<2>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, stream);
 }
 
 }  // namespace rp
