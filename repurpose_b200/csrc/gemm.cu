@@ -41,6 +41,9 @@ constexpr int SLAB_BYTES = 32 * 128;   // 32 rows x 128 B: one TMA box of the ou
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_SLABS = 5;
+#ifndef RP_RESID_SLABS
+#define RP_RESID_SLABS 4
+#endif
 
 // Shared-memory budget per (epilogue kind, CTA-group size): the residual epilogue trades operand
 // stages for a deeper slab ring (loads and stores both live there).
@@ -50,9 +53,9 @@ struct Cfg {
   static constexpr int B_ROWS = BN / CG;               // rows of W staged by each CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;      // 32 KB (CG=1) / 16 KB (CG=2)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SLABS = RESID ? 5 : 2;          // per epilogue warp
-  static constexpr int LOOKAHEAD = 3;                  // residual chunks in flight per warp
-  static constexpr int STAGES = (229376 - 4 * SLABS * SLAB_BYTES) / STAGE_BYTES;  // CG1: 4/3, CG2: 6/4
+  static constexpr int SLABS = RESID ? RP_RESID_SLABS : 2;          // per epilogue warp
+  static constexpr int LOOKAHEAD = SLABS - 2;          // residual chunks in flight per warp
+  static constexpr int STAGES = (229376 - 4 * SLABS * SLAB_BYTES) / STAGE_BYTES;  // CG1: 4/3, CG2: 6/5
   static constexpr int SMEM_A_OFF = 0;
   static constexpr int SMEM_B_OFF = STAGES * A_BYTES;
   static constexpr int SMEM_D_OFF = SMEM_B_OFF + STAGES * B_BYTES;
