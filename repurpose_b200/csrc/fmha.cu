@@ -129,7 +129,7 @@ __device__ __forceinline__ void exp2_emulated2(unsigned long long x2, float& p0,
   p1 = __uint_as_float((__float_as_uint(t1) << 23) + __float_as_uint(q1));
 }
 
-template <int MASK_MODE, int EMU_PAIRS, int NQ>
+template <int MASK_MODE, int EMU_PAIRS, int NQ, int BF16EXP>
 __global__ void __launch_bounds__(Cfg<NQ>::NUM_THREADS, Cfg<NQ>::MIN_CTAS)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -399,43 +399,46 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 3);
 
         if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 4);
-        // Block A: every exp2 of my 64 scores, results overwrite the score registers.  All 64
-        // evaluations are independent, so the MUFU queue stays full; the consumers (row sum, bf16
-        // pack, TMEM store) live in block B behind a branch the compiler cannot fold, which keeps
-        // ptxas from scheduling each consumer right behind its producer (an in-order warp would
-        // then eat the full MUFU latency once per pair).
+        // Block A: every exp2 of my 64 scores.  All evaluations are independent, so the MUFU queue
+        // stays full; the consumers (row sum, TMEM store) live in block B behind a branch the
+        // compiler cannot fold, which keeps ptxas from scheduling each consumer right behind its
+        // producer (an in-order warp would then eat the full MUFU latency once per pair).
+        // BF16EXP: x = s - m is rounded to bf16x2 and ONE MUFU op (ex2.approx.ftz.bf16x2) yields
+        // both probabilities already in the packed bf16 form the PV MMA consumes — half the MUFU
+        // work of the fp32 path, which is what bounds d=64 attention.
         const unsigned long long negm2 = pack2(-m, -m);
+        uint32_t pk[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const unsigned long long x2 =
               add2(pack2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1])), negm2);
-          float p0, p1;
+          float x0, x1;
           if ((c & 3) < EMU_PAIRS) {
+            float p0, p1;
             exp2_emulated2(x2, p0, p1);
-          } else {
-            float x0, x1;
+            pk[c] = pack_bf16x2(p0, p1);
+          } else if (BF16EXP) {
+            // fp32 -> bf16 by truncation on the ALU (PRMT): the F2FP conversion shares the XU pipe
+            // with the MUFU, so a rounding convert per pair would double the XU work again.  The
+            // extra <= 2^-8 relative error on x is common-mode between p and the row sum.
             unpack2(x2, x0, x1);
-            p0 = ex2_approx(x0);
-            p1 = ex2_approx(x1);
+            pk[c] = ex2_bf16x2(__byte_perm(__float_as_uint(x0), __float_as_uint(x1), 0x7632));
+          } else {
+            unpack2(x2, x0, x1);
+            pk[c] = pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
           }
-          sr[2 * c] = __float_as_uint(p0);
-          sr[2 * c + 1] = __float_as_uint(p1);
         }
-        if (opaque_true) {  // Block B
+        if (opaque_true) {  // Block B: row sum of the bf16-rounded probabilities (what the MMA sees)
           unsigned long long sumA = pack2(0.f, 0.f), sumB = pack2(0.f, 0.f);
 #pragma unroll
-          for (int qd = 0; qd < 2; ++qd) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const int i0 = qd * 32 + 2 * c;
-              const float p0 = __uint_as_float(sr[i0]), p1 = __uint_as_float(sr[i0 + 1]);
-              if (c & 1) sumB = add2(sumB, pack2(p0, p1));
-              else sumA = add2(sumA, pack2(p0, p1));
-              pk[c] = pack_bf16x2(p0, p1);
-            }
-            tmem_st16(t_p + qd * 16, pk);
+          for (int c = 0; c < 32; ++c) {
+            const unsigned long long p2 =
+                pack2(__uint_as_float(pk[c] << 16), __uint_as_float(pk[c] & 0xffff0000u));
+            if (c & 1) sumB = add2(sumB, p2);
+            else sumA = add2(sumA, p2);
           }
+          tmem_st16(t_p, pk);
+          tmem_st16(t_p + 16, pk + 16);
           lsum2 = add2(lsum2, add2(sumA, sumB));
         }
         if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 5);
@@ -495,18 +498,18 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-template <int MASK_MODE, int EMU_PAIRS, int NQ>
+template <int MASK_MODE, int EMU_PAIRS, int NQ, int BF16EXP>
 int launch_variant(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                    const CUtensorMap& tmO, const FmhaParams& p, cudaStream_t stream) {
   using C = Cfg<NQ>;
   static bool configured = false;
   if (!configured) {
-    RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ>,
+    RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ, BF16EXP>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));
     configured = true;
   }
   dim3 grid((p.Tq + NQ * QT - 1) / (NQ * QT), p.H, p.B);
-  fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ><<<grid, C::NUM_THREADS, C::SMEM_TOTAL, stream>>>(tmQ, tmK, tmV, tmO, p);
+  fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ, BF16EXP><<<grid, C::NUM_THREADS, C::SMEM_TOTAL, stream>>>(tmQ, tmK, tmV, tmO, p);
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;
@@ -555,14 +558,24 @@ int launch_fmha(const FmhaArgs& a, cudaStream_t stream) {
   FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride};
   // RP_FMHA_NQ: query tiles per CTA (2 = one big CTA per SM, 1 = two independent CTAs per SM)
   static const int nq_cfg = getenv("RP_FMHA_NQ") ? atoi(getenv("RP_FMHA_NQ")) : 1;
-  if (a.mask_mode == 1) return launch_variant<1, 1, 1>(tmQ, tmK, tmV, tmO, p, stream);
-  switch (emu_pairs_setting() * 2 + (nq_cfg == 2 ? 1 : 0)) {
-    case 0: return launch_variant<0, 0, 1>(tmQ, tmK, tmV, tmO, p, stream);
-    case 1: return launch_variant<0, 0, 2>(tmQ, tmK, tmV, tmO, p, stream);
-    case 3: return launch_variant<0, 1, 2>(tmQ, tmK, tmV, tmO, p, stream);
-    case 4: return launch_variant<0, 2, 1>(tmQ, tmK, tmV, tmO, p, stream);
-    case 5: return launch_variant<0, 2, 2>(tmQ, tmK, tmV, tmO, p, stream);
-    default: return launch_variant<0, 1, 1>(tmQ, tmK, tmV, tmO, p, stream);
+  // RP_FMHA_BF16EXP: 1 = packed bf16x2 MUFU exp2 (experiment: MUFU.EX2.BF16x2 costs 16 cycles per
+  // warp instruction, i.e. no cheaper per score than two fp32 MUFU ops), 0 = fp32 exp2 (default)
+  static const int bfexp = getenv("RP_FMHA_BF16EXP") ? atoi(getenv("RP_FMHA_BF16EXP")) : 0;
+  if (a.mask_mode == 1) {
+    return bfexp ? launch_variant<1, 0, 1, 1>(tmQ, tmK, tmV, tmO, p, stream)
+              : launch_variant<1, 1, 1, 0>(tmQ, tmK, tmV, tmO, p, stream);
+  }
+  const int key = (bfexp ? 100 : 0) + emu_pairs_setting() * 10 + (nq_cfg == 2 ? 2 : 1);
+  switch (key) {
+    case 101: return launch_variant<0, 0, 1, 1>(tmQ, tmK, tmV, tmO, p, stream);
+    case 102: return launch_variant<0, 0, 2, 1>(tmQ, tmK, tmV, tmO, p, stream);
+    case 111: return launch_variant<0, 1, 1, 1>(tmQ, tmK, tmV, tmO, p, stream);
+    case 121: return launch_variant<0, 2, 1, 1>(tmQ, tmK, tmV, tmO, p, stream);
+    case 1:   return launch_variant<0, 0, 1, 0>(tmQ, tmK, tmV, tmO, p, stream);
+    case 2:   return launch_variant<0, 0, 2, 0>(tmQ, tmK, tmV, tmO, p, stream);
+    case 12:  return launch_variant<0, 1, 2, 0>(tmQ, tmK, tmV, tmO, p, stream);
+    case 11:  return launch_variant<0, 1, 1, 0>(tmQ, tmK, tmV, tmO, p, stream);
+    default:  return launch_variant<0, 1, 1, 0>(tmQ, tmK, tmV, tmO, p, stream);
   }
 }
 
