@@ -128,8 +128,12 @@ __global__ void __launch_bounds__(256)
 layernorm512_kernel(const LnArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = int64_t(gridDim.x) * (blockDim.x >> 5);
-  for (int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5); row < a.M;
-       row += warps_total) {
+  // Rows are visited from the END of the buffer: the producer GEMM wrote its last tiles most
+  // recently, so those rows are still L2-resident, and this kernel in turn finishes on row 0,
+  // where the consumer GEMM starts.
+  for (int64_t it = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5); it < a.M;
+       it += warps_total) {
+    const int64_t row = a.M - 1 - it;
     Row x, y;
     row_load(x, a.x + row * 512, lane);
     row_norm(y, x, a.g0, a.b0, a.eps, lane);

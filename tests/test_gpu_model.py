@@ -284,3 +284,65 @@ def test_inference_pipeline_matches_inference_():
             assert torch.equal(r["labels"], w["labels"].cpu())
             assert torch.allclose(r["segments"], w["segments"].cpu()) and torch.allclose(r["scores"], w["scores"].cpu())
             assert not r["segments"].is_cuda
+
+
+# ------------------------------------------------------------------------------------ BASELINE configs 3/4
+def test_long_video_stress_config4():
+    """T = 8192 feature steps (beyond the reference's 5000-row PE buffer: extended table, SURVEY
+    App. A.2), pre_nms_topk = 4096, max_seg_num = 41; 2-layer model against the fp32 oracle, and
+    Soft-NMS fed exactly 4096 candidates per video."""
+    T = 8192
+    torch.manual_seed(21)
+    m = MMCTransformer(512, 2048, 384, 512, 2, 3, 3, 8, max_len=T)
+    sd = synth.bias_reg_head({k: v.clone() for k, v in m.state_dict().items()})
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    assert sd["positional_encoding.pe"].shape == (1, T, 512)
+    batch = synth.make_batch([T, 6000], seed=8)
+    dbatch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    cfg = dict(synth.TEST_CFG, pre_nms_topk=4096)
+    _, logits, offsets, _, _, _ = m(dbatch)
+    o_logits, o_offsets, _ = mmct.forward(sd, batch)
+    valid = batch["masks"][:, 0, :]
+    assert _rel_err(logits.cpu()[valid], o_logits[valid]) < REL_TOL
+    assert _rel_err(offsets.cpu()[valid], o_offsets[valid]) < REL_TOL
+    res = m.inference_(dbatch, cfg)
+    assert len(res[0]["scores"]) <= synth.max_seg_num(T, 0.3) == 41
+    # identical fp32 candidates -> bit-exact keep at the 4096-candidate / 41-segment limits
+    r = m._run_decode(o_logits[:, :, 0].to(DEV).contiguous(), o_offsets.to(DEV).contiguous(),
+                      torch.tensor([T, 6000], dtype=torch.int32, device=DEV),
+                      [synth.max_seg_num(T, 0.3), synth.max_seg_num(6000, 0.3)], cfg, want_candidates=True)
+    for i in range(2):
+        o = mmct.decode_single_video(batch["masks"][i], o_logits[i, :, 0], o_offsets[i], cfg)
+        n = int(r["ncand"][i])
+        assert n == o["scores"].numel() and n > 1000
+        keep = soft_nms_intervals_oracle(o["scores"].numpy(), o["segments"].numpy(), 0.5, 0.01,
+                                         synth.max_seg_num(batch["duration"][i], 0.3))
+        k = int(r["counts"][i])
+        assert np.array_equal(r["labels"][i, :k].cpu().numpy(), o["labels"].numpy()[keep]), i
+
+
+def test_atiou_parity_on_a_synthetic_set():
+    """AtIoU (inference.py:45-55) of our segments vs the oracle's on 24 ragged videos, 3-layer model:
+    within 0.1 point (north_star), plus identical kept-label sets for the overwhelming majority."""
+    torch.manual_seed(31)
+    m = MMCTransformer(512, 2048, 384, 512, 3, 3, 3, 8)
+    sd = synth.bias_reg_head({k: v.clone() for k, v in m.state_dict().items()})
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    lens = synth.sample_lengths(24, seed=5, t_max=900)
+    gts, ours, refs, same = [], [], [], 0
+    for b0 in range(0, 24, 8):
+        batch = synth.make_batch(lens[b0:b0 + 8], seed=40 + b0)
+        dbatch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        got = m.inference_(dbatch, synth.TEST_CFG, to_host=True)
+        want = mmct.inference(sd, batch, synth.TEST_CFG)
+        for i, (g, w) in enumerate(zip(got, want)):
+            gts.append(synth.make_gt_segments(batch["duration"][i], 900 + b0 + i))
+            ours.append(g["segments"].tolist())
+            refs.append(w["segments"].tolist())
+            same += int(g["labels"].tolist() == w["labels"].tolist())
+    a_ours, _ = mmct.atiou(gts, ours)
+    a_ref, _ = mmct.atiou(gts, refs)
+    assert abs(a_ours - a_ref) * 100 <= 0.1, f"AtIoU {100 * a_ours:.3f} vs oracle {100 * a_ref:.3f}"
+    assert same >= 20, f"only {same}/24 videos keep the identical segment list"
