@@ -16,6 +16,25 @@ int launch_gemm(int epilogue, const void* A, int64_t lda, const void* W, int64_t
                 int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
                 cudaStream_t stream);
 
+// LayerNorm folded into the GEMMs around it (used by rp_forward):
+//   producer side (EPI_BIAS_RESID_F32 only): besides h (f32) the epilogue writes hb = bf16(h) and
+//     accumulates per-row (sum, sum of squares) of h into stats_out[row]; it also clears stats_zero[row].
+//   consumer side (epilogues 0/1/2): A = hb, W = gamma-folded weights, and the epilogue applies
+//     out = rstd*(acc - mean*c1[n]) + bias[n] with (mean, rstd) from stats_in[row] over `ln_width` columns.
+struct GemmLnFusion {
+  const float* stats_in = nullptr;   // [M][2]
+  const float* c1 = nullptr;         // [N]  sum_k of the bf16-rounded gamma-folded weight row
+  float* stats_out = nullptr;        // [M][2]
+  float* stats_zero = nullptr;       // [M][2]
+  void* hb_out = nullptr;            // bf16 [M, N]
+  int64_t ld_hb = 0;
+  int ln_width = 512;
+  float eps = 1e-5f;
+};
+int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
+                   int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
+                   const GemmLnFusion& ln, cudaStream_t stream);
+
 // ---- fused multi-head attention (d_k = 64) -----------------------------------------------------
 // q/k/v: bf16, row pitch ld* elements, batch pitch bs* elements; head h occupies columns
 // [h*64, h*64+64) of each row.  q is expected pre-scaled by log2(e)/sqrt(d_k).
