@@ -9,7 +9,10 @@ import ctypes as C
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "librepurpose_b200.so"
+import os
+
+# RP_LIB_PATH: load another build of the library (A/B experiments); default = the in-tree build
+LIB_PATH = Path(os.environ.get("RP_LIB_PATH", _PKG / "librepurpose_b200.so"))
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 

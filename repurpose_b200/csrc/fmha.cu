@@ -63,6 +63,10 @@ struct Cfg {
   static constexpr int TM_P = 128 * NQ;  // + q*64
   static constexpr int TM_O = 192 * NQ;  // + q*64
 };
+#ifndef RP_PV_WAIT_LATE
+#define RP_PV_WAIT_LATE 1
+#endif
+constexpr bool PV_WAIT_LATE = RP_PV_WAIT_LATE != 0;  // wait for PV_{j-1} only right before P is overwritten
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units; stale max keeps p <= 2^8
 constexpr float MASK_FILL_LOG2 = -1.0e9f * 1.4426950408889634f;
 
@@ -82,6 +86,7 @@ struct FmhaParams {
   const int32_t* kv_lens;
   const uint8_t* mask;
   int64_t mask_b_stride, mask_q_stride;
+  int pingpong;  // NQ=2 only: the two query tiles take turns in the exp phase (named barriers 11/12)
 };
 
 // ---- packed f32x2 helpers (sm_100 FFMA2/FADD2) ---------------------------------------------------
@@ -328,6 +333,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
 
       const bool opaque_true = (p.H != 0);  // always true; unknown to the compiler
+      const bool pingpong = NQ == 2 && nq == 2 && p.pingpong != 0;
+      if (pingpong && q == 1) named_bar_arrive(11, 512);
       for (int j = 0; j < n_kv; ++j) {
         if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 0);
         mbar_wait(s_full(q), uint32_t(j) & 1u);
@@ -337,6 +344,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld32(t_s + 0, sr + 0);
         tmem_ld32(t_s + 32, sr + 32);
         tmem_ld_wait();
+        if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 2);
         // S now lives in registers: release the TMEM columns so QK^T of the next key tile can start
         tc_fence_before();
         __syncwarp();
@@ -363,10 +371,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (c + 2 < 64) mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])));
         }
         const float mxh = fmaxf(mx0, mx1);
+        if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 3);
         float* xrow = xch + (((j & 1) * NQ + q) * 2) * 128 + row_in_tile;
         xrow[h * 128] = mxh;
         named_bar_sync(pair_bar, 64);
         const float m_new = fmaxf(m, fmaxf(mxh, xrow[(h ^ 1) * 128]));
+        if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 4);
         bool pv_waited = false;
         if (j == 0) {
           m = m_new;
@@ -391,14 +401,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
         }
-        if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 2);
-        if (j > 0 && !pv_waited) {
+        if (!PV_WAIT_LATE && j > 0 && !pv_waited) {
           mbar_wait(pv_done(q), uint32_t(j - 1) & 1u);  // PV_{j-1} has finished reading P
           tc_fence_after();
         }
-        if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 3);
-
-        if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 4);
+        if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 5);
+        if (pingpong) {
+          if (q == 0) named_bar_sync(11, 512); else named_bar_sync(12, 512);
+        }
         // Block A: every exp2 of my 64 scores.  All evaluations are independent, so the MUFU queue
         // stays full; the consumers (row sum, TMEM store) live in block B behind a branch the
         // compiler cannot fold, which keeps ptxas from scheduling each consumer right behind its
@@ -428,6 +438,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             pk[c] = pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
           }
         }
+        if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 6);
         if (opaque_true) {  // Block B: row sum of the bf16-rounded probabilities (what the MMA sees)
           unsigned long long sumA = pack2(0.f, 0.f), sumB = pack2(0.f, 0.f);
 #pragma unroll
@@ -437,13 +448,19 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (c & 1) sumB = add2(sumB, p2);
             else sumA = add2(sumA, p2);
           }
+          if (PV_WAIT_LATE && j > 0 && !pv_waited) {
+            mbar_wait(pv_done(q), uint32_t(j - 1) & 1u);  // PV_{j-1} has finished reading P
+            tc_fence_after();
+          }
           tmem_st16(t_p, pk);
           tmem_st16(t_p + 16, pk + 16);
           lsum2 = add2(lsum2, add2(sumA, sumB));
         }
-        if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 5);
-        if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 6);
+        if (pingpong && !(q == 1 && j == n_kv - 1)) {
+          if (q == 0) named_bar_arrive(12, 512); else named_bar_arrive(11, 512);
+        }
         tmem_st_wait();
+        if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 7);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready(q));
@@ -555,7 +572,8 @@ int launch_fmha(const FmhaArgs& a, cudaStream_t stream) {
   if ((rc = make_tmap_3d(&tmV, bf, a.v, cols, a.Tk, a.B, a.ldv * 2, a.bsv * 2, HD, KT))) return rc;
   if ((rc = make_tmap_3d(&tmO, bf, a.o, cols, a.Tq, a.B, a.ldo * 2, a.bso * 2, HD, QT))) return rc;
 
-  FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride};
+  static const int pp = getenv("RP_FMHA_PINGPONG") ? atoi(getenv("RP_FMHA_PINGPONG")) : 0;
+  FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride, pp};
   // RP_FMHA_NQ: query tiles per CTA (2 = one big CTA per SM, 1 = two independent CTAs per SM)
   static const int nq_cfg = getenv("RP_FMHA_NQ") ? atoi(getenv("RP_FMHA_NQ")) : 1;
   // RP_FMHA_BF16EXP: 1 = packed bf16x2 MUFU exp2 (experiment: MUFU.EX2.BF16x2 costs 16 cycles per

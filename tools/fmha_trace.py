@@ -20,8 +20,8 @@ assert raw.rp_debug_fmha_trace(buf.ctypes.data) == 0
 tr = buf.reshape(8, 512).astype(np.int64)
 t0 = tr[tr > 0].min()
 n = 8
-print("j | QKissue(q0,q1 for j+1) | PVissue(q0,q1) | WG0: wait_s, got_s, wait_pv, got_pv, got_turn, A_done, B_done | WG1: ...")
+print("j | QKissue(q0,q1 for j+1) | PVissue(q0,q1) | WG0: wait_s, got_s, ldtm, max, xchg, got_pv, A_issued, B_done | WG1: ...")
 for j in range(n):
     f = lambda r, i: int(tr[r, i] - t0) if tr[r, i] > 0 else -1
-    print(j, "|", f(0, j), f(1, j), "|", f(2, j), f(3, j), "|", [f(4, 8 * j + k) for k in range(7)], "|",
-          [f(5, 8 * j + k) for k in range(7)])
+    print(j, "|", f(0, j), f(1, j), "|", f(2, j), f(3, j), "|", [f(4, 8 * j + k) for k in range(8)], "|",
+          [f(5, 8 * j + k) for k in range(8)])
