@@ -332,7 +332,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mrow = p.mask + int64_t(b) * p.mask_b_stride + int64_t(qrow) * p.mask_q_stride;
       }
 
-      const bool opaque_true = (p.H != 0);  // always true; unknown to the compiler
       const bool pingpong = NQ == 2 && nq == 2 && p.pingpong != 0;
       if (pingpong && q == 1) named_bar_arrive(11, 512);
       for (int j = 0; j < n_kv; ++j) {
@@ -417,36 +416,43 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // both probabilities already in the packed bf16 form the PV MMA consumes — half the MUFU
         // work of the fp32 path, which is what bounds d=64 attention.
         const unsigned long long negm2 = pack2(-m, -m);
-        uint32_t pk[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const unsigned long long x2 =
               add2(pack2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1])), negm2);
-          float x0, x1;
+          float p0, p1;
           if ((c & 3) < EMU_PAIRS) {
-            float p0, p1;
             exp2_emulated2(x2, p0, p1);
-            pk[c] = pack_bf16x2(p0, p1);
           } else if (BF16EXP) {
-            // fp32 -> bf16 by truncation on the ALU (PRMT): the F2FP conversion shares the XU pipe
-            // with the MUFU, so a rounding convert per pair would double the XU work again.  The
-            // extra <= 2^-8 relative error on x is common-mode between p and the row sum.
+            // experiment: one packed MUFU op per pair (bf16 in/out); costs 16 XU cycles, no gain
+            float x0, x1;
             unpack2(x2, x0, x1);
-            pk[c] = ex2_bf16x2(__byte_perm(__float_as_uint(x0), __float_as_uint(x1), 0x7632));
+            const uint32_t pb = ex2_bf16x2(__byte_perm(__float_as_uint(x0), __float_as_uint(x1), 0x7632));
+            p0 = __uint_as_float(pb << 16);
+            p1 = __uint_as_float(pb & 0xffff0000u);
           } else {
+            float x0, x1;
             unpack2(x2, x0, x1);
-            pk[c] = pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
+            p0 = ex2_approx(x0);
+            p1 = ex2_approx(x1);
           }
+          sr[2 * c] = __float_as_uint(p0);      // probabilities overwrite the scores in place
+          sr[2 * c + 1] = __float_as_uint(p1);
         }
         if (h == 0 && wl == 0 && lane == 0) TRACE(4 + q, 8 * j + 6);
-        if (opaque_true) {  // Block B: row sum of the bf16-rounded probabilities (what the MMA sees)
+        // Block B sits behind a branch whose condition is re-materialised every iteration by a
+        // volatile asm, so the compiler can neither fold it nor unswitch the loop on it.
+        uint32_t opaque_one;
+        asm volatile("mov.u32 %0, 1;" : "=r"(opaque_one));
+        if (opaque_one != 0) {  // Block B: row sum, bf16 pack, TMEM store
           unsigned long long sumA = pack2(0.f, 0.f), sumB = pack2(0.f, 0.f);
+          uint32_t pk[32];
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
-            const unsigned long long p2 =
-                pack2(__uint_as_float(pk[c] << 16), __uint_as_float(pk[c] & 0xffff0000u));
-            if (c & 1) sumB = add2(sumB, p2);
-            else sumA = add2(sumA, p2);
+            const float p0 = __uint_as_float(sr[2 * c]), p1 = __uint_as_float(sr[2 * c + 1]);
+            if (c & 1) sumB = add2(sumB, pack2(p0, p1));
+            else sumA = add2(sumA, pack2(p0, p1));
+            pk[c] = pack_bf16x2(p0, p1);
           }
           if (PV_WAIT_LATE && j > 0 && !pv_waited) {
             mbar_wait(pv_done(q), uint32_t(j - 1) & 1u);  // PV_{j-1} has finished reading P
