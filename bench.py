@@ -210,9 +210,14 @@ def run_ours(args, rank, world, local_rank):
     fm_ms, fm_n = prof["fmha"]
     fmha_flops = 4.0 * BATCH * 8 * SEQ * SEQ * 64  # per launch: QK^T + PV over all heads
     fm_tflops = fmha_flops / (fm_ms / fm_n * 1e-3) / 1e12
-    roofline = {"kernel": "fmha_fwd_kernel<0>", "bound": "tensor", "achieved": fm_tflops,
-                "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": fm_tflops / peaks["tflops_sustained"], "traffic": None,
+    # DRAM bytes per FMHA launch at this shape from the committed `ncu --set full` capture
+    # (profiles/r01_prof_fmha_final_summary.txt: 177.1 MB read + 42.0 MB written; algorithmic
+    # 177 MB qkv in + 59 MB o out) — only valid for the default B=32, T=1801 workload
+    fmha_traffic = 219.07e6 if (BATCH, SEQ) == (32, 1801) else None
+    roofline = {"kernel": "fmha_fwd_kernel<mask=0,emu=1,nq=1,bf16exp=0>", "bound": "tensor",
+                "achieved": fm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": fm_tflops / peaks["tflops_sustained"], "traffic": fmha_traffic,
+                "flops_per_launch": fmha_flops, "launch_ms": fm_ms / fm_n,
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside the step)",
                 "share_of_step": kern["fmha"]["share"]}
     ln_ms, ln_n = prof["layernorm"]
