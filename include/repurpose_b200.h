@@ -10,6 +10,7 @@
  *   rp_soft_nms       <- soft_nms_intervals_cpu            models/softnms.py:3-38
  *   rp_fmha (+ rp_gemm_bf16 / rp_cast_bf16)
  *                     <- MultiHeadAttention.forward        models/transformer.py:52-81
+ *   rp_atiou          <- calculate_tiou + averaging      utils/metrics.py:82-111, inference.py:45-55
  *   rp_load_weight    <- model.load_state_dict(ckpt['model'])  inference.py:33-34 (same key names)
  *
  * Conventions: every pointer is a DEVICE pointer unless stated otherwise; sizes are explicit; the
@@ -113,6 +114,15 @@ int32_t rp_decode_nms(const float* logits, const float* offsets, const int32_t* 
 int32_t rp_soft_nms(const float* scores, const float* segs, const int32_t* n, const int32_t* max_seg,
                     int32_t B, int32_t Nmax, float sigma, float thresh, int32_t Kcap, int32_t* keep,
                     float* kscores, int32_t* counts, void* stream);
+
+/* AtIoU on the device: calculate_tiou (utils/metrics.py:82-111) per video and the
+ * averaging of inference.py:45-55, in float64 with the reference's operation order.
+ * slots [n,1+4K] f32 = [count,(start,end,score,label)*K] per video (the all-gathered layout),
+ * gt [n,Gmax,2] f64, gt_counts [n] i32, thresholds [n_thr<=8] f64 -> per_video [n,n_thr] f64,
+ * out [n_thr+1] f64: mean precision per threshold, then their mean (the reported "average tIoU"). */
+int32_t rp_atiou(const float* slots, int32_t n_videos, int32_t K, const double* gt,
+                 const int32_t* gt_counts, int32_t Gmax, const double* thresholds, int32_t n_thr,
+                 double* per_video, double* out, void* stream);
 
 /* ---- building blocks (also what the unit tests drive) ---------------------------------------- */
 /* D[M,N] = A[M,K] * W[N,K]^T + bias (+ReLU | +residual); A, W bf16 row-major with pitches lda/ldw

@@ -45,6 +45,7 @@ SIGNATURES = {
                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "rp_soft_nms": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_f32, c_i32, c_vp, c_vp,
                             c_vp, c_vp]),
+    "rp_atiou": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "rp_gemm_bf16": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i32,
                              c_i32, c_i32, c_vp]),
     "rp_fmha": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,

@@ -591,6 +591,14 @@ int32_t rp_soft_nms(const float* scores, const float* segs, const int32_t* n, co
                          counts, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int32_t rp_atiou(const float* slots, int32_t n_videos, int32_t K, const double* gt,
+                 const int32_t* gt_counts, int32_t Gmax, const double* thresholds, int32_t n_thr,
+                 double* per_video, double* out, void* stream) {
+  RP_CHECK(slots && gt && gt_counts && thresholds && per_video && out, "rp_atiou: null argument");
+  return launch_atiou(slots, n_videos, K, gt, gt_counts, Gmax, thresholds, n_thr, per_video, out,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
 int32_t rp_gemm_bf16(int32_t epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
                      int64_t ldd, const float* bias, const float* resid, int64_t ldr, int32_t M,
                      int32_t N, int32_t K, void* stream) {

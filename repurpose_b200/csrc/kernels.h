@@ -101,4 +101,11 @@ int launch_soft_nms(const float* scores, const float* segs, const int32_t* n, co
                     int B, int Nmax, float sigma, float thresh, int Kcap, int32_t* keep,
                     float* kscores, int32_t* counts, cudaStream_t stream);
 
+// ---- AtIoU on the device (utils/metrics.py:82-111 + inference.py:45-55), float64, bit-exact ----------
+// slots [n,1+4K] f32 (scheduler layout), gt [n,Gmax,2] f64, gt_counts [n], thresholds [n_thr] f64 ->
+// per_video [n,n_thr] f64 precision, out [n_thr+1] f64 (per-threshold means, then their mean = AtIoU).
+int launch_atiou(const float* slots, int n_videos, int K, const double* gt, const int32_t* gt_counts,
+                 int Gmax, const double* thresholds, int n_thr, double* per_video, double* out,
+                 cudaStream_t stream);
+
 }  // namespace rp

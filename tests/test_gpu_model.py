@@ -357,3 +357,30 @@ def test_atiou_parity_on_a_synthetic_set():
     assert abs(a_ours - a_ref) * 100 <= tol_points, \
         f"AtIoU {100 * a_ours:.3f} vs oracle {100 * a_ref:.3f} (tolerance {tol_points:.2f}, {differing} differing videos)"
     assert same >= n_videos * 0.6, f"only {same}/{n_videos} videos keep the identical segment list"
+
+
+# ------------------------------------------------------------------------------------ AtIoU on device (f4)
+def test_atiou_on_device_is_bit_exact_vs_python_metric():
+    from repurpose_b200.metrics import atiou
+    from repurpose_b200.scheduler import pack_slots
+    rng = np.random.default_rng(3)
+    n, K = 97, 9
+    counts = torch.tensor(rng.integers(0, K + 1, size=n), dtype=torch.int32)
+    centres = torch.tensor(rng.uniform(0, 1800, size=(n, K)), dtype=torch.float32)
+    half = torch.tensor(rng.uniform(5, 45, size=(n, K)), dtype=torch.float32)
+    segs = torch.stack([centres - half, centres + half], -1)
+    scores = torch.rand(n, K)
+    labels = torch.zeros(n, K, dtype=torch.int32)
+    slots = pack_slots(segs, scores, labels, counts).to(DEV)
+    gts = []
+    for v in range(n):
+        g = synth.make_gt_segments(1801, 1000 + v) if v % 7 else []   # some videos without GT
+        if v % 5 == 0 and int(counts[v]) > 0 and g:                    # plant exact / near matches
+            g[0] = [float(segs[v, 0, 0]), float(segs[v, 0, 1])]
+        gts.append(g)
+    avg, by_thr, per_video = atiou(slots, gts)
+    preds = [segs[v, :int(counts[v])].tolist() for v in range(n)]
+    ref_avg, ref_by = mmct.atiou(gts, preds)
+    assert avg == ref_avg, (avg, ref_avg)
+    assert all(by_thr[t] == ref_by[t] for t in ref_by)
+    assert per_video.shape == (n, 5)
