@@ -50,19 +50,31 @@ tiou_precision_kernel(const float* __restrict__ slots, int n_videos, int K, cons
   }
 }
 
-// sequential (video order) accumulation, as Python's sum(): out[t] = mean_v prec[v,t]; out[n_thr] = mean_t
+// Python's sum() over floats (CPython >= 3.12: Neumaier compensated summation, video order).
+struct PySum {
+  double f = 0.0, c = 0.0;
+  __device__ void add(double x) {
+    const double t = __dadd_rn(f, x);
+    if (fabs(f) >= fabs(x)) c = __dadd_rn(c, __dadd_rn(__dsub_rn(f, t), x));
+    else c = __dadd_rn(c, __dadd_rn(__dsub_rn(x, t), f));
+    f = t;
+  }
+  __device__ double result() const { return (c != 0.0 && isfinite(c)) ? __dadd_rn(f, c) : f; }
+};
+
+// out[t] = sum_v(prec[v,t]) / n_videos ; out[n_thr] = sum_t(out[t]) / n_thr   (inference.py:49-53)
 __global__ void atiou_reduce_kernel(const double* __restrict__ prec, int n_videos, int n_thr,
                                     double* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double total = 0.0;
+  PySum total;
   for (int t = 0; t < n_thr; ++t) {
-    double s = 0.0;
-    for (int v = 0; v < n_videos; ++v) s += prec[int64_t(v) * n_thr + t];
-    const double m = s / double(n_videos);
+    PySum s;
+    for (int v = 0; v < n_videos; ++v) s.add(prec[int64_t(v) * n_thr + t]);
+    const double m = s.result() / double(n_videos);
     out[t] = m;
-    total += m;
+    total.add(m);
   }
-  out[n_thr] = total / double(n_thr);
+  out[n_thr] = total.result() / double(n_thr);
 }
 
 }  // namespace

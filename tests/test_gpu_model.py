@@ -382,5 +382,5 @@ def test_atiou_on_device_is_bit_exact_vs_python_metric():
     preds = [segs[v, :int(counts[v])].tolist() for v in range(n)]
     ref_avg, ref_by = mmct.atiou(gts, preds)
     assert avg == ref_avg, (avg, ref_avg)
-    assert all(by_thr[t] == ref_by[t] for t in ref_by)
+    assert all(by_thr[t] == ref_by[t] for t in ref_by), (by_thr, ref_by)
     assert per_video.shape == (n, 5)
