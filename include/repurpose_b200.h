@@ -85,6 +85,17 @@ int32_t rp_forward(rp_handle* h, const float* vis, const float* aud, const float
                    const int32_t* lens, int32_t B, int32_t T, float* out_logits, float* out_offsets,
                    float* out_feats, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Same forward from UNPADDED per-video features (GPU collate): vis / aud hold the videos'
+ * rows back to back ([sum(lens), dim]; video b starts at row row_off[b]), txt likewise from txt_off[b]
+ * with txt_lens[b] rows available (text may be shorter than visual: dataset/RepurposeClip.py:975-980).
+ * Padding rows are materialised as zeros on the device, as preprocessing() does on the host
+ * (dataset/RepurposeClip.py:450-485).  Outputs are padded [B,T,...] exactly like rp_forward. */
+int32_t rp_forward_ragged(rp_handle* h, const float* vis, const float* aud, const float* txt,
+                          const int32_t* row_off, const int32_t* txt_off, const int32_t* txt_lens,
+                          const int32_t* lens, int32_t B, int32_t T, float* out_logits,
+                          float* out_offsets, float* out_feats, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+
 /* Optional in-situ profiler: between begin and end every kernel rp_forward launches is bracketed
  * by CUDA events on the caller's stream; end() returns the summed device time (ms) and launch count
  * per kernel class.  Arrays must hold RP_NUM_TAGS entries. */

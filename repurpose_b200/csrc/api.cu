@@ -399,9 +399,17 @@ int64_t rp_workspace_bytes(const rp_handle* h, int32_t B, int32_t T) {
   return carve(h->cfg, int64_t(B) * T, nullptr).bytes;
 }
 
-int32_t rp_forward(rp_handle* h, const float* vis, const float* aud, const float* txt,
-                   const int32_t* lens, int32_t B, int32_t T, float* out_logits, float* out_offsets,
-                   float* out_feats, void* workspace, int64_t workspace_bytes, void* stream) {
+// Ragged input description (rp_forward_ragged); all null for the padded entry point.
+struct RaggedIn {
+  const int32_t* row_off = nullptr;   // [B] first row of video b in vis / aud
+  const int32_t* txt_off = nullptr;   // [B] first row of video b in txt
+  const int32_t* txt_lens = nullptr;  // [B] rows of text features available for video b
+};
+
+static int32_t forward_core(rp_handle* h, const float* vis, const float* aud, const float* txt,
+                            const RaggedIn& rg, const int32_t* lens, int32_t B, int32_t T,
+                            float* out_logits, float* out_offsets, float* out_feats, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
   RP_CHECK(h && vis && aud && txt && lens && out_logits && out_offsets && out_feats && workspace,
            "rp_forward: null argument");
   RP_CHECK(B > 0 && T > 0, "rp_forward: empty batch");
@@ -442,7 +450,11 @@ int32_t rp_forward(rp_handle* h, const float* vis, const float* aud, const float
 
   // (1) concat + cast, input projection (fp32 out), input_norm + PE -> h, layers[0].norm1 -> u
   __nv_bfloat16* xcat = w.qkv;
-  RUN(RP_TAG_CAST, launch_concat_cast(vis, aud, txt, c.vis_dim, c.aud_dim, c.text_dim, xcat, M, st));
+  if (rg.row_off != nullptr)
+    RUN(RP_TAG_CAST, launch_ragged_concat_cast(vis, aud, txt, c.vis_dim, c.aud_dim, c.text_dim, rg.row_off,
+                                               rg.txt_off, rg.txt_lens, lens, B, T, xcat, st));
+  else
+    RUN(RP_TAG_CAST, launch_concat_cast(vis, aud, txt, c.vis_dim, c.aud_dim, c.text_dim, xcat, M, st));
   RUN(RP_TAG_GEMM_IN, launch_gemm(EPI_BIAS_F32, xcat, Cin, h->w_in, Cin, w.h, D, h->b_in, nullptr, 0, M, D, Cin, st));
   {
     LnArgs a{};
@@ -538,6 +550,25 @@ int32_t rp_forward(rp_handle* h, const float* vis, const float* aud, const float
   RUN(RP_TAG_HEAD_OUT, launch_head_out(a2c, a2r, h->w_c7, h->b_c7, h->w_r7, h->b_r7, out_logits, out_offsets, M, st));
 #undef RUN
   return RP_OK;
+}
+
+int32_t rp_forward(rp_handle* h, const float* vis, const float* aud, const float* txt,
+                   const int32_t* lens, int32_t B, int32_t T, float* out_logits, float* out_offsets,
+                   float* out_feats, void* workspace, int64_t workspace_bytes, void* stream) {
+  return forward_core(h, vis, aud, txt, RaggedIn{}, lens, B, T, out_logits, out_offsets, out_feats,
+                      workspace, workspace_bytes, stream);
+}
+
+int32_t rp_forward_ragged(rp_handle* h, const float* vis, const float* aud, const float* txt,
+                          const int32_t* row_off, const int32_t* txt_off, const int32_t* txt_lens,
+                          const int32_t* lens, int32_t B, int32_t T, float* out_logits,
+                          float* out_offsets, float* out_feats, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+  RP_CHECK(row_off && txt_off && txt_lens, "rp_forward_ragged: null offsets");
+  RaggedIn rg;
+  rg.row_off = row_off; rg.txt_off = txt_off; rg.txt_lens = txt_lens;
+  return forward_core(h, vis, aud, txt, rg, lens, B, T, out_logits, out_offsets, out_feats, workspace,
+                      workspace_bytes, stream);
 }
 
 int32_t rp_profile_begin(rp_handle* h) {

@@ -56,6 +56,40 @@ concat_cast_kernel(const float* __restrict__ vis, const float* __restrict__ aud,
 }
 
 __global__ void __launch_bounds__(256)
+ragged_concat_cast_kernel(const float* __restrict__ vis, const float* __restrict__ aud,
+                          const float* __restrict__ txt, int Cv, int Ca, int Ct,
+                          const int32_t* __restrict__ row_off, const int32_t* __restrict__ txt_off,
+                          const int32_t* __restrict__ txt_lens, const int32_t* __restrict__ lens, int B,
+                          int T, __nv_bfloat16* __restrict__ out) {
+  const int C = Cv + Ca + Ct;
+  const int groups_per_row = C >> 3;
+  const int64_t total = int64_t(B) * T * groups_per_row;
+  for (int64_t g = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; g < total;
+       g += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t m = g / groups_per_row;         // padded row index b*T + t
+    const int c = int(g - m * groups_per_row) << 3;
+    const int b = int(m / T);
+    const int t = int(m - int64_t(b) * T);
+    const float* src = nullptr;
+    if (t < lens[b]) {
+      if (c < Cv) src = vis + (int64_t(row_off[b]) + t) * Cv + c;
+      else if (c < Cv + Ca) src = aud + (int64_t(row_off[b]) + t) * Ca + (c - Cv);
+      else if (t < txt_lens[b]) src = txt + (int64_t(txt_off[b]) + t) * Ct + (c - Cv - Ca);
+    }
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (src != nullptr) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
+      const float4 bq = __ldcs(reinterpret_cast<const float4*>(src) + 1);
+      o.x = pack_bf16x2(a.x, a.y);
+      o.y = pack_bf16x2(a.z, a.w);
+      o.z = pack_bf16x2(bq.x, bq.y);
+      o.w = pack_bf16x2(bq.z, bq.w);
+    }
+    *reinterpret_cast<uint4*>(out + m * C + c) = o;
+  }
+}
+
+__global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n8) {
   for (int64_t g = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; g < n8;
        g += int64_t(gridDim.x) * blockDim.x) {
@@ -224,6 +258,20 @@ int launch_concat_cast(const float* vis, const float* aud, const float* txt, int
   const int64_t groups = M * ((Cv + Ca + Ct) / 8);
   concat_cast_kernel<<<grid_for(groups, 256), 256, 0, stream>>>(
       vis, aud, txt, Cv, Ca, Ct, reinterpret_cast<__nv_bfloat16*>(out_bf16), M);
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+int launch_ragged_concat_cast(const float* vis, const float* aud, const float* txt, int Cv, int Ca, int Ct,
+                              const int32_t* row_off, const int32_t* txt_off, const int32_t* txt_lens,
+                              const int32_t* lens, int B, int T, void* out_bf16, cudaStream_t stream) {
+  RP_CHECK(B > 0 && T > 0, "ragged_concat_cast: empty");
+  RP_CHECK(Cv % 8 == 0 && Ca % 8 == 0 && Ct % 8 == 0, "ragged_concat_cast: dims must be multiples of 8");
+  const int64_t groups = int64_t(B) * T * ((Cv + Ca + Ct) / 8);
+  ragged_concat_cast_kernel<<<grid_for(groups, 256), 256, 0, stream>>>(
+      vis, aud, txt, Cv, Ca, Ct, row_off, txt_off, txt_lens, lens, B, T,
+      reinterpret_cast<__nv_bfloat16*>(out_bf16));
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;

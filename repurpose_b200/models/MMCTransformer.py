@@ -167,23 +167,38 @@ class MMCTransformer(nn.Module):
         """batch: dict with visual_feats [B,T,Cv], audio_feats [B,T,Ca], text_feats [B,T,Ct] fp32,
         masks [B,1,T] bool (True = valid, left-aligned as built by dataset/RepurposeClip.py:528-531),
         labels, segments (passed through).  Returns (masks, cls_logits [B,T,1], offsets [B,T,2],
-        labels, segments, feats [B,T,d_model]) like the reference."""
+        labels, segments, feats [B,T,d_model]) like the reference.
+        A batch from `repurpose_b200.features.collate_ragged` (unpadded rows + offsets) is accepted
+        too: the padding then happens on the device."""
         self._ensure_ready()
         dev = self.device
         vis = self._as_f32(batch["visual_feats"], dev)
         aud = self._as_f32(batch["audio_feats"], dev)
         txt = self._as_f32(batch["text_feats"], dev)
-        masks = batch["masks"]
-        B, T = vis.shape[0], vis.shape[1]
-        lens = masks.to(dev, non_blocking=True).reshape(B, -1).ne(0).sum(dim=1, dtype=torch.int32).contiguous()
+        lib = _lib.load()
+        if batch.get("ragged"):
+            i32 = lambda t: t.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+            lens = i32(batch["lens"])
+            B, T = len(batch["duration"]), int(batch.get("max_len") or max(batch["duration"]))
+            masks = (torch.arange(T, device=dev)[None, :] < lens[:, None]).unsqueeze(1)
+            roff, toff, tlen = i32(batch["row_offsets"]), i32(batch["text_offsets"]), i32(batch["text_lens"])
+        else:
+            masks = batch["masks"]
+            B, T = vis.shape[0], vis.shape[1]
+            lens = masks.to(dev, non_blocking=True).reshape(B, -1).ne(0).sum(dim=1, dtype=torch.int32).contiguous()
         logits = torch.empty(B, T, 1, dtype=torch.float32, device=dev)
         offsets = torch.empty(B, T, 2, dtype=torch.float32, device=dev)
         feats = torch.empty(B, T, self._cfg["d_model"], dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             ws = self._get_workspace(B, T)
-            check(_lib.load().rp_forward(self._handle, ptr(vis), ptr(aud), ptr(txt), ptr(lens), B, T,
-                                         ptr(logits), ptr(offsets), ptr(feats), ptr(ws), ws.numel(),
-                                         cur_stream()), "rp_forward")
+            if batch.get("ragged"):
+                check(lib.rp_forward_ragged(self._handle, ptr(vis), ptr(aud), ptr(txt), ptr(roff), ptr(toff),
+                                            ptr(tlen), ptr(lens), B, T, ptr(logits), ptr(offsets), ptr(feats),
+                                            ptr(ws), ws.numel(), cur_stream()), "rp_forward_ragged")
+            else:
+                check(lib.rp_forward(self._handle, ptr(vis), ptr(aud), ptr(txt), ptr(lens), B, T,
+                                     ptr(logits), ptr(offsets), ptr(feats), ptr(ws), ws.numel(),
+                                     cur_stream()), "rp_forward")
         self._last_lens = lens
         return masks, logits, offsets, batch.get("labels"), batch.get("segments"), feats
 

@@ -114,6 +114,7 @@ class InferencePipeline:
     Host tensors should be pinned (`collate(..., pin=True)`) for the copies to overlap."""
 
     FEATS = ("visual_feats", "audio_feats", "text_feats", "masks")
+    RAGGED = ("visual_feats", "audio_feats", "text_feats", "row_offsets", "text_offsets", "text_lens", "lens")
 
     def __init__(self, model, test_cfg: dict, depth: int = 2):
         self.model, self.cfg, self.depth = model, test_cfg, max(2, depth)
@@ -130,7 +131,7 @@ class InferencePipeline:
         with torch.cuda.stream(self.copy_stream):
             if self._free[slot] is not None:
                 self.copy_stream.wait_event(self._free[slot])
-            for k in self.FEATS:
+            for k in (self.RAGGED if batch.get("ragged") else self.FEATS):
                 src = batch[k]
                 dst = bufs.get(k)
                 if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:

@@ -1,0 +1,35 @@
+"""CPU suite, part 4: feature-file loading and ragged collation (host side of the GPU collate)."""
+import numpy as np
+import torch
+
+from repurpose_b200.features import collate_ragged, load_video_features
+
+
+def test_load_video_features_follows_reference_slicing(tmp_path):
+    rng = np.random.default_rng(0)
+    vis = rng.normal(size=(50, 8)).astype(np.float64)     # extractors may write float64
+    aud = rng.normal(size=(48, 16)).astype(np.float32)    # audio one step shorter than visual
+    txt = rng.normal(size=(45, 4)).astype(np.float32)     # text shorter still: NOT part of the minimum
+    for name, a in (("v", vis), ("a", aud), ("t", txt)):
+        np.save(tmp_path / f"{name}.npy", a)
+    paths = [tmp_path / "v.npy", tmp_path / "a.npy", tmp_path / "t.npy"]
+    full = load_video_features(*paths, time_range=[0, 50.0])
+    assert full["duration"] == 48 and full["visual_feats"].dtype == np.float32
+    assert full["text_feats"].shape[0] == 45                 # dataset/RepurposeClip.py:975-980
+    np.testing.assert_array_equal(full["visual_feats"], vis[:48].astype(np.float32))
+    part = load_video_features(*paths, time_range=[10.7, 30.2], n_labels=15)
+    assert part["duration"] == 15                            # rows [10, 30) then min with the label count
+    np.testing.assert_array_equal(part["audio_feats"], aud[10:25])
+
+
+def test_collate_ragged_layout():
+    vids = [{"visual_feats": torch.full((3, 8), 1.0), "audio_feats": torch.full((3, 16), 2.0),
+             "text_feats": torch.full((2, 8), 3.0)},
+            {"visual_feats": torch.full((5, 8), 4.0), "audio_feats": torch.full((5, 16), 5.0),
+             "text_feats": torch.full((5, 8), 6.0), "video_id": "b"}]
+    b = collate_ragged(vids, pin=False)
+    assert b["ragged"] and b["duration"] == [3, 5] and b["video_id"] == [0, "b"]
+    assert b["visual_feats"].shape == (8, 8) and b["text_feats"].shape == (7, 8)
+    assert b["row_offsets"].tolist() == [0, 3] and b["text_offsets"].tolist() == [0, 2]
+    assert b["text_lens"].tolist() == [2, 5] and b["lens"].tolist() == [3, 5]
+    assert b["visual_feats"][3:].eq(4.0).all() and b["text_feats"][:2].eq(3.0).all()

@@ -384,3 +384,32 @@ def test_atiou_on_device_is_bit_exact_vs_python_metric():
     assert avg == ref_avg, (avg, ref_avg)
     assert all(by_thr[t] == ref_by[t] for t in ref_by), (by_thr, ref_by)
     assert per_video.shape == (n, 5)
+
+
+# ------------------------------------------------------------------------------------ GPU collate (f2)
+def test_ragged_gpu_collate_equals_padded_path():
+    from repurpose_b200.features import collate_ragged
+    from repurpose_b200.scheduler import InferencePipeline, collate
+    torch.manual_seed(17)
+    m = MMCTransformer(512, 2048, 384, 512, 2, 3, 3, 8)
+    m.load_state_dict(synth.bias_reg_head({k: v.clone() for k, v in m.state_dict().items()}))
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(4)
+    vids = []
+    for i, t in enumerate([310, 64, 129, 257]):
+        tt = t - 3 if i == 1 else t          # one video with a shorter text track
+        vids.append({"visual_feats": torch.randn(t, 512, generator=g), "audio_feats": torch.randn(t, 2048, generator=g),
+                     "text_feats": torch.randn(tt, 384, generator=g), "video_id": f"v{i}"})
+    padded_vids = [dict(v) for v in vids]
+    padded_vids[1]["text_feats"] = torch.cat([vids[1]["text_feats"], torch.zeros(3, 384)])  # what preprocessing() pads
+    pb = collate(padded_vids)
+    dpb = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in pb.items()}
+    _, l0, o0, _, _, f0 = m(dpb)
+    rb = collate_ragged(vids)
+    masks, l1, o1, _, _, f1 = m(rb)
+    assert torch.equal(masks.cpu(), pb["masks"])
+    assert torch.equal(l0, l1) and torch.equal(o0, o1) and torch.equal(f0, f1)   # same bytes in, same bytes out
+    want = m.inference_(dpb, synth.TEST_CFG, to_host=True)
+    got = list(InferencePipeline(m, synth.TEST_CFG).run([rb]))[0]
+    for a, b in zip(got, want):
+        assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["segments"], b["segments"])
