@@ -70,11 +70,14 @@ constexpr bool PV_WAIT_LATE = RP_PV_WAIT_LATE != 0;  // wait for PV_{j-1} only r
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units; stale max keeps p <= 2^8
 constexpr float MASK_FILL_LOG2 = -1.0e9f * 1.4426950408889634f;
 
+#ifndef RP_TRACE_Z
+#define RP_TRACE_Z 1
+#endif
 #ifdef RP_FMHA_TRACE
 __device__ unsigned long long g_fmha_trace[8 * 512];  // [role][event] = clock64
 #define TRACE(role, idx)                                                              \
   do {                                                                                \
-    if (blockIdx.x == 2 && blockIdx.y == 3 && blockIdx.z == 1 && (idx) < 512)          \
+    if (blockIdx.x == 2 && blockIdx.y == 3 && blockIdx.z == RP_TRACE_Z && (idx) < 512) \
       g_fmha_trace[(role) * 512 + (idx)] = clock64();                                  \
   } while (0)
 #else
@@ -87,7 +90,9 @@ struct FmhaParams {
   const uint8_t* mask;
   int64_t mask_b_stride, mask_q_stride;
   int pingpong;  // NQ=2 only: the two query tiles take turns in the exp phase (named barriers 11/12)
+  int skew;      // cycles every second CTA landing on an SM waits before it starts (phase offset)
 };
+__device__ unsigned int g_sm_arrivals[1024];
 
 // ---- packed f32x2 helpers (sm_100 FFMA2/FADD2) ---------------------------------------------------
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
@@ -198,6 +203,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     fence_mbar_init();
   }
   if (warp == C::MMA_WARP) tmem_alloc<TMEM_COLS>(base + SMEM_BAR_OFF + 176);
+  if (p.skew > 0 && threadIdx.x == 0) {
+    // Co-resident CTAs that start together stay in phase (their MUFU-heavy and MUFU-idle phases
+    // coincide); delaying every second arrival on an SM offsets them.
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (atomicAdd(&g_sm_arrivals[smid & 1023u], 1u) & 1u) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.skew) {}
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -568,6 +583,8 @@ int launch_fmha(const FmhaArgs& a, cudaStream_t stream) {
            "fmha: pointers must be 16-byte aligned");
   RP_CHECK(a.mask_mode == 0 || (a.mask_mode == 1 && a.mask != nullptr), "fmha: bad mask arguments");
   RP_CHECK(a.B <= 65535 && a.H <= 65535, "fmha: grid too large");
+  static const int impl = getenv("RP_FMHA_IMPL") ? atoi(getenv("RP_FMHA_IMPL")) : 1;
+  if (impl == 2) return launch_fmha2(a, stream);
 
   const uint64_t cols = uint64_t(a.H) * HD;
   CUtensorMap tmQ, tmK, tmV, tmO;
@@ -579,7 +596,8 @@ int launch_fmha(const FmhaArgs& a, cudaStream_t stream) {
   if ((rc = make_tmap_3d(&tmO, bf, a.o, cols, a.Tq, a.B, a.ldo * 2, a.bso * 2, HD, QT))) return rc;
 
   static const int pp = getenv("RP_FMHA_PINGPONG") ? atoi(getenv("RP_FMHA_PINGPONG")) : 0;
-  FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride, pp};
+  static const int skew = getenv("RP_FMHA_SKEW") ? atoi(getenv("RP_FMHA_SKEW")) : 0;
+  FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride, pp, skew};
   // RP_FMHA_NQ: query tiles per CTA (2 = one big CTA per SM, 1 = two independent CTAs per SM)
   static const int nq_cfg = getenv("RP_FMHA_NQ") ? atoi(getenv("RP_FMHA_NQ")) : 1;
   // RP_FMHA_BF16EXP: 1 = packed bf16x2 MUFU exp2 (experiment: MUFU.EX2.BF16x2 costs 16 cycles per

@@ -66,6 +66,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (mbarrier.test_wait): lets a thread ask early and consume the answer later, so
+// that the round trip to the barrier unit overlaps other work instead of stalling an in-order warp.
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a protocol bug becomes a trap (visible as a CUDA error on the host) instead of a
 // hung GPU.  The timer is only consulted every 4096 failed probes, so the fast path is one try_wait.
 #ifndef RP_MBAR_TIMEOUT_NS
@@ -86,6 +101,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       }
     }
   }
+}
+
+// Lean wait for hot loops whose barriers are known to complete (no timeout bookkeeping: the inlined
+// slow path of mbar_wait costs instruction-cache footprint in large unrolled loops).
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+// Pins a value in a register: ptxas cannot rematerialise it from its definition at every use.
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -314,6 +341,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// warp-group register re-allocation (all warps of the CTA must reach a matching total)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(

@@ -6,7 +6,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from repurpose_b200 import _lib
 from repurpose_b200._lib import check, cur_stream, ptr
 lib = _lib.load()
-B, T, H, D = 4, 1801, 8, 512
+import os
+B, T, H, D = int(os.environ.get('TRACE_B', 4)), 1801, 8, 512
 qkv = torch.randn(B, T, 3 * D, device="cuda"); qkv[..., :D] *= 1.4427 / 8; qkv = qkv.bfloat16()
 o = torch.empty(B, T, D, dtype=torch.bfloat16, device="cuda")
 for _ in range(2):
