@@ -583,8 +583,10 @@ int launch_fmha(const FmhaArgs& a, cudaStream_t stream) {
            "fmha: pointers must be 16-byte aligned");
   RP_CHECK(a.mask_mode == 0 || (a.mask_mode == 1 && a.mask != nullptr), "fmha: bad mask arguments");
   RP_CHECK(a.B <= 65535 && a.H <= 65535, "fmha: grid too large");
-  static const int impl = getenv("RP_FMHA_IMPL") ? atoi(getenv("RP_FMHA_IMPL")) : 1;
-  if (impl == 2) return launch_fmha2(a, stream);
+  // RP_FMHA_IMPL: 2 (default) = row-per-thread pipelined kernel (fmha2.cu); 1 = this file's kernel
+  // (two threads per score row with a shared-memory max exchange), kept for A/B measurements.
+  static const int impl = getenv("RP_FMHA_IMPL") ? atoi(getenv("RP_FMHA_IMPL")) : 2;
+  if (impl != 1) return launch_fmha2(a, stream);
 
   const uint64_t cols = uint64_t(a.H) * HD;
   CUtensorMap tmQ, tmK, tmV, tmO;

@@ -66,6 +66,11 @@ struct Cfg {
   static constexpr int SOFTMAX_REGS = NQ == 2 ? 232 : 216;
   static constexpr int AUX_REGS = 40;
 };
+#ifndef RP_FMHA_CHUNK
+#define RP_FMHA_CHUNK 16
+#endif
+constexpr int CH = RP_FMHA_CHUNK;  // scores per pipeline step (16 or 32)
+constexpr int NCH = KT / CH;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units; stale max keeps p <= 2^8
 constexpr float MASK_FILL_LOG2 = -1.0e9f * 1.4426950408889634f;
 
@@ -372,12 +377,12 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int one = int(pin_u32(uint32_t(p.one)));
       const bool lane0 = pin_u32(lane == 0 ? 1u : 0u) != 0u;
 
-      // running max of chunk c (16 scores)
+      // running max of chunk c (CH scores)
       auto max_chunk = [&](int c, float& mx0, float& mx1) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          mx0 = max3(mx0, __uint_as_float(xs[16 * c + i]), __uint_as_float(xs[16 * c + i + 1]));
-          mx1 = max3(mx1, __uint_as_float(xs[16 * c + i + 2]), __uint_as_float(xs[16 * c + i + 3]));
+        for (int i = 0; i < CH; i += 4) {
+          mx0 = max3(mx0, __uint_as_float(xs[CH * c + i]), __uint_as_float(xs[CH * c + i + 1]));
+          mx1 = max3(mx1, __uint_as_float(xs[CH * c + i + 2]), __uint_as_float(xs[CH * c + i + 3]));
         }
       };
       // Masking is needed for the last (partial) key tile only — and for every tile with an explicit
@@ -396,7 +401,7 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         mx0 = mx1 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) max_chunk(c, mx0, mx1);
+        for (int c = 0; c < NCH; ++c) max_chunk(c, mx0, mx1);
       };
 
       if (n_kv > 0) {
@@ -418,7 +423,7 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mask_tile(0, mx0, mx1);
         } else {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) max_chunk(c, mx0, mx1);
+          for (int c = 0; c < NCH; ++c) max_chunk(c, mx0, mx1);
         }
         m = fmaxf(mx0, mx1);
       }
@@ -431,27 +436,27 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t probe_pv = 0, probe_s = 0;
         if (tracer) TRACE(4, 2 * j);
 #pragma unroll
-        for (int s = 0; s <= 8; ++s) {
+        for (int s = 0; s <= NCH; ++s) {
           // Half h of P may be overwritten once P V_{j-1,h} has completed, and half h of the next
           // tile's scores (a dummy after the last tile) read once S_{j+1,h} is in TMEM: waited for
-          // ahead of the step that first touches them, outside its basic block.
-          if (s == 1 || s == 5) {
+          // ahead of the step that first touches them.
+          if (s == 1 || s == NCH / 2 + 1) {
             // (probed one step ago: the answer is normally "complete" and already in a register)
-            if (!probe_pv) mbar_wait_spin(pv_done(q, s / 4), par_next);
-            if (!probe_s) mbar_wait_spin(s_full(q, s / 4), par_next);
+            if (!probe_pv) mbar_wait_spin(pv_done(q, s > 1), par_next);
+            if (!probe_s) mbar_wait_spin(s_full(q, s > 1), par_next);
             tc_fence_after();
           }
-          if ((s % RP_FMHA_FENCE_EVERY) != 0 || opaque_true(j, one)) {  // one basic block per step: E, M and D interleave freely
+          if ((s % RP_FMHA_FENCE_EVERY) != 0 || opaque_true(j, one)) {
             if (tracer) TRACE(5, 16 * j + s);
-            if (s == 0 || s == 4) {
-              probe_pv = j > 0 ? mbar_test_wait(pv_done(q, s / 4), par_next) : 1u;
-              probe_s = mbar_test_wait(s_full(q, s / 4), par_next);
+            if (s == 0 || s == NCH / 2) {
+              probe_pv = j > 0 ? mbar_test_wait(pv_done(q, s > 0), par_next) : 1u;
+              probe_s = mbar_test_wait(s_full(q, s > 0), par_next);
             }
             // ---- E(s): exp2 of chunk s, in place
-            if (s < 8) {
+            if (s < NCH) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int c0 = 16 * s + 2 * i;
+              for (int i = 0; i < CH / 2; ++i) {
+                const int c0 = CH * s + 2 * i;
                 const unsigned long long x2 =
                     add2(pack2(__uint_as_float(xs[c0]), __uint_as_float(xs[c0 + 1])), negm2);
                 float p0, p1;
@@ -472,9 +477,9 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               tmem_ld_wait();
               max_chunk(s - 2, mx0, mx1);
             }
-            if (s == 5) {
-              // first halves are complete: P columns [0,32) stored (D(3), step 4) and the next tile's
-              // score columns [0,64) read (loads of steps 1..4, waited for above)
+            if (s == NCH / 2 + 1) {
+              // first halves are complete: P columns [0,32) stored (step NCH/2) and the next tile's
+              // score columns [0,64) read (loads of steps 1..NCH/2, waited for above)
               tmem_st_wait();
               tc_fence_before();
               __syncwarp();
@@ -486,16 +491,21 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             // ---- D(s-1): consume chunk s-1 (row sum, bf16 pack, P store), refill its registers
             if (s >= 1) {
               const int c = s - 1;
-              uint32_t pk[8];
+              uint32_t pk[CH / 2];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float p0 = __uint_as_float(xs[16 * c + 2 * i]), p1 = __uint_as_float(xs[16 * c + 2 * i + 1]);
+              for (int i = 0; i < CH / 2; ++i) {
+                const float p0 = __uint_as_float(xs[CH * c + 2 * i]), p1 = __uint_as_float(xs[CH * c + 2 * i + 1]);
                 if (i & 1) lsumB = add2(lsumB, pack2(p0, p1));
                 else lsumA = add2(lsumA, pack2(p0, p1));
                 pk[i] = pack_bf16x2(p0, p1);
               }
-              tmem_st8(t_p + 8 * c, pk);
-              tmem_ld16(t_s + 16 * c, xs + 16 * c);
+              if (CH == 16) {
+                tmem_st8(t_p + (CH / 2) * c, pk);
+                tmem_ld16(t_s + CH * c, xs + CH * c);
+              } else {
+                tmem_st16(t_p + (CH / 2) * c, pk);
+                tmem_ld32(t_s + CH * c, xs + CH * c);
+              }
             }
           }
         }
@@ -503,7 +513,7 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // ---- tail: second halves
         tmem_st_wait();
         tmem_ld_wait();
-        max_chunk(7, mx0, mx1);
+        max_chunk(NCH - 1, mx0, mx1);
         tc_fence_before();
         __syncwarp();
         if (lane0) {
