@@ -135,7 +135,7 @@ def run_reference(args, rank):
 
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from oracle import synth  # synthetic inputs only; the oracle compute is used for cpu_baseline below
+    from repurpose_b200 import synth  # synthetic inputs (the oracle is only used by the cpu_baseline leg)
     from repurpose_b200 import _lib
     from repurpose_b200.models.MMCTransformer import MMCTransformer
     from repurpose_b200.scheduler import pack_slots

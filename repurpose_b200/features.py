@@ -62,3 +62,23 @@ def collate_ragged(videos: Sequence[dict], pin: bool = True) -> dict:
             "lens": torch.tensor(lens, dtype=torch.int32),
             "video_id": [v.get("video_id", i) for i, v in enumerate(videos)],
             "duration": lens, "labels": None, "segments": None}
+
+
+def ragged_batch(videos: Sequence[dict]) -> dict:
+    """Zero-copy variant of `collate_ragged`: the batch only references the per-video arrays
+    (`parts`), and the host->device stage copies each one straight to its row offset of the device
+    buffers (`InferencePipeline`), so the host never touches the feature bytes.  Sources should be
+    pinned torch tensors for the copies to be asynchronous."""
+    lens = [int(v["visual_feats"].shape[0]) for v in videos]
+    tlens = [min(int(v["text_feats"].shape[0]), l) for v, l in zip(videos, lens)]
+    off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    toff = np.concatenate([[0], np.cumsum(tlens)[:-1]]).astype(np.int32)
+    as_t = lambda a: torch.as_tensor(a, dtype=torch.float32)
+    return {"ragged": True,
+            "parts": {"visual_feats": [as_t(v["visual_feats"][:l]) for v, l in zip(videos, lens)],
+                      "audio_feats": [as_t(v["audio_feats"][:l]) for v, l in zip(videos, lens)],
+                      "text_feats": [as_t(v["text_feats"][:l]) for v, l in zip(videos, tlens)]},
+            "row_offsets": torch.from_numpy(off), "text_offsets": torch.from_numpy(toff),
+            "text_lens": torch.tensor(tlens, dtype=torch.int32), "lens": torch.tensor(lens, dtype=torch.int32),
+            "video_id": [v.get("video_id", i) for i, v in enumerate(videos)],
+            "duration": lens, "labels": None, "segments": None}

@@ -172,6 +172,11 @@ class MMCTransformer(nn.Module):
         too: the padding then happens on the device."""
         self._ensure_ready()
         dev = self.device
+        if batch.get("parts") is not None:  # zero-copy ragged batch used outside the pipeline
+            batch = dict(batch)
+            for k, ts in batch.pop("parts").items():
+                batch[k] = torch.cat([t.to(dev, non_blocking=True) for t in ts]) if sum(int(t.shape[0]) for t in ts) \
+                    else torch.zeros(1, int(ts[0].shape[1]), device=dev)
         vis = self._as_f32(batch["visual_feats"], dev)
         aud = self._as_f32(batch["audio_feats"], dev)
         txt = self._as_f32(batch["text_feats"], dev)

@@ -124,6 +124,16 @@ class InferencePipeline:
         self._free = [None] * self.depth                      # event: compute that read slot is done
         self._host_out = [None] * self.depth
 
+    def _buffer(self, bufs: dict, key: str, shape, dtype) -> torch.Tensor:
+        """grow-only device staging buffer for `key`, viewed with `shape`"""
+        n = 1
+        for d in shape:
+            n *= int(d)
+        flat = bufs.get(key)
+        if flat is None or flat.dtype != dtype or flat.numel() < n:
+            flat = bufs[key] = torch.empty(max(n, 1), dtype=dtype, device=self.dev)
+        return flat[:n].view(*shape)
+
     def _stage(self, slot: int, batch: dict) -> dict:
         """enqueue the H2D copies of `batch` into staging slot `slot` on the copy stream"""
         bufs = self._bufs[slot]
@@ -131,13 +141,24 @@ class InferencePipeline:
         with torch.cuda.stream(self.copy_stream):
             if self._free[slot] is not None:
                 self.copy_stream.wait_event(self._free[slot])
+            parts = batch.get("parts")
             for k in (self.RAGGED if batch.get("ragged") else self.FEATS):
-                src = batch[k]
-                dst = bufs.get(k)
-                if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:
-                    dst = bufs[k] = torch.empty(src.shape, dtype=src.dtype, device=self.dev)
-                dst.copy_(src, non_blocking=True)
+                if parts is not None and k in parts:
+                    # zero-copy ragged batch: every video goes straight to its row offset
+                    rows = sum(int(t.shape[0]) for t in parts[k])
+                    dst = self._buffer(bufs, k, (max(rows, 1), int(parts[k][0].shape[1])), torch.float32)
+                    pos = 0
+                    for t in parts[k]:
+                        n = int(t.shape[0])
+                        if n:
+                            dst[pos:pos + n].copy_(t, non_blocking=True)
+                        pos += n
+                else:
+                    src = batch[k]
+                    dst = self._buffer(bufs, k, tuple(src.shape), src.dtype)
+                    dst.copy_(src, non_blocking=True)
                 dbatch[k] = dst
+            dbatch.pop("parts", None)
             ready = torch.cuda.Event()
             ready.record(self.copy_stream)
         return dbatch, ready

@@ -413,3 +413,26 @@ def test_ragged_gpu_collate_equals_padded_path():
     got = list(InferencePipeline(m, synth.TEST_CFG).run([rb]))[0]
     for a, b in zip(got, want):
         assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["segments"], b["segments"])
+
+
+def test_zero_copy_ragged_batch_through_pipeline():
+    from repurpose_b200.features import collate_ragged, ragged_batch
+    from repurpose_b200.scheduler import InferencePipeline
+    torch.manual_seed(19)
+    m = MMCTransformer(512, 2048, 384, 512, 2, 3, 3, 8)
+    m.load_state_dict(synth.bias_reg_head({k: v.clone() for k, v in m.state_dict().items()}))
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(5)
+    def mk(ts):
+        return [{"visual_feats": torch.randn(t, 512, generator=g).pin_memory(), "audio_feats": torch.randn(t, 2048, generator=g).pin_memory(),
+                 "text_feats": torch.randn(t, 384, generator=g).pin_memory(), "video_id": i} for i, t in enumerate(ts)]
+    sets = [mk([200, 130, 77]), mk([300, 64]), mk([150, 150, 150, 90])]      # varying row totals: staging buffers grow and get re-viewed
+    want = [m.inference_(collate_ragged(v, pin=False), synth.TEST_CFG, to_host=True) for v in sets]
+    got = list(InferencePipeline(m, synth.TEST_CFG).run(ragged_batch(v) for v in sets))
+    direct = m.inference_(ragged_batch(sets[0]), synth.TEST_CFG, to_host=True)     # `parts` outside the pipeline
+    for a, b in zip(direct, want[0]):
+        assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["segments"], b["segments"])
+    for gs, ws in zip(got, want):
+        assert len(gs) == len(ws)
+        for a, b in zip(gs, ws):
+            assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["segments"], b["segments"]) and torch.equal(a["scores"], b["scores"])

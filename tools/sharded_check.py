@@ -8,7 +8,7 @@ import argparse, os, sys
 from pathlib import Path
 import torch, torch.distributed as dist
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-from oracle import synth
+from repurpose_b200 import synth
 from repurpose_b200.models.MMCTransformer import MMCTransformer
 from repurpose_b200 import scheduler as S
 
