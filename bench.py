@@ -144,6 +144,9 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # pinned host buffers on the GPU's own NUMA node (matters for the end-to-end arm at N > 1)
+    from repurpose_b200.affinity import bind_to_gpu_numa
+    placement = bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -265,7 +268,7 @@ def run_ours(args, rank, world, local_rank):
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(BATCH * slot * 4),
            "ms_per_step": ms_e2e / args.steps, "segments_last_step": int(sum(len(r["scores"]) for r in res)),
            "api": "repurpose_b200.scheduler.InferencePipeline.run (double-buffered H2D/compute/D2H)",
-           "serial_inference__ms_per_step": ms_serial}
+           "serial_inference__ms_per_step": ms_serial, "host_numa_node": placement["numa_node"]}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -34,6 +34,8 @@ def main():
     lr = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
+    from repurpose_b200.affinity import bind_to_gpu_numa
+    placement = bind_to_gpu_numa(lr)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
@@ -97,7 +99,7 @@ def main():
                           "seconds": dt.item(), "mean_len": float(np.mean(lens)), "batch": a.batch,
                           "collate": "host-padded" if a.padded else "gpu (ragged rows over PCIe)",
                           "padding_efficiency": pad_eff, "segments": int(counts.sum().item()),
-                          "videos_with_segments": int((counts > 0).sum().item()),
+                          "videos_with_segments": int((counts > 0).sum().item()), "host_numa_node_rank0": placement["numa_node"],
                           "timing": "host wall clock around pipeline + all-gather, max over ranks; includes host collation and H2D"}))
     if world > 1:
         dist.barrier()
