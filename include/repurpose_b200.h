@@ -96,6 +96,18 @@ int32_t rp_forward_ragged(rp_handle* h, const float* vis, const float* aud, cons
                           float* out_offsets, float* out_feats, void* workspace,
                           int64_t workspace_bytes, void* stream);
 
+/* Same as rp_forward_ragged for feature rows stored as bf16 (feature files converted once, offline):
+ * the first thing the forward does with fp32 features is round them to bf16 (concat + cast feeding the
+ * bf16 input projection), so results are bit-identical to rp_forward_ragged on the fp32 originals
+ * while the host->device copy — the end-to-end bound of this path — moves half the bytes
+ * (replaces the fp32 `.npy` load of dataset/RepurposeClip.py:415-446 for pre-converted
+ * features). vis/aud/txt: bf16 [sum T, C]. */
+int32_t rp_forward_ragged_bf16(rp_handle* h, const void* vis, const void* aud, const void* txt,
+                          const int32_t* row_off, const int32_t* txt_off, const int32_t* txt_lens,
+                          const int32_t* lens, int32_t B, int32_t T, float* out_logits,
+                          float* out_offsets, float* out_feats, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+
 /* Optional in-situ profiler: between begin and end every kernel rp_forward launches is bracketed
  * by CUDA events on the caller's stream; end() returns the summed device time (ms) and launch count
  * per kernel class.  Arrays must hold RP_NUM_TAGS entries. */

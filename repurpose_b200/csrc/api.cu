@@ -404,12 +404,16 @@ struct RaggedIn {
   const int32_t* row_off = nullptr;   // [B] first row of video b in vis / aud
   const int32_t* txt_off = nullptr;   // [B] first row of video b in txt
   const int32_t* txt_lens = nullptr;  // [B] rows of text features available for video b
+  bool bf16 = false;                  // feature rows are bf16 (pre-converted feature files) instead of fp32
 };
 
-static int32_t forward_core(rp_handle* h, const float* vis, const float* aud, const float* txt,
+static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, const void* txt_v,
                             const RaggedIn& rg, const int32_t* lens, int32_t B, int32_t T,
                             float* out_logits, float* out_offsets, float* out_feats, void* workspace,
                             int64_t workspace_bytes, void* stream) {
+  const float* vis = static_cast<const float*>(vis_v);
+  const float* aud = static_cast<const float*>(aud_v);
+  const float* txt = static_cast<const float*>(txt_v);
   RP_CHECK(h && vis && aud && txt && lens && out_logits && out_offsets && out_feats && workspace,
            "rp_forward: null argument");
   RP_CHECK(B > 0 && T > 0, "rp_forward: empty batch");
@@ -451,7 +455,7 @@ static int32_t forward_core(rp_handle* h, const float* vis, const float* aud, co
   // (1) concat + cast, input projection (fp32 out), input_norm + PE -> h, layers[0].norm1 -> u
   __nv_bfloat16* xcat = w.qkv;
   if (rg.row_off != nullptr)
-    RUN(RP_TAG_CAST, launch_ragged_concat_cast(vis, aud, txt, c.vis_dim, c.aud_dim, c.text_dim, rg.row_off,
+    RUN(RP_TAG_CAST, launch_ragged_concat_cast(vis_v, aud_v, txt_v, rg.bf16, c.vis_dim, c.aud_dim, c.text_dim, rg.row_off,
                                                rg.txt_off, rg.txt_lens, lens, B, T, xcat, st));
   else
     RUN(RP_TAG_CAST, launch_concat_cast(vis, aud, txt, c.vis_dim, c.aud_dim, c.text_dim, xcat, M, st));
@@ -567,6 +571,18 @@ int32_t rp_forward_ragged(rp_handle* h, const float* vis, const float* aud, cons
   RP_CHECK(row_off && txt_off && txt_lens, "rp_forward_ragged: null offsets");
   RaggedIn rg;
   rg.row_off = row_off; rg.txt_off = txt_off; rg.txt_lens = txt_lens;
+  return forward_core(h, vis, aud, txt, rg, lens, B, T, out_logits, out_offsets, out_feats, workspace,
+                      workspace_bytes, stream);
+}
+
+int32_t rp_forward_ragged_bf16(rp_handle* h, const void* vis, const void* aud, const void* txt,
+                               const int32_t* row_off, const int32_t* txt_off, const int32_t* txt_lens,
+                               const int32_t* lens, int32_t B, int32_t T, float* out_logits,
+                               float* out_offsets, float* out_feats, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
+  RP_CHECK(row_off && txt_off && txt_lens, "rp_forward_ragged_bf16: null offsets");
+  RaggedIn rg;
+  rg.row_off = row_off; rg.txt_off = txt_off; rg.txt_lens = txt_lens; rg.bf16 = true;
   return forward_core(h, vis, aud, txt, rg, lens, B, T, out_logits, out_offsets, out_feats, workspace,
                       workspace_bytes, stream);
 }

@@ -61,8 +61,8 @@ int launch_concat_cast(const float* vis, const float* aud, const float* txt, int
 // GPU collate: per-video features stored back to back (no padding) -> padded bf16
 // [B,T,Cv+Ca+Ct]; rows t >= lens[b] (and text rows t >= txt_lens[b]) are zero, exactly what
 // dataset/RepurposeClip.py:450-485 pads with.
-int launch_ragged_concat_cast(const float* vis, const float* aud, const float* txt, int Cv, int Ca, int Ct,
-                              const int32_t* row_off, const int32_t* txt_off, const int32_t* txt_lens,
+int launch_ragged_concat_cast(const void* vis, const void* aud, const void* txt, bool in_bf16, int Cv, int Ca,
+                              int Ct, const int32_t* row_off, const int32_t* txt_off, const int32_t* txt_lens,
                               const int32_t* lens, int B, int T, void* out_bf16, cudaStream_t stream);
 // generic fp32 -> bf16 cast of a contiguous buffer (n % 8 == 0)
 int launch_cast_bf16(const float* in, void* out_bf16, int64_t n, cudaStream_t stream);

@@ -106,7 +106,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // Lean wait for hot loops whose barriers are known to complete (no timeout bookkeeping: the inlined
 // slow path of mbar_wait costs instruction-cache footprint in large unrolled loops).
 __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++polls > (1u << 26)) __trap();  // seconds of polling: a protocol bug must not hang the GPU
+  }
 }
 // Pins a value in a register: ptxas cannot rematerialise it from its definition at every use.
 __device__ __forceinline__ uint32_t pin_u32(uint32_t v) {

@@ -55,9 +55,10 @@ concat_cast_kernel(const float* __restrict__ vis, const float* __restrict__ aud,
   }
 }
 
+template <typename IN>
 __global__ void __launch_bounds__(256)
-ragged_concat_cast_kernel(const float* __restrict__ vis, const float* __restrict__ aud,
-                          const float* __restrict__ txt, int Cv, int Ca, int Ct,
+ragged_concat_cast_kernel(const IN* __restrict__ vis, const IN* __restrict__ aud,
+                          const IN* __restrict__ txt, int Cv, int Ca, int Ct,
                           const int32_t* __restrict__ row_off, const int32_t* __restrict__ txt_off,
                           const int32_t* __restrict__ txt_lens, const int32_t* __restrict__ lens, int B,
                           int T, __nv_bfloat16* __restrict__ out) {
@@ -70,7 +71,7 @@ ragged_concat_cast_kernel(const float* __restrict__ vis, const float* __restrict
     const int c = int(g - m * groups_per_row) << 3;
     const int b = int(m / T);
     const int t = int(m - int64_t(b) * T);
-    const float* src = nullptr;
+    const IN* src = nullptr;
     if (t < lens[b]) {
       if (c < Cv) src = vis + (int64_t(row_off[b]) + t) * Cv + c;
       else if (c < Cv + Ca) src = aud + (int64_t(row_off[b]) + t) * Ca + (c - Cv);
@@ -78,12 +79,16 @@ ragged_concat_cast_kernel(const float* __restrict__ vis, const float* __restrict
     }
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
     if (src != nullptr) {
-      const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
-      const float4 bq = __ldcs(reinterpret_cast<const float4*>(src) + 1);
-      o.x = pack_bf16x2(a.x, a.y);
-      o.y = pack_bf16x2(a.z, a.w);
-      o.z = pack_bf16x2(bq.x, bq.y);
-      o.w = pack_bf16x2(bq.z, bq.w);
+      if (sizeof(IN) == 4) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(src));
+        const float4 bq = __ldcs(reinterpret_cast<const float4*>(src) + 1);
+        o.x = pack_bf16x2(a.x, a.y);
+        o.y = pack_bf16x2(a.z, a.w);
+        o.z = pack_bf16x2(bq.x, bq.y);
+        o.w = pack_bf16x2(bq.z, bq.w);
+      } else {
+        o = __ldcs(reinterpret_cast<const uint4*>(src));  // features already stored as bf16
+      }
     }
     *reinterpret_cast<uint4*>(out + m * C + c) = o;
   }
@@ -263,15 +268,23 @@ int launch_concat_cast(const float* vis, const float* aud, const float* txt, int
   return RP_OK;
 }
 
-int launch_ragged_concat_cast(const float* vis, const float* aud, const float* txt, int Cv, int Ca, int Ct,
-                              const int32_t* row_off, const int32_t* txt_off, const int32_t* txt_lens,
+int launch_ragged_concat_cast(const void* vis, const void* aud, const void* txt, bool in_bf16, int Cv, int Ca,
+                              int Ct, const int32_t* row_off, const int32_t* txt_off, const int32_t* txt_lens,
                               const int32_t* lens, int B, int T, void* out_bf16, cudaStream_t stream) {
   RP_CHECK(B > 0 && T > 0, "ragged_concat_cast: empty");
   RP_CHECK(Cv % 8 == 0 && Ca % 8 == 0 && Ct % 8 == 0, "ragged_concat_cast: dims must be multiples of 8");
   const int64_t groups = int64_t(B) * T * ((Cv + Ca + Ct) / 8);
-  ragged_concat_cast_kernel<<<grid_for(groups, 256), 256, 0, stream>>>(
-      vis, aud, txt, Cv, Ca, Ct, row_off, txt_off, txt_lens, lens, B, T,
-      reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  auto* out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  if (in_bf16) {
+    using T16 = __nv_bfloat16;
+    ragged_concat_cast_kernel<T16><<<grid_for(groups, 256), 256, 0, stream>>>(
+        static_cast<const T16*>(vis), static_cast<const T16*>(aud), static_cast<const T16*>(txt), Cv, Ca, Ct,
+        row_off, txt_off, txt_lens, lens, B, T, out);
+  } else {
+    ragged_concat_cast_kernel<float><<<grid_for(groups, 256), 256, 0, stream>>>(
+        static_cast<const float*>(vis), static_cast<const float*>(aud), static_cast<const float*>(txt), Cv, Ca, Ct,
+        row_off, txt_off, txt_lens, lens, B, T, out);
+  }
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;

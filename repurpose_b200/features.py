@@ -73,7 +73,8 @@ def ragged_batch(videos: Sequence[dict]) -> dict:
     tlens = [min(int(v["text_feats"].shape[0]), l) for v, l in zip(videos, lens)]
     off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
     toff = np.concatenate([[0], np.cumsum(tlens)[:-1]]).astype(np.int32)
-    as_t = lambda a: torch.as_tensor(a, dtype=torch.float32)
+    def as_t(a):  # fp32 like the reference's loader, or bf16 rows converted once with `to_bf16`
+        return a if torch.is_tensor(a) and a.dtype == torch.bfloat16 else torch.as_tensor(a, dtype=torch.float32)
     return {"ragged": True,
             "parts": {"visual_feats": [as_t(v["visual_feats"][:l]) for v, l in zip(videos, lens)],
                       "audio_feats": [as_t(v["audio_feats"][:l]) for v, l in zip(videos, lens)],
@@ -82,3 +83,14 @@ def ragged_batch(videos: Sequence[dict]) -> dict:
             "text_lens": torch.tensor(tlens, dtype=torch.int32), "lens": torch.tensor(lens, dtype=torch.int32),
             "video_id": [v.get("video_id", i) for i, v in enumerate(videos)],
             "duration": lens, "labels": None, "segments": None}
+
+
+def to_bf16(video: dict, pin: bool = True) -> dict:
+    """One-off conversion of a video's feature arrays to bf16 (round to nearest even — exactly what the
+    device does to fp32 features before the input projection), e.g. when caching feature files.
+    Batches built from such videos with `ragged_batch` take the `rp_forward_ragged_bf16` entry point."""
+    out = dict(video)
+    for k in ("visual_feats", "audio_feats", "text_feats"):
+        t = torch.as_tensor(video[k], dtype=torch.float32).to(torch.bfloat16).contiguous()
+        out[k] = t.pin_memory() if pin and torch.cuda.is_available() else t
+    return out

@@ -176,10 +176,15 @@ class MMCTransformer(nn.Module):
             batch = dict(batch)
             for k, ts in batch.pop("parts").items():
                 batch[k] = torch.cat([t.to(dev, non_blocking=True) for t in ts]) if sum(int(t.shape[0]) for t in ts) \
-                    else torch.zeros(1, int(ts[0].shape[1]), device=dev)
-        vis = self._as_f32(batch["visual_feats"], dev)
-        aud = self._as_f32(batch["audio_feats"], dev)
-        txt = self._as_f32(batch["text_feats"], dev)
+                    else torch.zeros(1, int(ts[0].shape[1]), device=dev, dtype=ts[0].dtype)
+        # ragged batches may carry pre-converted bf16 feature rows (half the PCIe bytes, identical results)
+        feats_bf16 = bool(batch.get("ragged")) and all(
+            torch.is_tensor(batch[k]) and batch[k].dtype == torch.bfloat16
+            for k in ("visual_feats", "audio_feats", "text_feats"))
+        conv = (lambda t, d: t.to(d, non_blocking=True).contiguous()) if feats_bf16 else self._as_f32
+        vis = conv(batch["visual_feats"], dev)
+        aud = conv(batch["audio_feats"], dev)
+        txt = conv(batch["text_feats"], dev)
         lib = _lib.load()
         if batch.get("ragged"):
             i32 = lambda t: t.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
@@ -197,9 +202,10 @@ class MMCTransformer(nn.Module):
         with torch.cuda.device(dev):
             ws = self._get_workspace(B, T)
             if batch.get("ragged"):
-                check(lib.rp_forward_ragged(self._handle, ptr(vis), ptr(aud), ptr(txt), ptr(roff), ptr(toff),
-                                            ptr(tlen), ptr(lens), B, T, ptr(logits), ptr(offsets), ptr(feats),
-                                            ptr(ws), ws.numel(), cur_stream()), "rp_forward_ragged")
+                fwd = lib.rp_forward_ragged_bf16 if feats_bf16 else lib.rp_forward_ragged
+                check(fwd(self._handle, ptr(vis), ptr(aud), ptr(txt), ptr(roff), ptr(toff),
+                          ptr(tlen), ptr(lens), B, T, ptr(logits), ptr(offsets), ptr(feats),
+                          ptr(ws), ws.numel(), cur_stream()), "rp_forward_ragged")
             else:
                 check(lib.rp_forward(self._handle, ptr(vis), ptr(aud), ptr(txt), ptr(lens), B, T,
                                      ptr(logits), ptr(offsets), ptr(feats), ptr(ws), ws.numel(),

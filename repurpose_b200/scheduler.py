@@ -146,7 +146,7 @@ class InferencePipeline:
                 if parts is not None and k in parts:
                     # zero-copy ragged batch: every video goes straight to its row offset
                     rows = sum(int(t.shape[0]) for t in parts[k])
-                    dst = self._buffer(bufs, k, (max(rows, 1), int(parts[k][0].shape[1])), torch.float32)
+                    dst = self._buffer(bufs, k, (max(rows, 1), int(parts[k][0].shape[1])), parts[k][0].dtype)
                     pos = 0
                     for t in parts[k]:
                         n = int(t.shape[0])

@@ -436,3 +436,22 @@ def test_zero_copy_ragged_batch_through_pipeline():
         assert len(gs) == len(ws)
         for a, b in zip(gs, ws):
             assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["segments"], b["segments"]) and torch.equal(a["scores"], b["scores"])
+
+
+def test_bf16_feature_rows_give_identical_results():
+    from repurpose_b200.features import ragged_batch, to_bf16
+    from repurpose_b200.scheduler import InferencePipeline
+    torch.manual_seed(23)
+    m = MMCTransformer(512, 2048, 384, 512, 2, 3, 3, 8)
+    m.load_state_dict(synth.bias_reg_head({k: v.clone() for k, v in m.state_dict().items()}))
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(6)
+    vids = [{"visual_feats": torch.randn(t, 512, generator=g), "audio_feats": torch.randn(t, 2048, generator=g),
+             "text_feats": torch.randn(t - (2 if i == 0 else 0), 384, generator=g), "video_id": i} for i, t in enumerate([222, 97, 160])]
+    _, l0, o0, _, _, f0 = m(ragged_batch(vids))
+    _, l1, o1, _, _, f1 = m(ragged_batch([to_bf16(v) for v in vids]))
+    assert torch.equal(l0, l1) and torch.equal(o0, o1) and torch.equal(f0, f1)
+    a = list(InferencePipeline(m, synth.TEST_CFG).run([ragged_batch(vids)]))[0]
+    b = list(InferencePipeline(m, synth.TEST_CFG).run([ragged_batch([to_bf16(v) for v in vids])]))[0]
+    for x, y in zip(a, b):
+        assert torch.equal(x["labels"], y["labels"]) and torch.equal(x["segments"], y["segments"]) and torch.equal(x["scores"], y["scores"])

@@ -28,6 +28,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--videos", type=int, default=10000)
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--bf16", action="store_true", help="feature rows pre-converted to bf16 (half the H2D bytes)")
     ap.add_argument("--padded", action="store_true", help="host-side padding (reference-style collate) instead of the GPU collate")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -53,6 +54,9 @@ def main():
     pool = {"visual_feats": torch.randn(POOL, 512, generator=g).pin_memory(),
             "audio_feats": torch.randn(POOL, 2048, generator=g).pin_memory(),
             "text_feats": torch.randn(POOL, 384, generator=g).pin_memory()}
+
+    if a.bf16:
+        pool = {k: v.to(torch.bfloat16).pin_memory() for k, v in pool.items()}
 
     def video(i):
         t = lens[i]
@@ -97,7 +101,7 @@ def main():
         pad_eff = sum(lens) / sum(max(lens[i] for i in b) * len(b) for sh in shards for b in S.make_batches(sh, a.batch))
         print(json.dumps({"metric": "videos/s", "value": a.videos / dt.item(), "n_gpus": world, "videos": a.videos,
                           "seconds": dt.item(), "mean_len": float(np.mean(lens)), "batch": a.batch,
-                          "collate": "host-padded" if a.padded else "gpu (ragged rows over PCIe)",
+                          "collate": "host-padded" if a.padded else "gpu (ragged rows over PCIe)", "feature_dtype": "bf16" if a.bf16 else "fp32",
                           "padding_efficiency": pad_eff, "segments": int(counts.sum().item()),
                           "videos_with_segments": int((counts > 0).sum().item()), "host_numa_node_rank0": placement["numa_node"],
                           "timing": "host wall clock around pipeline + all-gather, max over ranks; includes host collation and H2D"}))
