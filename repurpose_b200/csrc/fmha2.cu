@@ -234,6 +234,7 @@ fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the set-up above overlapped the previous kernel's tail
 
   if (warp >= C::SOFTMAX_WARPS) setmaxnreg_dec<C::AUX_REGS>();
   if (warp == C::PRODUCER_WARP) {
@@ -613,7 +614,8 @@ int launch_variant(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtenso
     configured = true;
   }
   dim3 grid((p.Tq + NQ * QT - 1) / (NQ * QT), p.H, p.B);
-  fmha2_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ><<<grid, C::NUM_THREADS, C::SMEM_TOTAL, stream>>>(tmQ, tmK, tmV, tmO, p);
+  RP_CUDA_CHECK(launch_pdl(fmha2_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ>, grid, dim3(C::NUM_THREADS), C::SMEM_TOTAL, stream,
+                           tmQ, tmK, tmV, tmO, p));
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;

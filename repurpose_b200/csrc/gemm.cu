@@ -134,6 +134,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (CG == 2) cluster_sync_all();  // peer barriers initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its results are needed from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -416,13 +417,15 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   RP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, CG>, tmA, tmB, tmD, tmR, g));
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());

@@ -1,3 +1,5 @@
+#include <stdlib.h>
+
 #include "host_util.h"
 
 #include <atomic>
@@ -92,6 +94,12 @@ int make_tensor_map(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const
     return RP_ERR_CUDA;
   }
   return RP_OK;
+}
+
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("RP_PDL") && atoi(getenv("RP_PDL")) == 0);
+  return on;
 }
 
 }  // namespace rp

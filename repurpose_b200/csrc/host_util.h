@@ -58,4 +58,27 @@ int num_sms();
 void count_launch(int n = 1);
 int64_t launch_count();
 
+
+// Programmatic dependent launch: a kernel launched through launch_pdl may become resident while the
+// previous kernel of the stream is still draining; its prologue (barrier init, TMEM allocation,
+// descriptor prefetch) then overlaps that tail.  Such kernels call pdl_wait() (ptx.cuh) before they
+// touch global memory.  RP_PDL=0 falls back to plain stream order.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace rp

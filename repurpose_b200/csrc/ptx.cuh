@@ -103,6 +103,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Programmatic dependent launch (see launch_pdl in host_util.h): blocks until every prerequisite grid
+// has completed and its memory is visible; a no-op for a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Lean wait for hot loops whose barriers are known to complete (no timeout bookkeeping: the inlined
 // slow path of mbar_wait costs instruction-cache footprint in large unrolled loops).
 __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {

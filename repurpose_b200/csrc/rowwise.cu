@@ -165,6 +165,7 @@ __device__ __forceinline__ void row_norm(Row& out, const Row& in, const float* _
 template <int MODE>
 __global__ void __launch_bounds__(256)
 layernorm512_kernel(const LnArgs a) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = int64_t(gridDim.x) * (blockDim.x >> 5);
   // Rows are visited from the END of the buffer: the producer GEMM wrote its last tiles most
@@ -303,13 +304,13 @@ int launch_layernorm512(int mode, const LnArgs& a, cudaStream_t stream) {
   RP_CHECK(a.M > 0, "layernorm: empty");
   const int grid = grid_for(a.M, 8);
   switch (mode) {
-    case 0: layernorm512_kernel<0><<<grid, 256, 0, stream>>>(a); break;
+    case 0: RP_CUDA_CHECK(launch_pdl(layernorm512_kernel<0>, dim3(grid), dim3(256), 0, stream, a)); break;
     case 1:
       RP_CHECK(a.pe != nullptr && a.T > 0, "layernorm mode 1 needs pe and T");
-      layernorm512_kernel<1><<<grid, 256, 0, stream>>>(a);
+      RP_CUDA_CHECK(launch_pdl(layernorm512_kernel<1>, dim3(grid), dim3(256), 0, stream, a));
       break;
-    case 2: layernorm512_kernel<2><<<grid, 256, 0, stream>>>(a); break;
-    case 3: layernorm512_kernel<3><<<grid, 256, 0, stream>>>(a); break;
+    case 2: RP_CUDA_CHECK(launch_pdl(layernorm512_kernel<2>, dim3(grid), dim3(256), 0, stream, a)); break;
+    case 3: RP_CUDA_CHECK(launch_pdl(layernorm512_kernel<3>, dim3(grid), dim3(256), 0, stream, a)); break;
     default: set_last_error("layernorm: unknown mode %d", mode); return RP_ERR_INVALID;
   }
   count_launch();
