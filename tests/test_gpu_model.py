@@ -455,3 +455,54 @@ def test_bf16_feature_rows_give_identical_results():
     b = list(InferencePipeline(m, synth.TEST_CFG).run([ragged_batch([to_bf16(v) for v in vids])]))[0]
     for x, y in zip(a, b):
         assert torch.equal(x["labels"], y["labels"]) and torch.equal(x["segments"], y["segments"]) and torch.equal(x["scores"], y["scores"])
+
+
+# ------------------------------------------------------------------- BASELINE config 2 at full size
+def test_full_size_batch_properties(full_model):
+    """Batch 32 x T=1801, 16 layers: too big for the CPU oracle, so check size-independent properties.
+    (a) videos are independent: permuting the batch permutes the outputs bit for bit;
+    (b) padding is inert: a video run alone at its own length gives the same valid rows as inside the
+        T=1801 batch, bit for bit (key tiles beyond the length are skipped, padded keys masked);
+    (c) decode / Soft-NMS invariants: scores descending in selection order is NOT required by the
+        reference (decayed scores), but every kept segment satisfies the duration window, lies in the
+        candidate set of its video, and counts respect max_seg_num = ceil((len // 60) * 0.3)."""
+    m = full_model
+    orig = {k: v.cpu().clone() for k, v in m.state_dict().items()}
+    m.load_state_dict(synth.bias_reg_head({k: v.clone() for k, v in orig.items()}))
+    try:
+        T, B = synth.MAX_SEQ_LEN, 32
+        lens = synth.sample_lengths(B, seed=7)
+        lens[0], lens[5] = T, 61                                   # one full-length, one barely above a minute
+        batch = synth.make_batch(lens, seed=11, T=T)
+        dbatch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        _, logits, offsets, _, _, _ = m(dbatch)
+        r = m.inference_device(dbatch, synth.TEST_CFG)
+        # (a) permutation
+        perm = torch.randperm(B, generator=torch.Generator().manual_seed(3))
+        pbatch = {k: (v[perm.to(v.device)] if torch.is_tensor(v) else [v[i] for i in perm.tolist()]) for k, v in dbatch.items()}
+        _, pl, po, _, _, _ = m(pbatch)
+        assert torch.equal(pl, logits[perm.to(DEV)]) and torch.equal(po, offsets[perm.to(DEV)])
+        # (b) padding invariance for three videos
+        for i in (5, 9, 17):
+            L = lens[i]
+            solo = {k: (v[i:i + 1, ..., :L] if k == "masks" else v[i:i + 1, :L]) if torch.is_tensor(v) else [v[i]]
+                    for k, v in dbatch.items()}
+            _, sl, so, _, _, _ = m(solo)
+            assert torch.equal(sl[0, :L], logits[i, :L]) and torch.equal(so[0, :L], offsets[i, :L]), i
+        # (c) decode invariants
+        counts = r["counts"].cpu()
+        segs, labels = r["segments"].cpu(), r["labels"].cpu()
+        cfg = synth.TEST_CFG
+        prob = torch.sigmoid(logits[..., 0]).cpu()
+        for i in range(B):
+            k = int(counts[i])
+            assert k <= synth.max_seg_num(lens[i], cfg["max_seg_per_min"])
+            if k:
+                dur = segs[i, :k, 1] - segs[i, :k, 0]
+                assert bool(((dur > cfg["duration_thresh"]) & (dur < cfg["duration_thresh_max"])).all())
+                t = labels[i, :k].long()
+                assert bool((t < lens[i]).all()) and bool((prob[i, t] > cfg["pre_nms_thresh"]).all())
+                assert len(set(t.tolist())) == k                   # a centre is selected at most once
+        assert int(counts.sum()) > 0
+    finally:
+        m.load_state_dict(orig)
