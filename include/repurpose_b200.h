@@ -154,6 +154,13 @@ int32_t rp_atiou(const float* slots, int32_t n_videos, int32_t K, const double* 
 int32_t rp_gemm_bf16(int32_t epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
                      int64_t ldd, const float* bias, const float* resid, int64_t ldr, int32_t M,
                      int32_t N, int32_t K, void* stream);
+/* h[M,512] (f32, in place) += A[M,K] W[512,K]^T + bias, and u[M,512] (bf16) = LayerNorm(h; gamma, beta,
+ * eps) of the updated rows, in one kernel: the residual update of nn.TransformerEncoderLayer followed by
+ * the pre-LN of the next sub-block (models/MMCTransformer.py:135-138: x = x + sa(norm1(x)); x = x +
+ * ff(norm2(x))).  M > 128. */
+int32_t rp_gemm_resid_ln(const void* A, int64_t lda, const void* W, int64_t ldw, float* h, int64_t ldh,
+                         const float* bias, const float* gamma, const float* beta, float eps, void* u_bf16,
+                         int64_t ldu, int32_t M, int32_t K, void* stream);
 /* softmax(q k^T + mask) v per head of 64; q must be pre-scaled by log2(e)/8.  bf16 in/out; ld* row
  * pitch and bs* batch pitch in elements.  mask_mode 0: keys >= kv_lens[b] are -inf (kv_lens may be
  * NULL); mask_mode 1: uint8 mask, 0 => masked_fill(-1e9), mask_q_stride 0 broadcasts over queries. */

@@ -470,6 +470,11 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
   }
   // (2) encoder layers (pre-LN): h += MHA(LN1(h)); h += FFN(LN2(h))
   const bool fuse = ln_fusion_enabled();
+  // RP_LN_IN_GEMM=1: LayerNorm inside the residual GEMMs' epilogue (needs d_model = 512 and more than one
+  // 128-row block).  Off by default: it removes the 32 LayerNorm launches (-1.03 ms / step) but the two-pass
+  // epilogue on 132 SMs costs the out-proj / FF2 GEMMs +0.99 ms, a net +1 % (profiles/r01_notes.md).
+  static const bool ln_in_gemm_env = getenv("RP_LN_IN_GEMM") && atoi(getenv("RP_LN_IN_GEMM")) != 0;
+  const bool ln_in_gemm = ln_in_gemm_env && !fuse && D == 512 && M > 128;
   if (fuse) {
     if (!h->folded && (rc = fold_weights(h, st))) return rc;
     RP_CUDA_CHECK(cudaMemsetAsync(w.stats1, 0, size_t(M) * 8, st));
@@ -508,6 +513,17 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
       f2.stats_out = w.stats1; f2.stats_zero = w.stats2; f2.hb_out = hb; f2.ld_hb = D;
       RUN(RP_TAG_GEMM_FF2, launch_gemm_ln(EPI_BIAS_RESID_F32, w.ffn, F, L.w_ff2, F, w.h, D, L.b_ff2, w.h, D,
                                           M, D, F, f2, st));
+    } else if (ln_in_gemm) {
+      // The LayerNorm that follows each residual update runs inside the GEMM epilogue (clusters of
+      // four CTAs own complete 512-column rows): u = LN(h) is written next to the updated h.
+      GemmLnFusion f{};
+      f.eps = eps; f.u_out = w.u; f.ld_u = D;
+      f.ln_gamma = L.n2_g; f.ln_beta = L.n2_b;
+      RUN(RP_TAG_GEMM_OUT, launch_gemm_ln(EPI_BIAS_RESID_LN, w.attn, D, L.w_out, D, w.h, D, L.b_out, w.h, D, M, D, D, f, st));
+      RUN(RP_TAG_GEMM_FF1, launch_gemm(EPI_BIAS_RELU_BF16, w.u, D, L.w_ff1, D, w.ffn, F, L.b_ff1, nullptr, 0, M, F, D, st));
+      if (l + 1 < c.num_layers) { f.ln_gamma = h->layers[l + 1].n1_g; f.ln_beta = h->layers[l + 1].n1_b; }
+      else { f.ln_gamma = h->enc_g; f.ln_beta = h->enc_b; }  // encoder_norm feeds feature_map
+      RUN(RP_TAG_GEMM_FF2, launch_gemm_ln(EPI_BIAS_RESID_LN, w.ffn, F, L.w_ff2, F, w.h, D, L.b_ff2, w.h, D, M, D, F, f, st));
     } else {
       RUN(RP_TAG_GEMM_OUT, launch_gemm(EPI_BIAS_RESID_F32, w.attn, D, L.w_out, D, w.h, D, L.b_out, w.h, D, M, D, D, st));
       {
@@ -666,6 +682,16 @@ int32_t rp_fmha(const void* q, const void* k, const void* v, void* o, int64_t ld
   a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.kv_lens = kv_lens; a.mask_mode = mask_mode;
   a.mask = mask; a.mask_b_stride = mask_b_stride; a.mask_q_stride = mask_q_stride;
   return launch_fmha(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_gemm_resid_ln(const void* A, int64_t lda, const void* W, int64_t ldw, float* h, int64_t ldh,
+                         const float* bias, const float* gamma, const float* beta, float eps, void* u_bf16,
+                         int64_t ldu, int32_t M, int32_t K, void* stream) {
+  RP_CHECK(A && W && h && gamma && beta && u_bf16, "rp_gemm_resid_ln: null argument");
+  GemmLnFusion f{};
+  f.eps = eps; f.ln_gamma = gamma; f.ln_beta = beta; f.u_out = u_bf16; f.ld_u = ldu;
+  return launch_gemm_ln(EPI_BIAS_RESID_LN, A, lda, W, ldw, h, ldh, bias, h, ldh, M, 512, K, f,
+                        reinterpret_cast<cudaStream_t>(stream));
 }
 
 int32_t rp_concat_cast(const float* vis, const float* aud, const float* txt, int32_t Cv, int32_t Ca,

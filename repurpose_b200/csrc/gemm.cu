@@ -49,7 +49,8 @@ constexpr int MAX_SLABS = 5;
 // stages for a deeper slab ring (loads and stores both live there).
 template <int EPI, int CG>
 struct Cfg {
-  static constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32);
+  static constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_LN);
+  static constexpr bool LNF = (EPI == EPI_BIAS_RESID_LN);   // LayerNorm of the updated rows fused in (cluster of 4)
   static constexpr int B_ROWS = BN / CG;               // rows of W staged by each CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;      // 32 KB (CG=1) / 16 KB (CG=2)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -60,7 +61,9 @@ struct Cfg {
   static constexpr int SMEM_B_OFF = STAGES * A_BYTES;
   static constexpr int SMEM_D_OFF = SMEM_B_OFF + STAGES * B_BYTES;
   static constexpr int SMEM_BAR_OFF = SMEM_D_OFF + 4 * SLABS * SLAB_BYTES;
-  static constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 512 + 1024;  // barriers + alignment slack
+  static constexpr int SMEM_STATS_OFF = SMEM_BAR_OFF + 512;     // LNF: [2 buffers][128 rows] (sum, sumsq) from the partner pair
+  // barriers (+ LNF statistics) + alignment slack (the dynamic segment is declared 1024-aligned; checked at run time)
+  static constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 512 + (LNF ? 2048 + 512 : 1024);
   static_assert(STAGES >= 3 && STAGES <= 8, "stage count");
   static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 };
@@ -75,18 +78,20 @@ template <int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
-                 const GemmArgs g) {
+                 const __grid_constant__ CUtensorMap tmU, const GemmArgs g) {
   using C = Cfg<EPI, CG>;
   constexpr int STAGES = C::STAGES;
   constexpr int SLABS = C::SLABS;
-  constexpr bool OUT_F32 = (EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_RESID_F32);
+  constexpr bool OUT_F32 = (EPI == EPI_BIAS_F32 || C::RESID);
+  constexpr bool LNF = C::LNF;
   constexpr int CPC = OUT_F32 ? 32 : 64;  // output columns per 128-byte slab row
   constexpr int CHUNKS = BN / CPC;        // slab-sized chunks per tile and warp
 
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
+  if (LNF && base - raw_addr > 512u) __trap();  // the LNF budget only leaves 512 bytes of alignment slack
 
   // barrier map (bytes from bar_base): full[8] @0, empty[8] @64, tfull[2] @128, tempty[2] @144,
   // tmem slot @160, resid[4][5] @192
@@ -96,11 +101,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tfull_bar = [&](int b) { return bar_base + 128u + 8u * b; };
   auto tempty_bar = [&](int b) { return bar_base + 144u + 8u * b; };
   auto resid_bar = [&](int ew, int s) { return bar_base + 192u + 8u * (ew * MAX_SLABS + s); };
+  auto stats_bar = [&](int b) { return bar_base + 352u + 8u * b; };  // LNF: partner pair's row statistics have landed
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::SMEM_BAR_OFF + 160);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int cta_rank = CG == 2 ? int(cluster_ctarank()) : 0;   // 0 = leader of the pair
+  const int cluster_rank = CG == 2 ? int(cluster_ctarank()) : 0;  // LNF: clusters of 4 = two CTA pairs
+  const int cta_rank = cluster_rank & 1;                          // 0 = leader of the pair
+  const uint16_t pair_mask = uint16_t(3u << (cluster_rank & 2));
   const int group = blockIdx.x / CG;                           // tile-scheduler slot (pair index)
   const int num_groups = gridDim.x / CG;
 
@@ -123,6 +131,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(tempty_bar(b), 4 * CG);
     }
     for (int i = 0; i < 4 * MAX_SLABS; ++i) mbar_init(bar_base + 192u + 8u * i, 1);
+    for (int b = 0; b < 2; ++b) mbar_init(stats_bar(b), 128);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -195,8 +204,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
             }
             if constexpr (CG == 2) {
-              tc_commit_cg2(empty_bar(stage));  // frees the slot in BOTH CTAs once these MMAs retire
-              if (kb == k_blocks - 1) tc_commit_cg2(tfull_bar(buf));
+              tc_commit_cg2(empty_bar(stage), pair_mask);  // frees the slot in BOTH CTAs once these MMAs retire
+              if (kb == k_blocks - 1) tc_commit_cg2(tfull_bar(buf), pair_mask);
             } else {
               tc_commit(empty_bar(stage));
               if (kb == k_blocks - 1) tc_commit(tfull_bar(buf));
@@ -213,13 +222,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 2;  // slab ring / barrier set of this warp
     const uint32_t slab0 = base + C::SMEM_D_OFF + ew * SLABS * SLAB_BYTES;
     const int my_tiles = group < total_tiles ? (total_tiles - group + num_groups - 1) / num_groups : 0;
-    const int total_chunks = my_tiles * CHUNKS;
+    // Slab uses per tile: CHUNKS residual/output chunks, then (LNF) 4 chunks of normalised bf16 rows.
+    constexpr int UPT = CHUNKS + (LNF ? BN / 64 : 0);
+    static_assert(!LNF || (SLABS == 4 && UPT % SLABS == 0 && CHUNKS == 8), "LNF slab ring bookkeeping");
+    const int total_chunks = my_tiles * UPT;
     auto tile_row0 = [&](int m_blk) { return (m_blk * CG + cta_rank) * BM + q * 32; };
 
-    // residual chunk gc (per-warp chunk counter) -> issue its TMA load into slab gc % SLABS
+    // slab use gc (per-warp counter) -> if it is a residual chunk, issue its TMA load into slab gc % SLABS
     auto issue_resid_load = [&](int gc) {
-      const int tile = group + (gc / CHUNKS) * num_groups;
-      const int c = gc % CHUNKS;
+      const int c = gc % UPT;
+      if (c >= CHUNKS) return;  // a LayerNorm output chunk: nothing to load
+      const int tile = group + (gc / UPT) * num_groups;
       const int m_blk = tile / n_tiles;
       const int n_blk = tile - m_blk * n_tiles;
       const int s = gc % SLABS;
@@ -265,7 +278,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_store_wait_read<1>();
             issue_resid_load(gc + C::LOOKAHEAD);
           }
-          mbar_wait(resid_bar(ew, s), uint32_t(gc / SLABS) & 1u);
+          // completed loads into this slab so far: every use (plain) / two of its three uses per tile (LNF)
+          mbar_wait(resid_bar(ew, s), LNF ? uint32_t(c / SLABS) & 1u : uint32_t(gc / SLABS) & 1u);
         } else {
           // the TMA store that last read this slab (SLABS chunks ago) must have drained it
           if (lane == 0) tma_store_wait_read<SLABS - 1>();
@@ -327,7 +341,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                            "r"(v[4 * i + 1]), "r"(v[4 * i + 2]), "r"(v[4 * i + 3])
                            : "memory");
             }
-            if constexpr (C::RESID) {
+            if constexpr (LNF) {
+              // keep the updated row in TMEM for the normalisation pass and accumulate its statistics
+              tmem_st32(t_row + uint32_t(c * CPC + half * 32), v);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float x = __uint_as_float(v[i]);
+                st_sum += x;
+                st_sq = fmaf(x, x, st_sq);
+              }
+            }
+            if constexpr (C::RESID && !LNF) {
               if (g.ln.stats_out != nullptr) {  // LayerNorm fusion, producer side
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -372,7 +396,69 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_store_commit();
         }
       }
-      if constexpr (C::RESID) {
+      if constexpr (LNF) {
+        // ---- fused LayerNorm: swap (sum, sumsq) with the CTA of the partner pair that holds the other
+        // 256 columns of the same rows, then normalise the rows kept in TMEM and store them as bf16
+        tmem_st_wait();
+        const int my_row = q * 32 + lane;
+        const uint32_t partner = uint32_t(cluster_rank ^ 2);
+        st_cluster_f32x2(mapa_shared(base + C::SMEM_STATS_OFF + uint32_t(buf * 128 + my_row) * 8u, partner), st_sum, st_sq);
+        mbar_arrive_cluster(mapa_shared(stats_bar(buf), partner));
+        while (!mbar_try_wait_cluster(stats_bar(buf), use_parity)) {}
+        float2 other;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                     : "=f"(other.x), "=f"(other.y)
+                     : "r"(base + C::SMEM_STATS_OFF + uint32_t(buf * 128 + my_row) * 8u)
+                     : "memory");
+        const float inv_w = 1.0f / float(2 * BN);
+        const float mean = (st_sum + other.x) * inv_w;
+        const float rstd = rsqrtf(fmaxf((st_sq + other.y) * inv_w - mean * mean, 0.f) + g.ln.eps);
+        const float nmr = -mean * rstd;
+#pragma unroll 1
+        for (int c2 = 0; c2 < BN / 64; ++c2, ++gc) {
+          const int s = gc % SLABS;
+          const uint32_t slab = slab0 + s * SLAB_BYTES;
+          if (lane == 0) {
+            if (gc + C::LOOKAHEAD < total_chunks) {
+              tma_store_wait_read<1>();
+              issue_resid_load(gc + C::LOOKAHEAD);
+            } else {
+              tma_store_wait_read<SLABS - 1>();
+            }
+          }
+          __syncwarp();
+          const uint32_t row_addr = slab + uint32_t(lane) * 128u;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld32(t_row + uint32_t(c2 * 64 + half * 32), v);
+            tmem_ld_wait();
+            const int col0 = n_blk * BN + c2 * 64 + half * 32;
+            const float4* gp = reinterpret_cast<const float4*>(g.ln.ln_gamma + col0);
+            const float4* bp = reinterpret_cast<const float4*>(g.ln.ln_beta + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 g0 = __ldg(gp + 2 * i), g1 = __ldg(gp + 2 * i + 1);
+              const float4 b0 = __ldg(bp + 2 * i), b1 = __ldg(bp + 2 * i + 1);
+              auto nrm = [&](uint32_t x, float ga, float be) { return fmaf(fmaf(__uint_as_float(x), rstd, nmr), ga, be); };
+              const uint32_t p0 = pack_bf16x2(nrm(v[8 * i + 0], g0.x, b0.x), nrm(v[8 * i + 1], g0.y, b0.y));
+              const uint32_t p1 = pack_bf16x2(nrm(v[8 * i + 2], g0.z, b0.z), nrm(v[8 * i + 3], g0.w, b0.w));
+              const uint32_t p2 = pack_bf16x2(nrm(v[8 * i + 4], g1.x, b1.x), nrm(v[8 * i + 5], g1.y, b1.y));
+              const uint32_t p3 = pack_bf16x2(nrm(v[8 * i + 6], g1.z, b1.z), nrm(v[8 * i + 7], g1.w, b1.w));
+              const uint32_t dst = row_addr + (uint32_t((half * 4 + i) ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3)
+                           : "memory");
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmU, slab, n_blk * BN + c2 * 64, row0);
+            tma_store_commit();
+          }
+        }
+      }
+      if constexpr (C::RESID && !LNF) {
         if (g.ln.stats_out != nullptr && row_ok) {
           atomicAdd(g.ln.stats_out + 2 * int64_t(row), st_sum);
           atomicAdd(g.ln.stats_out + 2 * int64_t(row) + 1, st_sq);
@@ -404,9 +490,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int EPI, int CG>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
-               const CUtensorMap& tmR, const GemmArgs& g, int groups, cudaStream_t stream) {
+               const CUtensorMap& tmR, const CUtensorMap& tmU, const GemmArgs& g, int groups,
+               cudaStream_t stream) {
   using C = Cfg<EPI, CG>;
+  constexpr int CLUSTER = C::LNF ? 4 : CG;  // LNF: two CTA pairs per cluster share full 512-column rows
   static bool configured = false;
+  static int max_clusters = 0;
   if (!configured) {
     RP_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, CG>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));
@@ -419,14 +508,27 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = CLUSTER;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (C::LNF) {
+    // Clusters of four do not tile all 148 SMs (GPC sizes): size the persistent grid to what can be
+    // co-resident (33 clusters = 132 SMs on B200).  Pairs 2c / 2c+1 walk tiles (m, 0) / (m, 1) in step.
+    if (max_clusters == 0) {
+      cfg.gridDim = dim3(unsigned(num_sms() / 4 * 4));
+      RP_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters, gemm_bf16_kernel<EPI, CG>, &cfg));
+      RP_CHECK(max_clusters > 0, "gemm: no cluster of 4 CTAs fits");
+    }
+    const int m_tiles = (g.M + BM * CG - 1) / (BM * CG);
+    const int clusters = m_tiles < max_clusters ? m_tiles : max_clusters;
+    cfg.gridDim = dim3(unsigned(clusters * 4));
+  }
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  RP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, CG>, tmA, tmB, tmD, tmR, g));
+  RP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, CG>, tmA, tmB, tmD, tmR, tmU, g));
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;
@@ -436,8 +538,9 @@ template <int CG>
 int launch_cg(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd,
               const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
               const GemmLnFusion& ln, cudaStream_t stream) {
-  const bool out_f32 = (epilogue == EPI_BIAS_F32 || epilogue == EPI_BIAS_RESID_F32);
-  CUtensorMap tmA, tmB, tmD, tmR;
+  const bool resid_epi = (epilogue == EPI_BIAS_RESID_F32 || epilogue == EPI_BIAS_RESID_LN);
+  const bool out_f32 = (epilogue == EPI_BIAS_F32 || resid_epi);
+  CUtensorMap tmA, tmB, tmD, tmR, tmU;
   int rc;
   if ((rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, A, K, M, lda * 2, BK, BM))) return rc;
   if ((rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, W, K, N, ldw * 2, BK, BN / CG))) return rc;
@@ -447,8 +550,11 @@ int launch_cg(int epilogue, const void* A, int64_t lda, const void* W, int64_t l
     rc = make_tmap_2d(&tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, D, N, M, ldd * 2, 64, 32);
   if (rc) return rc;
   tmR = tmD;
-  if (epilogue == EPI_BIAS_RESID_F32 &&
-      (rc = make_tmap_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, resid, N, M, ldr * 4, 32, 32)))
+  if (resid_epi && (rc = make_tmap_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, resid, N, M, ldr * 4, 32, 32)))
+    return rc;
+  tmU = tmD;
+  if (epilogue == EPI_BIAS_RESID_LN &&
+      (rc = make_tmap_2d(&tmU, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, ln.u_out, N, M, ln.ld_u * 2, 64, 32)))
     return rc;
 
   GemmArgs g{M, N, K, bias, ln};
@@ -458,10 +564,14 @@ int launch_cg(int epilogue, const void* A, int64_t lda, const void* W, int64_t l
   const int max_groups = sms / CG;
   const int groups = total_tiles < max_groups ? total_tiles : max_groups;
   switch (epilogue) {
-    case EPI_BIAS_BF16: return launch_one<EPI_BIAS_BF16, CG>(tmA, tmB, tmD, tmR, g, groups, stream);
-    case EPI_BIAS_RELU_BF16: return launch_one<EPI_BIAS_RELU_BF16, CG>(tmA, tmB, tmD, tmR, g, groups, stream);
-    case EPI_BIAS_F32: return launch_one<EPI_BIAS_F32, CG>(tmA, tmB, tmD, tmR, g, groups, stream);
-    case EPI_BIAS_RESID_F32: return launch_one<EPI_BIAS_RESID_F32, CG>(tmA, tmB, tmD, tmR, g, groups, stream);
+    case EPI_BIAS_BF16: return launch_one<EPI_BIAS_BF16, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
+    case EPI_BIAS_RELU_BF16: return launch_one<EPI_BIAS_RELU_BF16, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
+    case EPI_BIAS_F32: return launch_one<EPI_BIAS_F32, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
+    case EPI_BIAS_RESID_F32: return launch_one<EPI_BIAS_RESID_F32, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
+    case EPI_BIAS_RESID_LN:
+      if constexpr (CG == 2) return launch_one<EPI_BIAS_RESID_LN, 2>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
+      set_last_error("gemm: the LayerNorm-fused epilogue needs CTA pairs");
+      return RP_ERR_INVALID;
     default: set_last_error("gemm: unknown epilogue %d", epilogue); return RP_ERR_INVALID;
   }
 }
@@ -475,10 +585,14 @@ int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int6
   RP_CHECK(N % BN == 0, "gemm: N=%d must be a multiple of %d", N, BN);
   RP_CHECK(K % BK == 0, "gemm: K=%d must be a multiple of %d", K, BK);
   RP_CHECK(lda % 8 == 0 && ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 elements");
-  const bool out_f32 = (epilogue == EPI_BIAS_F32 || epilogue == EPI_BIAS_RESID_F32);
+  const bool resid_epi = (epilogue == EPI_BIAS_RESID_F32 || epilogue == EPI_BIAS_RESID_LN);
+  const bool out_f32 = (epilogue == EPI_BIAS_F32 || resid_epi);
   RP_CHECK((ldd * (out_f32 ? 4 : 2)) % 16 == 0, "gemm: output pitch must be 16-byte aligned");
-  RP_CHECK(epilogue != EPI_BIAS_RESID_F32 || (resid != nullptr && ldr % 4 == 0),
+  RP_CHECK(!resid_epi || (resid != nullptr && ldr % 4 == 0),
            "gemm: residual epilogue needs a 16-byte aligned residual");
+  RP_CHECK(epilogue != EPI_BIAS_RESID_LN ||
+               (N == 2 * BN && M > BM && ln.ln_gamma && ln.ln_beta && ln.u_out && ln.ld_u % 8 == 0),
+           "gemm: the LayerNorm-fused epilogue needs N = 512, M > 128, gamma/beta and a bf16 output");
   RP_CHECK((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) |
             reinterpret_cast<uintptr_t>(D) | reinterpret_cast<uintptr_t>(bias) |
             reinterpret_cast<uintptr_t>(resid)) % 16 == 0,
@@ -490,7 +604,7 @@ int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int6
            "gemm: LayerNorm-producer fusion needs the residual epilogue and a bf16 copy buffer");
   // RP_GEMM_CG=1 selects the single-CTA kernel (A/B experiments); the CTA-pair kernel is the default
   static const int cg = getenv("RP_GEMM_CG") ? atoi(getenv("RP_GEMM_CG")) : 2;
-  if (cg == 1 || M <= BM)
+  if ((cg == 1 || M <= BM) && epilogue != EPI_BIAS_RESID_LN)
     return launch_cg<1>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, ln, stream);
   return launch_cg<2>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, ln, stream);
 }

@@ -11,6 +11,7 @@ enum GemmEpilogue : int {
   EPI_BIAS_RELU_BF16 = 1,  // D(bf16) = relu(acc + bias)
   EPI_BIAS_F32 = 2,        // D(f32)  = acc + bias
   EPI_BIAS_RESID_F32 = 3,  // D(f32)  = acc + bias + R   (R may alias D)
+  EPI_BIAS_RESID_LN = 4,   // same, plus U(bf16) = LayerNorm(D row; gamma, beta) — N must be 512 (GemmLnFusion::u_out)
 };
 int launch_gemm(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
                 int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
@@ -30,6 +31,13 @@ struct GemmLnFusion {
   int64_t ld_hb = 0;
   int ln_width = 512;
   float eps = 1e-5f;
+  // EPI_BIAS_RESID_LN: the LayerNorm that follows the residual update is computed by the GEMM itself.
+  // Clusters of four CTAs (two CTA pairs) cover the full 512-column rows of a 256-row block; the pairs
+  // swap per-row (sum, sum of squares) through distributed shared memory, so no extra pass over h.
+  const float* ln_gamma = nullptr;   // [512]
+  const float* ln_beta = nullptr;    // [512]
+  void* u_out = nullptr;             // bf16 [M, 512]
+  int64_t ld_u = 0;
 };
 int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
                    int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,

@@ -256,12 +256,38 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap*
       : "memory");
 }
 // MMA completion -> arrive on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void tc_commit_cg2(uint32_t bar) {
+__device__ __forceinline__ void tc_commit_cg2(uint32_t bar, uint16_t cta_mask = 3) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
           "r"(bar),
-      "h"(uint16_t(3))
+      "h"(cta_mask)  // bit per CTA rank in the cluster: the two CTAs of the issuing pair
       : "memory");
+}
+// ---- distributed shared memory (thread-block cluster) ----
+// address of the same shared-memory location in the CTA with rank `target` of this cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t target) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(target));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 // arrive on the leader CTA's copy of a barrier (from either CTA)
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {

@@ -107,7 +107,7 @@ def collate(videos: Sequence[dict], pin: bool = False) -> dict:
 
 
 class InferencePipeline:
-    """Double-buffered host->device->host inference over a stream of collated HOST batches (the
+    """Multi-buffered (default: three staging slots) host->device->host inference over a stream of collated HOST batches (the
     batched replacement of the reference's `for batch in loader: .to('cuda'); inference_()` loop,
     inference.py:39-47).  The H2D copy of batch i+1 runs on a side stream while batch i computes;
     each batch's fixed-slot result block comes back with one async D2H copy into pinned memory.
@@ -116,7 +116,7 @@ class InferencePipeline:
     FEATS = ("visual_feats", "audio_feats", "text_feats", "masks")
     RAGGED = ("visual_feats", "audio_feats", "text_feats", "row_offsets", "text_offsets", "text_lens", "lens")
 
-    def __init__(self, model, test_cfg: dict, depth: int = 2):
+    def __init__(self, model, test_cfg: dict, depth: int = 3):
         self.model, self.cfg, self.depth = model, test_cfg, max(2, depth)
         self.dev = model.device
         self.copy_stream = torch.cuda.Stream(device=self.dev)
@@ -182,10 +182,11 @@ class InferencePipeline:
             slot = (slot + 1) % self.depth
             return True
 
-        stage_next()
+        for _ in range(self.depth - 1):                    # keep depth-1 uploads queued ahead of the compute
+            stage_next()
         while staged:
             s, dbatch, ready, b = staged.pop(0)
-            stage_next()                                   # H2D of the next batch overlaps this compute
+            stage_next()                                   # H2D of later batches overlaps this compute
             main.wait_event(ready)
             r = self.model.inference_device(dbatch, self.cfg)
             slots = pack_slots(r["segments"], r["scores"], r["labels"], r["counts"])

@@ -261,3 +261,28 @@ def test_fmha_explicit_mask(Tq, Tk, kind):
     ref = _attn_ref(q, k, v, mask=mask.to(torch.uint8))
     g2, r2 = got.view(B * Tq, -1), ref.view(B * Tq, -1)
     assert torch.allclose(g2.float(), r2, atol=2e-2, rtol=2e-2), _describe(g2, r2, f"fmha mask {kind}")
+
+
+@pytest.mark.parametrize("M,K", [(300, 512), (1000, 2048), (57632, 512), (4099, 2048)])
+def test_gemm_residual_layernorm_fused(M, K):
+    """h += A W^T + b and u = LayerNorm(h) in one kernel (clusters of four CTAs exchange row statistics)."""
+    lib = _lib.load()
+    torch.manual_seed(M + K)
+    A = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
+    W = (torch.randn(512, K, device=DEV) / K ** 0.5).bfloat16()
+    bias = torch.randn(512, device=DEV)
+    h0 = torch.randn(M, 512, device=DEV) * 2 + torch.randn(M, 1, device=DEV)       # rows with a mean offset
+    gamma, beta = torch.rand(512, device=DEV) + 0.5, torch.randn(512, device=DEV)
+    h = h0.clone()
+    u = torch.empty(M, 512, device=DEV, dtype=torch.bfloat16)
+    check(lib.rp_gemm_resid_ln(ptr(A), K, ptr(W), K, ptr(h), 512, ptr(bias), ptr(gamma), ptr(beta), 1e-5, ptr(u), 512,
+                               M, K, cur_stream()), "rp_gemm_resid_ln")
+    ref_h = h0 + A.float() @ W.float().t() + bias
+    ref_u = torch.nn.functional.layer_norm(ref_h, (512,), gamma, beta, 1e-5)
+    assert torch.allclose(h, ref_h, atol=2e-3, rtol=1e-4), (h - ref_h).abs().max().item()
+    err = (u.float() - ref_u).abs().max().item()
+    assert err < 3e-2, err                      # bf16 output of O(1..4) values
+    # the unfused pair of kernels computes the same thing: h bit for bit, u within bf16 rounding of the statistics
+    h2 = h0.clone()
+    check(lib.rp_gemm_bf16(3, ptr(A), K, ptr(W), K, ptr(h2), 512, ptr(bias), ptr(h2), 512, M, 512, K, cur_stream()), "gemm")
+    assert torch.equal(h, h2)
