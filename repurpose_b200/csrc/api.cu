@@ -470,10 +470,10 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
   }
   // (2) encoder layers (pre-LN): h += MHA(LN1(h)); h += FFN(LN2(h))
   const bool fuse = ln_fusion_enabled();
-  // RP_LN_IN_GEMM=1: LayerNorm inside the residual GEMMs' epilogue (needs d_model = 512 and more than one
-  // 128-row block).  Off by default: it removes the 32 LayerNorm launches (-1.03 ms / step) but the two-pass
-  // epilogue on 132 SMs costs the out-proj / FF2 GEMMs +0.99 ms, a net +1 % (profiles/r01_notes.md).
-  static const bool ln_in_gemm_env = getenv("RP_LN_IN_GEMM") && atoi(getenv("RP_LN_IN_GEMM")) != 0;
+  // RP_LN_IN_GEMM (default 1; 0 = stand-alone LayerNorm kernels): the LayerNorm after each residual update
+  // runs inside the GEMM epilogue (needs d_model = 512 and more than one 128-row block).  Removes 32
+  // launches / 1.05 ms per step, costs the out-proj / FF2 GEMMs 0.7 ms: +2.4 % (profiles/r01_notes.md).
+  static const bool ln_in_gemm_env = !(getenv("RP_LN_IN_GEMM") && atoi(getenv("RP_LN_IN_GEMM")) == 0);
   const bool ln_in_gemm = ln_in_gemm_env && !fuse && D == 512 && M > 128;
   if (fuse) {
     if (!h->folded && (rc = fold_weights(h, st))) return rc;

@@ -271,6 +271,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c = 0; c < CHUNKS; ++c, ++gc) {
         const int s = gc % SLABS;
         const uint32_t slab = slab0 + s * SLAB_BYTES;
+        // bias of this chunk: requested before the barrier waits below so that the global-load
+        // latency overlaps them (fp32 epilogues: 32 columns per chunk)
+        float4 bpre[8];
+        if constexpr (OUT_F32) {
+          if (g.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(g.bias + n_blk * BN + c * CPC);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bpre[i] = __ldg(bp + i);
+          }
+        }
         if constexpr (C::RESID) {
           // keep LOOKAHEAD residual loads in flight: chunk gc+LOOKAHEAD lands in the slab chunk gc-2
           // was stored from, so all but the most recent store must have finished reading smem
@@ -309,7 +319,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float4* bp = reinterpret_cast<const float4*>(g.bias + col0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 b4 = __ldg(bp + i);
+              const float4 b4 = OUT_F32 ? bpre[i] : __ldg(bp + i);
               v[4 * i + 0] = __float_as_uint(__uint_as_float(v[4 * i + 0]) + b4.x);
               v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + b4.y);
               v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + b4.z);
@@ -324,19 +334,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t row_addr = slab + uint32_t(lane) * 128u;
           if constexpr (OUT_F32) {
 #pragma unroll
+            if constexpr (C::RESID) {
+              // slab currently holds the residual: read the whole row first (eight independent loads in
+              // flight instead of a load -> add -> store chain per 16 bytes), then update in place
+              uint32_t r[32];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t src = row_addr + (uint32_t(i ^ (lane & 7)) << 4);
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r[4 * i]), "=r"(r[4 * i + 1]), "=r"(r[4 * i + 2]), "=r"(r[4 * i + 3])
+                             : "r"(src));
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(r[i]));
+            }
+#pragma unroll
             for (int i = 0; i < 8; ++i) {
               const uint32_t dst = row_addr + (uint32_t(i ^ (lane & 7)) << 4);
-              if constexpr (C::RESID) {  // slab currently holds the residual: update in place
-                uint32_t r0, r1, r2, r3;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                             : "r"(dst)
-                             : "memory");
-                v[4 * i + 0] = __float_as_uint(__uint_as_float(v[4 * i + 0]) + __uint_as_float(r0));
-                v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + __uint_as_float(r1));
-                v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + __uint_as_float(r2));
-                v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + __uint_as_float(r3));
-              }
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[4 * i]),
                            "r"(v[4 * i + 1]), "r"(v[4 * i + 2]), "r"(v[4 * i + 3])
                            : "memory");
@@ -432,14 +446,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int half = 0; half < 2; ++half) {
             uint32_t v[32];
             tmem_ld32(t_row + uint32_t(c2 * 64 + half * 32), v);
-            tmem_ld_wait();
             const int col0 = n_blk * BN + c2 * 64 + half * 32;
             const float4* gp = reinterpret_cast<const float4*>(g.ln.ln_gamma + col0);
             const float4* bp = reinterpret_cast<const float4*>(g.ln.ln_beta + col0);
+            float4 gq[8], bq[8];  // requested while the TMEM load is in flight
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              gq[i] = __ldg(gp + i);
+              bq[i] = __ldg(bp + i);
+            }
+            tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 g0 = __ldg(gp + 2 * i), g1 = __ldg(gp + 2 * i + 1);
-              const float4 b0 = __ldg(bp + 2 * i), b1 = __ldg(bp + 2 * i + 1);
+              const float4 g0 = gq[2 * i], g1 = gq[2 * i + 1];
+              const float4 b0 = bq[2 * i], b1 = bq[2 * i + 1];
               auto nrm = [&](uint32_t x, float ga, float be) { return fmaf(fmaf(__uint_as_float(x), rstd, nmr), ga, be); };
               const uint32_t p0 = pack_bf16x2(nrm(v[8 * i + 0], g0.x, b0.x), nrm(v[8 * i + 1], g0.y, b0.y));
               const uint32_t p1 = pack_bf16x2(nrm(v[8 * i + 2], g0.z, b0.z), nrm(v[8 * i + 3], g0.w, b0.w));
