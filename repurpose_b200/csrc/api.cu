@@ -26,7 +26,6 @@ struct WeightSlot {
   WeightKind kind;
   int64_t numel;       // expected element count (W_PE: elements per position row * max_len)
   void* dev = nullptr; // bf16 for matrices, f32 otherwise
-  float* raw = nullptr; // fp32 staging copy (only for tensors that are LayerNorm-folded later)
   bool loaded = false;
 };
 
@@ -34,9 +33,6 @@ struct LayerW {
   __nv_bfloat16 *w_qkv, *w_out, *w_ff1, *w_ff2;
   float *b_qkv, *b_out, *b_ff1, *b_ff2;
   float *n1_g, *n1_b, *n2_g, *n2_b;
-  // LayerNorm-folded copies: W' = bf16(gamma o W), c1 = rowsum(W'), c2 = W beta + b
-  __nv_bfloat16 *wf_qkv = nullptr, *wf_ff1 = nullptr;
-  float *c1_qkv = nullptr, *c2_qkv = nullptr, *c1_ff1 = nullptr, *c2_ff1 = nullptr;
 };
 
 }  // namespace
@@ -52,10 +48,6 @@ struct rp_handle {
   float *r0_g, *r0_b, *b_r1, *b_r4, *w_r7, *b_r7;
   float* pe;
   int64_t pe_rows_loaded = 0;
-  __nv_bfloat16* wf_fm = nullptr;   // feature_map.0 folded with encoder_norm
-  float *c1_fm = nullptr, *c2_fm = nullptr;
-  std::vector<void*> fold_allocs;
-  bool folded = false;
   // optional per-kernel-class CUDA-event profiler (rp_profile_begin / rp_profile_end)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_pool;
@@ -88,37 +80,6 @@ __global__ void repack_f32_kernel(const float* __restrict__ src, float* __restri
        i += int64_t(gridDim.x) * blockDim.x) {
     const float v = src[i];
     dst[i] = i < n_scaled ? v * scale : v;
-  }
-}
-
-// One warp per output row n of a Linear that consumes LayerNorm(x; gamma, beta):
-//   Wf[n,k] = bf16(gamma[k] * W[n,k] * sc),  c1[n] = sum_k float(Wf[n,k]),
-//   c2[n]   = sum_k beta[k] * W[n,k] * sc + b[n] * sc          (sc = scale for rows < n_scaled)
-__global__ void fold_layernorm_kernel(const float* __restrict__ W, const float* __restrict__ b,
-                                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      int N, int K, int n_scaled, float scale,
-                                      __nv_bfloat16* __restrict__ Wf, float* __restrict__ c1,
-                                      float* __restrict__ c2) {
-  const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (n >= N) return;
-  const float sc = n < n_scaled ? scale : 1.0f;
-  float s1 = 0.f, s2 = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    const float w = W[int64_t(n) * K + k] * sc;
-    const __nv_bfloat16 wf = __float2bfloat16_rn(gamma[k] * w);
-    Wf[int64_t(n) * K + k] = wf;
-    s1 += __bfloat162float(wf);
-    s2 += beta[k] * w;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  }
-  if (lane == 0) {
-    c1[n] = s1;
-    c2[n] = s2 + b[n] * sc;
   }
 }
 
@@ -166,39 +127,10 @@ int build_slots(rp_handle* h) {
     ADD(p + "norm2.weight", W_VEC_F32, D, L.n2_g);
     ADD(p + "norm2.bias", W_VEC_F32, D, L.n2_b);
   }
-  // fp32 staging + folded buffers for the Linear layers that sit behind a LayerNorm
-  auto need_raw = [&](const std::string& name) {
-    WeightSlot& sl = h->slots[name];
-    return cudaMalloc(reinterpret_cast<void**>(&sl.raw), size_t(sl.numel) * 4);
-  };
-  auto alloc_fold = [&](void** p, size_t bytes) {
-    cudaError_t e = cudaMalloc(p, bytes);
-    if (e == cudaSuccess) h->fold_allocs.push_back(*p);
-    return e;
-  };
-  for (int l = 0; l < c.num_layers; ++l) {
-    const std::string p = "multimodal_encoder.layers." + std::to_string(l) + ".";
-    LayerW& L = h->layers[l];
-    RP_CUDA_CHECK(need_raw(p + "self_attn.in_proj_weight"));
-    RP_CUDA_CHECK(need_raw(p + "self_attn.in_proj_bias"));
-    RP_CUDA_CHECK(need_raw(p + "linear1.weight"));
-    RP_CUDA_CHECK(need_raw(p + "linear1.bias"));
-    RP_CUDA_CHECK(alloc_fold(reinterpret_cast<void**>(&L.wf_qkv), size_t(3 * D * D) * 2));
-    RP_CUDA_CHECK(alloc_fold(reinterpret_cast<void**>(&L.c1_qkv), size_t(3 * D) * 4));
-    RP_CUDA_CHECK(alloc_fold(reinterpret_cast<void**>(&L.c2_qkv), size_t(3 * D) * 4));
-    RP_CUDA_CHECK(alloc_fold(reinterpret_cast<void**>(&L.wf_ff1), size_t(F * D) * 2));
-    RP_CUDA_CHECK(alloc_fold(reinterpret_cast<void**>(&L.c1_ff1), size_t(F) * 4));
-    RP_CUDA_CHECK(alloc_fold(reinterpret_cast<void**>(&L.c2_ff1), size_t(F) * 4));
-  }
   ADD("encoder_norm.weight", W_VEC_F32, D, h->enc_g);
   ADD("encoder_norm.bias", W_VEC_F32, D, h->enc_b);
   ADD("feature_map.0.weight", W_MAT_BF16, D * D, h->w_fm);
   ADD("feature_map.0.bias", W_VEC_F32, D, h->b_fm);
-  RP_CUDA_CHECK(need_raw("feature_map.0.weight"));
-  RP_CUDA_CHECK(need_raw("feature_map.0.bias"));
-  RP_CUDA_CHECK(alloc_fold(reinterpret_cast<void**>(&h->wf_fm), size_t(D * D) * 2));
-  RP_CUDA_CHECK(alloc_fold(reinterpret_cast<void**>(&h->c1_fm), size_t(D) * 4));
-  RP_CUDA_CHECK(alloc_fold(reinterpret_cast<void**>(&h->c2_fm), size_t(D) * 4));
   ADD("feature_map.1.weight", W_VEC_F32, D, h->fm_g);
   ADD("feature_map.1.bias", W_VEC_F32, D, h->fm_b);
   ADD("cls_head.0.weight", W_VEC_F32, D, h->c0_g);
@@ -228,8 +160,6 @@ struct Workspace {
   __nv_bfloat16* attn;  // [M,512]
   __nv_bfloat16* qkv;   // [M,1536]   } contiguous: also holds xcat [M,Cin] during the input stage
   __nv_bfloat16* ffn;   // [M,d_ff]   }
-  float* stats1;        // [M][2] row (sum, sum^2) of h feeding norm1 / encoder_norm consumers
-  float* stats2;        // [M][2] ... feeding norm2 consumers
   int64_t bytes;
 };
 
@@ -249,51 +179,14 @@ Workspace carve(const rp_model_cfg& c, int64_t M, void* base) {
   int64_t wide = M * (3 * D + c.d_ff) * 2;
   if (wide < M * Cin * 2) wide = M * Cin * 2;
   const int64_t o_q = take(wide);
-  const int64_t o_s1 = take(M * 8);
-  const int64_t o_s2 = take(M * 8);
   uint8_t* b = reinterpret_cast<uint8_t*>(base);
   w.h = reinterpret_cast<float*>(b + o_h);
   w.u = reinterpret_cast<__nv_bfloat16*>(b + o_u);
   w.attn = reinterpret_cast<__nv_bfloat16*>(b + o_a);
   w.qkv = reinterpret_cast<__nv_bfloat16*>(b + o_q);
   w.ffn = w.qkv + M * 3 * D;
-  w.stats1 = reinterpret_cast<float*>(b + o_s1);
-  w.stats2 = reinterpret_cast<float*>(b + o_s2);
   w.bytes = off;
   return w;
-}
-
-// Build the LayerNorm-folded weight copies from the fp32 staging buffers (once per weight load).
-int fold_weights(rp_handle* h, cudaStream_t st) {
-  const rp_model_cfg& c = h->cfg;
-  const int D = c.d_model, F = c.d_ff;
-  auto raw = [&](const std::string& name) { return h->slots[name].raw; };
-  auto run = [&](const float* W, const float* b, const float* g, const float* be, int N, int K,
-                 int n_scaled, float scale, __nv_bfloat16* Wf, float* c1, float* c2) {
-    fold_layernorm_kernel<<<(N + 7) / 8, 256, 0, st>>>(W, b, g, be, N, K, n_scaled, scale, Wf, c1, c2);
-    count_launch();
-  };
-  for (int l = 0; l < c.num_layers; ++l) {
-    const std::string p = "multimodal_encoder.layers." + std::to_string(l) + ".";
-    LayerW& L = h->layers[l];
-    run(raw(p + "self_attn.in_proj_weight"), raw(p + "self_attn.in_proj_bias"), L.n1_g, L.n1_b, 3 * D, D,
-        D, kQScale, L.wf_qkv, L.c1_qkv, L.c2_qkv);
-    run(raw(p + "linear1.weight"), raw(p + "linear1.bias"), L.n2_g, L.n2_b, F, D, 0, 1.0f, L.wf_ff1,
-        L.c1_ff1, L.c2_ff1);
-  }
-  run(raw("feature_map.0.weight"), raw("feature_map.0.bias"), h->enc_g, h->enc_b, D, D, 0, 1.0f, h->wf_fm,
-      h->c1_fm, h->c2_fm);
-  RP_CUDA_CHECK(cudaGetLastError());
-  h->folded = true;
-  return RP_OK;
-}
-
-bool ln_fusion_enabled() {
-  // Off by default: measured neutral (13.46 vs 13.34 ms/step) — the 1.0 ms of LayerNorm kernels it
-  // removes comes back as heavier GEMM epilogues (scattered bf16 copy stores, two more FMAs and a
-  // second broadcast vector per element).  Kept for the next round's epilogue work.
-  static const bool on = getenv("RP_LN_FUSE") ? atoi(getenv("RP_LN_FUSE")) != 0 : false;
-  return on;
 }
 
 }  // namespace
@@ -333,9 +226,7 @@ void rp_destroy(rp_handle* h) {
   if (h == nullptr) return;
   for (auto& kv : h->slots) {
     if (kv.second.dev) cudaFree(kv.second.dev);
-    if (kv.second.raw) cudaFree(kv.second.raw);
   }
-  for (void* p : h->fold_allocs) cudaFree(p);
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   delete h;
 }
@@ -380,10 +271,7 @@ int32_t rp_load_weight(rp_handle* h, const char* name, const float* src, int64_t
   }
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
-  if (s.raw != nullptr)
-    RP_CUDA_CHECK(cudaMemcpyAsync(s.raw, src, size_t(numel) * 4, cudaMemcpyDeviceToDevice, st));
   s.loaded = true;
-  h->folded = false;
   return RP_OK;
 }
 
@@ -469,51 +357,21 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
     RUN(RP_TAG_LAYERNORM, launch_layernorm512(1, a, st));
   }
   // (2) encoder layers (pre-LN): h += MHA(LN1(h)); h += FFN(LN2(h))
-  const bool fuse = ln_fusion_enabled();
   // RP_LN_IN_GEMM (default 1; 0 = stand-alone LayerNorm kernels): the LayerNorm after each residual update
   // runs inside the GEMM epilogue (needs d_model = 512 and more than one 128-row block).  Removes 32
   // launches / 1.05 ms per step, costs the out-proj / FF2 GEMMs 0.7 ms: +2.4 % (profiles/r01_notes.md).
   static const bool ln_in_gemm_env = !(getenv("RP_LN_IN_GEMM") && atoi(getenv("RP_LN_IN_GEMM")) == 0);
-  const bool ln_in_gemm = ln_in_gemm_env && !fuse && D == 512 && M > 128;
-  if (fuse) {
-    if (!h->folded && (rc = fold_weights(h, st))) return rc;
-    RP_CUDA_CHECK(cudaMemsetAsync(w.stats1, 0, size_t(M) * 8, st));
-    RP_CUDA_CHECK(cudaMemsetAsync(w.stats2, 0, size_t(M) * 8, st));
-  }
-  // With fusion the standalone LayerNorm kernels between the GEMMs disappear: the residual GEMMs
-  // emit hb = bf16(h) (into the `u` buffer) plus per-row (sum, sum^2), and the consuming GEMM
-  // applies  rstd * (hb W'^T - mean * c1) + c2  in its epilogue.
-  __nv_bfloat16* hb = w.u;
+  const bool ln_in_gemm = ln_in_gemm_env && D == 512 && M > 128;
   for (int l = 0; l < c.num_layers; ++l) {
     const LayerW& L = h->layers[l];
-    if (fuse && l > 0) {
-      GemmLnFusion f{};
-      f.stats_in = w.stats1; f.c1 = L.c1_qkv; f.ln_width = D; f.eps = eps;
-      RUN(RP_TAG_GEMM_QKV, launch_gemm_ln(EPI_BIAS_BF16, hb, D, L.wf_qkv, D, w.qkv, 3 * D, L.c2_qkv, nullptr,
-                                          0, M, 3 * D, D, f, st));
-    } else {
-      RUN(RP_TAG_GEMM_QKV, launch_gemm(EPI_BIAS_BF16, w.u, D, L.w_qkv, D, w.qkv, 3 * D, L.b_qkv, nullptr, 0, M, 3 * D, D, st));
-    }
+    RUN(RP_TAG_GEMM_QKV, launch_gemm(EPI_BIAS_BF16, w.u, D, L.w_qkv, D, w.qkv, 3 * D, L.b_qkv, nullptr, 0, M, 3 * D, D, st));
     FmhaArgs fa{};
     fa.q = w.qkv; fa.k = w.qkv + D; fa.v = w.qkv + 2 * D; fa.o = w.attn;
     fa.ldq = fa.ldk = fa.ldv = 3 * D; fa.ldo = D;
     fa.bsq = fa.bsk = fa.bsv = int64_t(T) * 3 * D; fa.bso = int64_t(T) * D;
     fa.B = B; fa.H = H; fa.Tq = T; fa.Tk = T; fa.kv_lens = lens; fa.mask_mode = 0;
     RUN(RP_TAG_FMHA, launch_fmha(fa, st));
-    if (fuse) {
-      GemmLnFusion f{};
-      f.stats_out = w.stats2; f.stats_zero = w.stats1; f.hb_out = hb; f.ld_hb = D;
-      RUN(RP_TAG_GEMM_OUT, launch_gemm_ln(EPI_BIAS_RESID_F32, w.attn, D, L.w_out, D, w.h, D, L.b_out, w.h, D,
-                                          M, D, D, f, st));
-      GemmLnFusion f1{};
-      f1.stats_in = w.stats2; f1.c1 = L.c1_ff1; f1.ln_width = D; f1.eps = eps;
-      RUN(RP_TAG_GEMM_FF1, launch_gemm_ln(EPI_BIAS_RELU_BF16, hb, D, L.wf_ff1, D, w.ffn, F, L.c2_ff1, nullptr,
-                                          0, M, F, D, f1, st));
-      GemmLnFusion f2{};
-      f2.stats_out = w.stats1; f2.stats_zero = w.stats2; f2.hb_out = hb; f2.ld_hb = D;
-      RUN(RP_TAG_GEMM_FF2, launch_gemm_ln(EPI_BIAS_RESID_F32, w.ffn, F, L.w_ff2, F, w.h, D, L.b_ff2, w.h, D,
-                                          M, D, F, f2, st));
-    } else if (ln_in_gemm) {
+    if (ln_in_gemm) {
       // The LayerNorm that follows each residual update runs inside the GEMM epilogue (clusters of
       // four CTAs own complete 512-column rows): u = LN(h) is written next to the updated h.
       GemmLnFusion f{};
@@ -543,14 +401,7 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
     }
   }
   // (3) feature_map: Linear -> LN -> ReLU = feats (returned); head LayerNorms
-  if (fuse) {
-    GemmLnFusion f{};
-    f.stats_in = w.stats1; f.c1 = h->c1_fm; f.ln_width = D; f.eps = eps;
-    RUN(RP_TAG_GEMM_FMAP, launch_gemm_ln(EPI_BIAS_F32, hb, D, h->wf_fm, D, w.h, D, h->c2_fm, nullptr, 0, M, D,
-                                         D, f, st));
-  } else {
-    RUN(RP_TAG_GEMM_FMAP, launch_gemm(EPI_BIAS_F32, w.u, D, h->w_fm, D, w.h, D, h->b_fm, nullptr, 0, M, D, D, st));
-  }
+  RUN(RP_TAG_GEMM_FMAP, launch_gemm(EPI_BIAS_F32, w.u, D, h->w_fm, D, w.h, D, h->b_fm, nullptr, 0, M, D, D, st));
   {
     LnArgs a{};
     a.x = w.h; a.M = M; a.T = T; a.eps = eps;

@@ -254,16 +254,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN);
       const int row0 = tile_row0(m_blk);
       const int row = row0 + lane;
-      const bool row_ok = row < g.M;
-      // LayerNorm fusion, consumer side: per-row mean / rstd of the producer's h (one row per thread)
-      float ln_mean = 0.f, ln_rstd = 1.f;
-      if (!C::RESID && g.ln.stats_in != nullptr && row_ok) {
-        const float2 st = *reinterpret_cast<const float2*>(g.ln.stats_in + 2 * int64_t(row));
-        const float inv_w = 1.0f / float(g.ln.ln_width);
-        ln_mean = st.x * inv_w;
-        ln_rstd = rsqrtf(fmaxf(st.y * inv_w - ln_mean * ln_mean, 0.f) + g.ln.eps);
-      }
-      float st_sum = 0.f, st_sq = 0.f;  // producer side: row statistics of the new h over this tile
+      float st_sum = 0.f, st_sq = 0.f;  // LNF: row statistics of the updated h over this tile's 256 columns
       mbar_wait(tfull_bar(buf), use_parity);
       tc_fence_after();
 
@@ -301,21 +292,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld32(t_row + uint32_t(c * CPC + half * 32), v);
           tmem_ld_wait();
           const int col0 = n_blk * BN + c * CPC + half * 32;
-          if (!C::RESID && g.ln.stats_in != nullptr) {
-            // out = rstd * (acc - mean * c1[n]) + bias[n]   (LayerNorm folded into this GEMM)
-            const float4* cp = reinterpret_cast<const float4*>(g.ln.c1 + col0);
-            const float4* bp = reinterpret_cast<const float4*>(g.bias + col0);
-            const float nm = -ln_mean;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 c4 = __ldg(cp + i);
-              const float4 b4 = __ldg(bp + i);
-              v[4 * i + 0] = __float_as_uint(fmaf(ln_rstd, fmaf(nm, c4.x, __uint_as_float(v[4 * i + 0])), b4.x));
-              v[4 * i + 1] = __float_as_uint(fmaf(ln_rstd, fmaf(nm, c4.y, __uint_as_float(v[4 * i + 1])), b4.y));
-              v[4 * i + 2] = __float_as_uint(fmaf(ln_rstd, fmaf(nm, c4.z, __uint_as_float(v[4 * i + 2])), b4.z));
-              v[4 * i + 3] = __float_as_uint(fmaf(ln_rstd, fmaf(nm, c4.w, __uint_as_float(v[4 * i + 3])), b4.w));
-            }
-          } else if (g.bias != nullptr) {
+          if (g.bias != nullptr) {
             const float4* bp = reinterpret_cast<const float4*>(g.bias + col0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -363,29 +340,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const float x = __uint_as_float(v[i]);
                 st_sum += x;
                 st_sq = fmaf(x, x, st_sq);
-              }
-            }
-            if constexpr (C::RESID && !LNF) {
-              if (g.ln.stats_out != nullptr) {  // LayerNorm fusion, producer side
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  const float x = __uint_as_float(v[i]);
-                  st_sum += x;
-                  st_sq = fmaf(x, x, st_sq);
-                }
-                if (row_ok) {
-                  uint4* hp = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(g.ln.hb_out) +
-                                                       int64_t(row) * g.ln.ld_hb + col0);
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    uint4 o;
-                    o.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
-                    o.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
-                    o.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
-                    o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
-                    hp[i] = o;
-                  }
-                }
               }
             }
           } else {
@@ -476,14 +430,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_store_2d(&tmU, slab, n_blk * BN + c2 * 64, row0);
             tma_store_commit();
           }
-        }
-      }
-      if constexpr (C::RESID && !LNF) {
-        if (g.ln.stats_out != nullptr && row_ok) {
-          atomicAdd(g.ln.stats_out + 2 * int64_t(row), st_sum);
-          atomicAdd(g.ln.stats_out + 2 * int64_t(row) + 1, st_sq);
-          if (n_blk == 0 && g.ln.stats_zero != nullptr)
-            *reinterpret_cast<float2*>(g.ln.stats_zero + 2 * int64_t(row)) = make_float2(0.f, 0.f);
         }
       }
       // all TMEM reads of this accumulator buffer are complete -> hand it back to the MMA warp
@@ -617,11 +563,6 @@ int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int6
             reinterpret_cast<uintptr_t>(D) | reinterpret_cast<uintptr_t>(bias) |
             reinterpret_cast<uintptr_t>(resid)) % 16 == 0,
            "gemm: pointers must be 16-byte aligned");
-  RP_CHECK(ln.stats_in == nullptr || (epilogue != EPI_BIAS_RESID_F32 && ln.c1 != nullptr && bias != nullptr),
-           "gemm: LayerNorm-consumer fusion needs c1 and bias and a non-residual epilogue");
-  RP_CHECK(ln.stats_out == nullptr ||
-               (epilogue == EPI_BIAS_RESID_F32 && ln.hb_out != nullptr && ln.ld_hb % 8 == 0),
-           "gemm: LayerNorm-producer fusion needs the residual epilogue and a bf16 copy buffer");
   // RP_GEMM_CG=1 selects the single-CTA kernel (A/B experiments); the CTA-pair kernel is the default
   static const int cg = getenv("RP_GEMM_CG") ? atoi(getenv("RP_GEMM_CG")) : 2;
   if ((cg == 1 || M <= BM) && epilogue != EPI_BIAS_RESID_LN)

@@ -17,19 +17,8 @@ int launch_gemm(int epilogue, const void* A, int64_t lda, const void* W, int64_t
                 int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
                 cudaStream_t stream);
 
-// LayerNorm folded into the GEMMs around it (used by rp_forward):
-//   producer side (EPI_BIAS_RESID_F32 only): besides h (f32) the epilogue writes hb = bf16(h) and
-//     accumulates per-row (sum, sum of squares) of h into stats_out[row]; it also clears stats_zero[row].
-//   consumer side (epilogues 0/1/2): A = hb, W = gamma-folded weights, and the epilogue applies
-//     out = rstd*(acc - mean*c1[n]) + bias[n] with (mean, rstd) from stats_in[row] over `ln_width` columns.
+// Arguments of the LayerNorm-fused residual epilogue:
 struct GemmLnFusion {
-  const float* stats_in = nullptr;   // [M][2]
-  const float* c1 = nullptr;         // [N]  sum_k of the bf16-rounded gamma-folded weight row
-  float* stats_out = nullptr;        // [M][2]
-  float* stats_zero = nullptr;       // [M][2]
-  void* hb_out = nullptr;            // bf16 [M, N]
-  int64_t ld_hb = 0;
-  int ln_width = 512;
   float eps = 1e-5f;
   // EPI_BIAS_RESID_LN: the LayerNorm that follows the residual update is computed by the GEMM itself.
   // Clusters of four CTAs (two CTA pairs) cover the full 512-column rows of a 256-row block; the pairs
