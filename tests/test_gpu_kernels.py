@@ -263,7 +263,8 @@ def test_fmha_explicit_mask(Tq, Tk, kind):
     assert torch.allclose(g2.float(), r2, atol=2e-2, rtol=2e-2), _describe(g2, r2, f"fmha mask {kind}")
 
 
-@pytest.mark.parametrize("M,K", [(300, 512), (1000, 2048), (57632, 512), (4099, 2048)])
+@pytest.mark.parametrize("M,K", [(129, 512), (256, 512), (257, 2048), (300, 512), (1000, 2048), (4099, 2048),
+                                 (8448, 512), (8449, 512), (16897, 2048), (57632, 512)])
 def test_gemm_residual_layernorm_fused(M, K):
     """h += A W^T + b and u = LayerNorm(h) in one kernel (clusters of four CTAs exchange row statistics)."""
     lib = _lib.load()
