@@ -49,7 +49,6 @@ struct FmhaArgs {
   const uint8_t* mask; int64_t mask_b_stride, mask_q_stride;
 };
 int launch_fmha(const FmhaArgs& a, cudaStream_t stream);
-int launch_fmha2(const FmhaArgs& a, cudaStream_t stream);  // row-per-thread pipelined variant (fmha2.cu)
 
 // ---- memory-bound kernels ------------------------------------------------------------------------
 // concat(vis, aud, txt) fp32 -> bf16 [M, Cv+Ca+Ct]

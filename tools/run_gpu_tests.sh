@@ -14,5 +14,4 @@ run fmha tests/test_gpu_kernels.py -k "fmha"
 run model tests/test_gpu_model.py
 RP_LN_IN_GEMM=0 run model_ln_standalone tests/test_gpu_model.py -k "forward or inference or full_size"
 RP_FMHA_NQ=2 run fmha_nq2 tests/test_gpu_kernels.py -k fmha
-RP_FMHA_IMPL=1 run fmha_impl1 tests/test_gpu_kernels.py -k "fmha or mha"
 RP_GEMM_CG=1 run gemm_cg1 tests/test_gpu_kernels.py -k gemm
