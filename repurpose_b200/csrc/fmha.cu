@@ -1,7 +1,7 @@
 // Fused multi-head attention forward for sm_100a, head dim 64, bf16 operands, fp32 softmax:
 // one score row per thread, software-pipelined softmax.
 //
-// One CTA = one (batch, head, NQ 128-row query tiles).  Roles ((4 NQ + 2) warps):
+// One CTA = one (batch, head, NQ 128-row query tiles).  Roles ((4 NQ + 4) warps):
 //   warps 0 .. 4NQ-1 : softmax; warp w owns TMEM lanes 32 (w & 3) .. +31 of query tile w >> 2 and
 //                      thread <-> lane <-> query row: the whole 128-key score row of a key tile
 //                      lives in one thread (no cross-thread max / sum exchange, no barriers)
@@ -17,13 +17,16 @@
 //   E(s)   exp2 of chunk s (MUFU, with EMU_PAIRS of every 4 pairs evaluated on the FMA pipe),
 //   D(s-1) row-sum + bf16 pack of chunk s-1, tcgen05.st of its 8 P columns, and tcgen05.ld of chunk
 //          s-1 of the NEXT tile's scores into the registers that just became free,
-//   M(s-2) mask + running max of the next tile's chunk s-2,
-// so every exp2 result is consumed a step after it was issued, the next tile's row max is known when
-// the iteration ends, and MUFU work is spread over the whole iteration instead of alternating with
-// MUFU-idle phases.  Half h of S / P is handed back to the MMA warp in the middle / at the end of the
-// iteration, which gives QK^T_{j+2,h} and P V_{j,h} more than half an iteration to complete before the
-// softmax threads need their result.  Steps are separated by branches the compiler cannot fold, which
-// keeps ptxas from sinking each producer next to its consumer.
+//   M(s-2) running max of the next tile's chunk s-2 (masking of a partial last tile happens once, when
+//          the whole tile is in registers),
+// so the next tile's row max is known when the iteration ends and S is single-buffered in TMEM but
+// double-buffered through registers.  Half h of S / P is handed back to the MMA warps in the middle /
+// at the end of the iteration, which gives QK^T_{j+2,h} and P V_{j,h} more than half an iteration to
+// complete before the softmax threads need their result; barrier probes (mbarrier.test_wait) are
+// issued a step before their answer is needed.  The loop always prefetches "a next tile" (a dummy
+// re-run of QK^T after the last one), so the iteration body is one basic block: ptxas front-loads the
+// exp2 work and interleaves the rest, which measured faster than forcing a per-chunk schedule with
+// opaque branches (profiles/r01_notes.md).
 //
 // Softmax arithmetic (per score): packed f32x2 subtract of the running reference, exp2 either on the
 // MUFU (ex2.approx) or — for EMU_PAIRS out of every 4 pairs — by a Cody-Waite split plus a degree-3
@@ -98,30 +101,11 @@ __device__ unsigned long long g_fmha_trace[8 * 512];  // [role][event] = clock64
 #define TRACE(role, idx) do {} while (0)
 #endif
 
-// A branch neither nvcc nor ptxas can fold, hoist or unswitch: the condition mixes the loop counter
-// with a kernel parameter that is always 1.  It ends the basic block, which keeps the work of one
-// pipeline step together (ptxas otherwise hoists all 96 MUFU operations of an iteration to its top
-// and re-creates separate MUFU-only / MUFU-idle phases).
-#ifndef RP_FMHA_FENCE_EVERY
-#define RP_FMHA_FENCE_EVERY 9
-#endif
-#ifndef RP_FMHA_STEP_FENCE
-#define RP_FMHA_STEP_FENCE 1
-#endif
-__device__ __forceinline__ bool opaque_true(int j, int one) {
-#if RP_FMHA_STEP_FENCE
-  return (uint32_t(j) | uint32_t(one)) != 0u;
-#else
-  return true;
-#endif
-}
-
 struct FmhaParams {
   int B, H, Tq, Tk;
   const int32_t* kv_lens;
   const uint8_t* mask;
   int64_t mask_b_stride, mask_q_stride;
-  int one;  // always 1 (see opaque_true)
 };
 
 // ---- packed f32x2 helpers (sm_100 FFMA2/FADD2) ---------------------------------------------------
@@ -385,7 +369,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (qrow < p.Tq) mrow = p.mask + int64_t(b) * p.mask_b_stride + int64_t(qrow) * p.mask_q_stride;
       }
       uint32_t xs[128];  // scores of the current tile -> probabilities -> scores of the next tile
-      const int one = int(pin_u32(uint32_t(p.one)));
       const bool lane0 = pin_u32(lane == 0 ? 1u : 0u) != 0u;
 
       // running max of chunk c (CH scores)
@@ -457,7 +440,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (!probe_s) mbar_wait_spin(s_full(q, s > 1), par_next);
             tc_fence_after();
           }
-          if ((s % RP_FMHA_FENCE_EVERY) != 0 || opaque_true(j, one)) {
+          {
             if (tracer) TRACE(5, 16 * j + s);
             if (s == 0 || s == NCH / 2) {
               probe_pv = j > 0 ? mbar_test_wait(pv_done(q, s > 0), par_next) : 1u;
@@ -658,7 +641,7 @@ int launch_fmha(const FmhaArgs& a, cudaStream_t stream) {
   if ((rc = make_tmap_3d(&tmV, bf, a.v, cols, a.Tk, a.B, a.ldv * 2, a.bsv * 2, HD, KT))) return rc;
   if ((rc = make_tmap_3d(&tmO, bf, a.o, cols, a.Tq, a.B, a.ldo * 2, a.bso * 2, HD, QT))) return rc;
 
-  FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride, 1};
+  FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride};
   static const int nq_cfg = getenv("RP_FMHA_NQ") ? atoi(getenv("RP_FMHA_NQ")) : 1;
   static const int emu = getenv("RP_FMHA_EMU") ? atoi(getenv("RP_FMHA_EMU")) : 1;
   if (a.mask_mode == 1) return launch_variant<1, 1, 1>(tmQ, tmK, tmV, tmO, p, stream);
