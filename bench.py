@@ -7,8 +7,9 @@ Soft-NMS) on B200.
 One "step" = one batch of 32 synthetic videos at T = 1801 feature steps (BASELINE.json configs[1]:
 Repurpose.yaml model, batch 32 at max_seq_len) per GPU through forward -> decode -> Soft-NMS, plus
 (N > 1) the single all-gather of the fixed-slot segment lists.  `value` = videos/s with inputs
-resident in HBM; `e2e` = the same through the public `MMCTransformer.inference_` call with pinned
-HOST inputs (H2D of the features and D2H of the segment slots inside the timed region).
+resident in HBM; `e2e` = the same through the public `scheduler.InferencePipeline.run` call with pinned
+HOST inputs (H2D of the features and D2H of the segment slots inside the timed region, overlapped with
+the compute of neighbouring steps); `e2e.bf16_feature_rows` = the same with feature rows pre-converted to bf16.
 `--impl reference` times the reference algorithm's CPU path (the oracle port; the reference is pure
 Python/PyTorch and cannot travel to the GPU box) on the host cores.
 Prints ONE JSON line on rank 0.
