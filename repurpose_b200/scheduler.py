@@ -163,8 +163,9 @@ class InferencePipeline:
             ready.record(self.copy_stream)
         return dbatch, ready
 
-    def run(self, batches):
-        """yields, per input batch and in order, the list of per-video result dicts (CPU tensors)"""
+    def run(self, batches, raw: bool = False):
+        """yields, per input batch and in order, the list of per-video result dicts (CPU tensors);
+        with raw=True the batch's fixed-slot block `[B, 1 + 4K]` (a CPU tensor) instead."""
         main = torch.cuda.current_stream(self.dev)
         it = iter(batches)
         pending = []        # (slot, batch, host_slots, done_event)
@@ -199,13 +200,15 @@ class InferencePipeline:
             self._free[s] = done
             pending.append((b, host, done))
             if len(pending) >= self.depth:                 # retire the oldest while the GPU works
-                yield self._finish(*pending.pop(0))
+                yield self._finish(*pending.pop(0), raw)
         while pending:
-            yield self._finish(*pending.pop(0))
+            yield self._finish(*pending.pop(0), raw)
 
     @staticmethod
-    def _finish(batch, host, done):
+    def _finish(batch, host, done, raw=False):
         done.synchronize()
+        if raw:
+            return host.clone()
         out = unpack_slots(host)
         for o, vid, dur in zip(out, batch["video_id"], batch["duration"]):
             o["video_id"], o["duration"] = vid, dur
@@ -226,15 +229,17 @@ def run_sharded_inference(model, videos: Sequence[dict], test_cfg: dict, batch_s
     shards = shard_videos(lengths, world)
     owned = shards[rank]
     dev = model.device
-    local = torch.zeros(len(owned), 1 + 4 * kcap, dtype=torch.float32, device=dev)
+    # this rank's share: length-bucketed batches through the pipelined host->device path; every video is
+    # copied straight from its own (ideally pinned) arrays to its row offset of the device batch
+    from .features import ragged_batch
+    local = torch.zeros(len(owned), 1 + 4 * kcap, dtype=torch.float32)
     pos = 0
-    for idxs in make_batches(owned, batch_size):
-        batch = collate([videos[i] for i in idxs])
-        r = model.inference_device(batch, test_cfg)
-        k = r["scores"].shape[1]
-        slots = pack_slots(r["segments"], r["scores"], r["labels"], r["counts"])
-        local[pos:pos + len(idxs), :1 + 4 * k] = slots
-        pos += len(idxs)
+    pipe = InferencePipeline(model, test_cfg)
+    for slots in pipe.run((ragged_batch([videos[i] for i in idxs]) for idxs in make_batches(owned, batch_size)),
+                          raw=True):
+        local[pos:pos + slots.shape[0], :slots.shape[1]] = slots
+        pos += slots.shape[0]
+    local = local.to(dev)
     merged = gather_slots(local, owned, shards, group)
     out = unpack_slots(merged)
     for i, o in enumerate(out):

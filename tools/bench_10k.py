@@ -74,13 +74,9 @@ def main():
         local = torch.zeros(len(owned), 1 + 4 * kcap, dtype=torch.float32)
         pos = 0
         pipe = S.InferencePipeline(m, synth.TEST_CFG)
-        for out in pipe.run(host_batches()):
-            for o in out:
-                k = len(o["scores"])
-                local[pos, 0] = k
-                if k:
-                    local[pos, 1:1 + 4 * k] = torch.cat([o["segments"], o["scores"][:, None], o["labels"][:, None].float()], 1).reshape(-1)
-                pos += 1
+        for slots in pipe.run(host_batches(), raw=True):
+            local[pos:pos + slots.shape[0], :slots.shape[1]] = slots
+            pos += slots.shape[0]
         return S.gather_slots(local.to(dev), owned, shards)
 
     # warm-up on a few batches (kernel configuration, workspace allocation, pinned staging)
