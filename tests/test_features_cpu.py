@@ -33,3 +33,10 @@ def test_collate_ragged_layout():
     assert b["row_offsets"].tolist() == [0, 3] and b["text_offsets"].tolist() == [0, 2]
     assert b["text_lens"].tolist() == [2, 5] and b["lens"].tolist() == [3, 5]
     assert b["visual_feats"][3:].eq(4.0).all() and b["text_feats"][:2].eq(3.0).all()
+
+
+def test_affinity_helpers_are_best_effort():
+    from repurpose_b200.affinity import _parse_cpulist, bind_to_gpu_numa
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and _parse_cpulist("") == set()
+    info = bind_to_gpu_numa(0)              # no GPU / no sysfs here: must not raise, must not change anything
+    assert set(info) == {"numa_node", "cpus"}
