@@ -368,7 +368,8 @@ int launch_soft_nms(const float* scores, const float* segs, const int32_t* n, co
   RP_CHECK(Nmax >= 1 && Nmax <= MAX_NMS_N, "soft_nms: Nmax=%d out of range [1,%d]", Nmax, MAX_NMS_N);
   RP_CHECK(Kcap >= 1, "soft_nms: Kcap must be >= 1");
   const size_t smem = size_t(Nmax) * 5 * 4;
-  static size_t configured = 0;
+  static size_t configured_on[kMaxDevices];
+  size_t& configured = configured_on[current_device()];
   if (smem > configured) {
     RP_CUDA_CHECK(cudaFuncSetAttribute(soft_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        int(smem)));
@@ -397,7 +398,8 @@ int launch_decode_nms(const float* logits, const float* offsets, const int32_t* 
   while (sort_cap < T) sort_cap <<= 1;
   const int cand_cap = cfg.pre_nms_topk < T ? cfg.pre_nms_topk : T;
   const size_t smem = size_t(sort_cap) * 8 + size_t(cand_cap) * 7 * 4;
-  static size_t configured = 0;
+  static size_t configured_on[kMaxDevices];
+  size_t& configured = configured_on[current_device()];
   if (smem > configured) {
     RP_CUDA_CHECK(cudaFuncSetAttribute(decode_nms_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

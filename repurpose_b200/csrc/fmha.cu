@@ -600,7 +600,8 @@ template <int MASK_MODE, int EMU_PAIRS, int NQ>
 int launch_variant(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                    const CUtensorMap& tmO, const FmhaParams& p, cudaStream_t stream) {
   using C = Cfg<NQ>;
-  static bool configured = false;
+  static bool configured_on[kMaxDevices];
+  bool& configured = configured_on[current_device()];
   if (!configured) {
     RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));

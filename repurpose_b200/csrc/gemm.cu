@@ -460,8 +460,10 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
                cudaStream_t stream) {
   using C = Cfg<EPI, CG>;
   constexpr int CLUSTER = C::LNF ? 4 : CG;  // LNF: two CTA pairs per cluster share full 512-column rows
-  static bool configured = false;
-  static int max_clusters = 0;
+  static bool configured_on[kMaxDevices];
+  static int max_clusters_on[kMaxDevices];
+  bool& configured = configured_on[current_device()];
+  int& max_clusters = max_clusters_on[current_device()];
   if (!configured) {
     RP_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, CG>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));

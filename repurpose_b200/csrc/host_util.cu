@@ -44,9 +44,19 @@ const char* last_error() { return g_err; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+
 int num_sms() {
-  static int sms = -1;
-  if (sms < 0) {
+  static int sms_of[kMaxDevices];  // 0 = not queried yet
+  int& sms = sms_of[current_device()];
+  if (sms <= 0) {
     int dev = 0, n = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||

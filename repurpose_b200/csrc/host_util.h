@@ -54,6 +54,10 @@ inline int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dtype, const void*
   return make_tensor_map(out, dtype, 3, base, dims, strides, box);
 }
 
+// Function attributes (dynamic shared memory opt-in) and device properties are per device: launchers keep
+// their "already configured" state per device so that one process may drive several GPUs.
+constexpr int kMaxDevices = 64;
+int current_device();  // clamped to [0, kMaxDevices)
 int num_sms();
 void count_launch(int n = 1);
 int64_t launch_count();

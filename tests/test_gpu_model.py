@@ -509,3 +509,25 @@ def test_full_size_batch_properties(full_model):
         assert int(counts.sum()) > 0
     finally:
         m.load_state_dict(orig)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process_agree():
+    """Per-device launcher state (dynamic shared-memory opt-in, SM / cluster counts): the second device of a
+    process must work and give the same bits as the first."""
+    torch.manual_seed(29)
+    ref = MMCTransformer(512, 2048, 384, 512, 2, 3, 3, 8)
+    sd = synth.bias_reg_head({k: v.clone() for k, v in ref.state_dict().items()})
+    batch = synth.make_batch([300, 211, 160], seed=8)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = MMCTransformer(512, 2048, 384, 512, 2, 3, 3, 8)
+        m.load_state_dict(sd)
+        m = m.to(dev).eval()
+        db = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        _, l, o, _, _, f = m(db)
+        res = m.inference_(db, synth.TEST_CFG, to_host=True)
+        outs.append((l.cpu(), o.cpu(), f.cpu(), res))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    for a, b in zip(outs[0][3], outs[1][3]):
+        assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["segments"], b["segments"])
