@@ -14,11 +14,13 @@ import numpy as np
 import torch
 
 
-def load_video_features(visual_path, audio_path, text_path, time_range=None, n_labels=None) -> dict:
+def load_video_features(visual_path, audio_path, text_path, time_range=None, n_labels=None,
+                        dtype: str = "fp32", pin: bool = False) -> dict:
     """One video's features with the reference's slicing rules (RepurposeClip.__getitem__ :962-994):
     rows [int(t0), int(t1)) of each file when timeRange[0] != 0; duration = min(visual, audio[, labels])
     rows — the text file is NOT part of the minimum and may end up shorter (its missing rows are zeros
-    after collation)."""
+    after collation).  dtype="bf16" returns torch bf16 tensors (see `to_bf16`); pin=True returns pinned torch
+    tensors so that `ragged_batch` + `InferencePipeline` can DMA them without a host copy."""
     vis = np.load(visual_path, allow_pickle=True)
     aud = np.load(audio_path, allow_pickle=True)
     txt = np.load(text_path, allow_pickle=True)
@@ -29,8 +31,16 @@ def load_video_features(visual_path, audio_path, text_path, time_range=None, n_l
     if n_labels is not None:
         n = min(n, int(n_labels))
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
-    return {"visual_feats": f32(vis[:n]), "audio_feats": f32(aud[:n]), "text_feats": f32(txt[:n]),
-            "duration": n}
+    video = {"visual_feats": f32(vis[:n]), "audio_feats": f32(aud[:n]), "text_feats": f32(txt[:n]),
+             "duration": n}
+    if dtype == "bf16":   # rows as the device would round them anyway: half the upload, identical results
+        return to_bf16(video, pin=pin)
+    if dtype != "fp32":
+        raise ValueError(f"dtype must be 'fp32' or 'bf16', got {dtype!r}")
+    if pin:
+        for k in ("visual_feats", "audio_feats", "text_feats"):
+            video[k] = torch.from_numpy(video[k]).pin_memory()
+    return video
 
 
 def collate_ragged(videos: Sequence[dict], pin: bool = True) -> dict:

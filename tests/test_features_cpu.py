@@ -40,3 +40,21 @@ def test_affinity_helpers_are_best_effort():
     assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and _parse_cpulist("") == set()
     info = bind_to_gpu_numa(0)              # no GPU / no sysfs here: must not raise, must not change anything
     assert set(info) == {"numa_node", "cpus"}
+
+
+def test_load_video_features_bf16(tmp_path):
+    rng = np.random.default_rng(1)
+    arrs = {"v": rng.normal(size=(20, 8)).astype(np.float32), "a": rng.normal(size=(20, 16)).astype(np.float32),
+            "t": rng.normal(size=(18, 8)).astype(np.float32)}
+    for k, a in arrs.items():
+        np.save(tmp_path / f"{k}.npy", a)
+    paths = [tmp_path / "v.npy", tmp_path / "a.npy", tmp_path / "t.npy"]
+    v = load_video_features(*paths, dtype="bf16")
+    assert v["visual_feats"].dtype == torch.bfloat16 and v["duration"] == 20 and v["text_feats"].shape == (18, 8)
+    assert torch.equal(v["audio_feats"], torch.from_numpy(arrs["a"]).to(torch.bfloat16))   # round to nearest even
+    from repurpose_b200.features import ragged_batch
+    b = ragged_batch([v, v])
+    assert b["parts"]["visual_feats"][0].dtype == torch.bfloat16 and b["text_lens"].tolist() == [18, 18]
+    import pytest
+    with pytest.raises(ValueError):
+        load_video_features(*paths, dtype="fp16")
