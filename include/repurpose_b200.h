@@ -147,6 +147,13 @@ int32_t rp_atiou(const float* slots, int32_t n_videos, int32_t K, const double* 
                  const int32_t* gt_counts, int32_t Gmax, const double* thresholds, int32_t n_thr,
                  double* per_video, double* out, void* stream);
 
+/* Forward value of MMCTransformer.losses (models/MMCTransformer.py:159-179): sum over valid steps of
+ * sigmoid_focal_loss(logits, labels; alpha, gamma) (models/losses.py:5-53; the reference uses alpha = 0.7,
+ * gamma = 2).  logits / targets [n] f32, mask [n] u8 (non-zero = valid step), scratch >= 296 doubles,
+ * out [1] f32.  Deterministic.  No gradient: the training step is outside this path. */
+int32_t rp_focal_loss_sum(const float* logits, const float* targets, const uint8_t* mask, int64_t n, float alpha,
+                          float gamma, double* scratch, float* out, void* stream);
+
 /* ---- building blocks (also what the unit tests drive) ---------------------------------------- */
 /* D[M,N] = A[M,K] * W[N,K]^T + bias (+ReLU | +residual); A, W bf16 row-major with pitches lda/ldw
  * (elements); epilogue: 0 bf16 out, 1 bf16 out + ReLU, 2 f32 out, 3 f32 out + residual (may alias D).

@@ -513,6 +513,13 @@ int32_t rp_atiou(const float* slots, int32_t n_videos, int32_t K, const double* 
                       reinterpret_cast<cudaStream_t>(stream));
 }
 
+int32_t rp_focal_loss_sum(const float* logits, const float* targets, const uint8_t* mask, int64_t n, float alpha,
+                          float gamma, double* scratch, float* out, void* stream) {
+  RP_CHECK(logits && targets && mask && scratch && out, "rp_focal_loss_sum: null argument");
+  return launch_focal_loss_sum(logits, targets, mask, n, alpha, gamma, scratch, out,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+
 int32_t rp_gemm_bf16(int32_t epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
                      int64_t ldd, const float* bias, const float* resid, int64_t ldr, int32_t M,
                      int32_t N, int32_t K, void* stream) {

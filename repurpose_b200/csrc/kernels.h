@@ -111,4 +111,8 @@ int launch_atiou(const float* slots, int n_videos, int K, const double* gt, cons
                  int Gmax, const double* thresholds, int n_thr, double* per_video, double* out,
                  cudaStream_t stream);
 
+// masked sigmoid focal loss, summed (forward of MMCTransformer.losses); scratch: >= 296 doubles
+int launch_focal_loss_sum(const float* logits, const float* targets, const uint8_t* mask, int64_t n, float alpha,
+                          float gamma, double* scratch, float* out, cudaStream_t stream);
+
 }  // namespace rp

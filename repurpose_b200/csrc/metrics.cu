@@ -94,3 +94,71 @@ int launch_atiou(const float* slots, int n_videos, int K, const double* gt, cons
 }
 
 }  // namespace rp
+
+// ---------------------------------------------------------------------------------------------
+// Masked sigmoid focal loss, summed (forward value of MMCTransformer.losses, models/MMCTransformer.py:
+// 159-179 with sigmoid_focal_loss of models/losses.py:5-53): fp32 element math in the reference's
+// operation order, deterministic two-stage reduction (per-block partials in float64, then one block
+// adds them in index order), so the same inputs always give the same bits.
+namespace rp {
+namespace {
+
+constexpr int FL_BLOCKS = 296;   // two CTAs per SM
+constexpr int FL_THREADS = 256;
+
+__device__ __forceinline__ float focal_term(float x, float t, float alpha, float gamma) {
+  const float p = 1.0f / (1.0f + expf(-x));  // torch.sigmoid
+  // binary_cross_entropy_with_logits: max(x, 0) - x t + log1p(exp(-|x|))
+  const float ce = __fadd_rn(__fsub_rn(fmaxf(x, 0.0f), __fmul_rn(x, t)), log1pf(expf(-fabsf(x))));
+  const float p_t = __fadd_rn(__fmul_rn(p, t), __fmul_rn(1.0f - p, 1.0f - t));
+  const float om = 1.0f - p_t;
+  const float mod = gamma == 2.0f ? __fmul_rn(om, om) : powf(om, gamma);
+  float loss = __fmul_rn(ce, mod);
+  if (alpha >= 0.0f) {
+    const float alpha_t = __fadd_rn(__fmul_rn(alpha, t), __fmul_rn(1.0f - alpha, 1.0f - t));
+    loss = __fmul_rn(alpha_t, loss);
+  }
+  return loss;
+}
+
+__global__ void __launch_bounds__(FL_THREADS)
+focal_partial_kernel(const float* __restrict__ logits, const float* __restrict__ targets,
+                     const uint8_t* __restrict__ mask, int64_t n, float alpha, float gamma,
+                     double* __restrict__ partial) {
+  __shared__ double red[FL_THREADS / 32];
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * int64_t(FL_THREADS) + threadIdx.x; i < n; i += int64_t(gridDim.x) * FL_THREADS) {
+    if (mask[i]) acc += double(focal_term(logits[i], targets[i], alpha, gamma));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < FL_THREADS / 32; ++w) s += red[w];
+    partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void focal_final_kernel(const double* __restrict__ partial, int n_partial, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n_partial; ++i) s += partial[i];
+    out[0] = float(s);
+  }
+}
+
+}  // namespace
+
+int launch_focal_loss_sum(const float* logits, const float* targets, const uint8_t* mask, int64_t n, float alpha,
+                          float gamma, double* scratch, float* out, cudaStream_t stream) {
+  RP_CHECK(n > 0, "focal_loss: empty input");
+  focal_partial_kernel<<<FL_BLOCKS, FL_THREADS, 0, stream>>>(logits, targets, mask, n, alpha, gamma, scratch);
+  focal_final_kernel<<<1, 32, 0, stream>>>(scratch, FL_BLOCKS, out);
+  count_launch(2);
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+}  // namespace rp

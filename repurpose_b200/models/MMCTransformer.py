@@ -226,9 +226,24 @@ class MMCTransformer(nn.Module):
         check(_lib.load().rp_profile_end(self._handle, ms, cnt), "rp_profile_end")
         return {t: (float(ms[i]), int(cnt[i])) for i, t in enumerate(_lib.PROFILE_TAGS)}
 
+    @torch.no_grad()
     def losses(self, masks, out_cls_logits, out_offsets, gt_cls_labels, gt_offsets, feats):
-        raise NotImplementedError(
-            "training losses are outside the inference hot path (SURVEY.md §8 f3)")
+        """Forward VALUE of the reference's loss (models/MMCTransformer.py:159-179): masked sigmoid focal
+        loss (alpha 0.7, gamma 2, models/losses.py:5-53) summed over valid steps, as main.py's evaluation
+        loop logs it (main.py:626-634).  Returns {'cls_loss': 0-dim fp32 tensor on the device}.  No
+        autograd graph: the training step is outside this path."""
+        dev = self.device
+        logits = out_cls_logits.to(dev, torch.float32).reshape(-1).contiguous()
+        targets = gt_cls_labels.to(dev, torch.float32).reshape(-1).contiguous()
+        mask = masks.to(dev).reshape(-1).ne(0).to(torch.uint8).contiguous()
+        if not (logits.numel() == targets.numel() == mask.numel()):
+            raise ValueError("losses: logits [B,T,1], labels [B,T] and masks [B,1,T] must cover the same steps")
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        scratch = torch.empty(296, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.load().rp_focal_loss_sum(ptr(logits), ptr(targets), ptr(mask), logits.numel(), 0.7, 2.0,
+                                                ptr(scratch), ptr(out), cur_stream()), "rp_focal_loss_sum")
+        return {"cls_loss": out[0]}
 
     # --------------------------------------------------------------------------------- decode
     @staticmethod

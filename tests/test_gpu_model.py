@@ -531,3 +531,21 @@ def test_two_devices_in_one_process_agree():
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
     for a, b in zip(outs[0][3], outs[1][3]):
         assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["segments"], b["segments"])
+
+
+def test_losses_value_matches_reference_golden(tiny_model, golden_dir):
+    """MMCTransformer.losses (masked sigmoid focal loss, summed) vs the reference's values; fp32 sums of up
+    to 3600 terms: 1e-5 relative covers the summation order."""
+    from oracle import losses as ol
+    g = np.load(golden_dir / "losses_cases.npz")
+    for name in g["names"]:
+        masks = torch.from_numpy(g[f"{name}_masks"]).to(DEV)
+        logits = torch.from_numpy(g[f"{name}_logits"]).to(DEV)
+        labels = torch.from_numpy(g[f"{name}_labels"]).to(DEV)
+        out = tiny_model.losses(masks, logits, None, labels, None, None)
+        assert set(out) == {"cls_loss"} and out["cls_loss"].dim() == 0 and out["cls_loss"].is_cuda
+        ref = float(g[f"{name}_loss"])
+        assert abs(float(out["cls_loss"]) - ref) <= 1e-5 * abs(ref), (name, float(out["cls_loss"]), ref)
+        again = tiny_model.losses(masks, logits, None, labels, None, None)["cls_loss"]
+        assert torch.equal(again, out["cls_loss"])                       # deterministic reduction
+        assert abs(float(ol.losses(masks.cpu(), logits.cpu(), labels.cpu())) - ref) <= 1e-6 * abs(ref)

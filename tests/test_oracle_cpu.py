@@ -120,3 +120,15 @@ def test_calculate_tiou_restatement():
     r = mmct.calculate_tiou(gt, pred, (0.5, 0.9))
     assert r[0.5] == pytest.approx(2 / 3) and r[0.9] == pytest.approx(1 / 3)
     assert mmct.calculate_tiou(gt, [], (0.5,))[0.5] == 0
+
+
+def test_losses_oracle_matches_reference_golden():
+    """oracle/losses.py vs the reference's MMCTransformer.losses values (tests/golden/losses_cases.npz)."""
+    from pathlib import Path
+    from oracle import losses as ol
+    g = np.load(Path(__file__).parent / "golden" / "losses_cases.npz")
+    for name in g["names"]:
+        got = ol.losses(torch.from_numpy(g[f"{name}_masks"]), torch.from_numpy(g[f"{name}_logits"]),
+                        torch.from_numpy(g[f"{name}_labels"]))
+        ref = float(g[f"{name}_loss"])
+        assert abs(float(got) - ref) <= 1e-6 * abs(ref), (name, float(got), ref)
