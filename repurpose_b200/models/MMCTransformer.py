@@ -299,23 +299,33 @@ class MMCTransformer(nn.Module):
     def inference_device(self, batch, inference_settings):
         """forward + decode + Soft-NMS with no host synchronisation: returns the fixed-slot device
         tensors of `_run_decode` (segments [B,K,2], scores, dscores, labels [B,K], counts [B])."""
-        _, logits, offsets, _, _, _ = self.forward(batch)
+        return self.decode_device(self.forward(batch), batch, inference_settings)
+
+    def decode_device(self, output, batch, inference_settings):
+        """decode + Soft-NMS of an existing `forward(batch)` result (the 6-tuple): main.py's evaluation loop
+        calls `model(batch)` for the loss and then `inference_(batch, ...)`, which in the reference runs the
+        whole forward a second time (main.py:626, :673-676); `inference_(batch, cfg, output=output)` reuses it."""
+        masks, logits, offsets = output[0], output[1], output[2]
+        dev = self.device
         max_seg = [int(np.ceil((int(v) // 60) * inference_settings["max_seg_per_min"]))
                    for v in batch["duration"]]
         B, T = logits.shape[0], logits.shape[1]
-        return self._run_decode(logits.view(B, T), offsets, self._last_lens, max_seg,
+        lens = masks.to(dev).reshape(B, -1).ne(0).sum(dim=1, dtype=torch.int32).contiguous()
+        return self._run_decode(logits.reshape(B, T).contiguous(), offsets.contiguous(), lens, max_seg,
                                 inference_settings)
 
     @torch.no_grad()
-    def inference_(self, batch, inference_settings, to_host=False):
+    def inference_(self, batch, inference_settings, to_host=False, output=None):
         """forward -> per-video decode -> Soft-NMS, all on the device (reference :231-275).
         Returns one dict per video: segments [K,2] f32 (feature-grid seconds), scores [K] f32
         (the candidate's probability, i.e. the reference's CUDA semantics),
         labels [K] int64, video_id, duration — in Soft-NMS selection order.
         Tensors live on the model's device like the reference's; `to_host=True` (extension) returns
         CPU tensors taken from one packed device->host copy, which is what callers that immediately
-        do `.tolist()` (inference.py:47, main.py:689) want."""
-        r = self.inference_device(batch, inference_settings)
+        do `.tolist()` (inference.py:47, main.py:689) want.  `output` (extension): a `forward(batch)` result to
+        decode instead of running the forward again."""
+        r = (self.inference_device(batch, inference_settings) if output is None
+             else self.decode_device(output, batch, inference_settings))
         vid_idxs = batch["video_id"]
         vid_lens = batch["duration"]
         results = []

@@ -549,3 +549,27 @@ def test_losses_value_matches_reference_golden(tiny_model, golden_dir):
         again = tiny_model.losses(masks, logits, None, labels, None, None)["cls_loss"]
         assert torch.equal(again, out["cls_loss"])                       # deterministic reduction
         assert abs(float(ol.losses(masks.cpu(), logits.cpu(), labels.cpu())) - ref) <= 1e-6 * abs(ref)
+
+
+def test_eval_loop_reuses_the_forward():
+    """main.py's evaluation: output = model(batch); losses(*output); inference_(batch, cfg) — with output= the
+    second forward disappears and the results are identical."""
+    torch.manual_seed(31)
+    m = MMCTransformer(512, 2048, 384, 512, 2, 3, 3, 8)
+    m.load_state_dict(synth.bias_reg_head({k: v.clone() for k, v in m.state_dict().items()}))
+    m = m.to(DEV).eval()
+    batch = synth.make_batch([400, 333, 150], seed=9)
+    db = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    db["labels"] = (torch.rand(3, 400, device=DEV) < 0.2).float()
+    output = m(db)
+    loss = m.losses(*output)["cls_loss"]
+    assert torch.isfinite(loss) and float(loss) > 0
+    from repurpose_b200 import _lib
+    n0 = _lib.load().rp_launch_count()
+    a = m.inference_(db, synth.TEST_CFG, output=output)
+    n1 = _lib.load().rp_launch_count()
+    b = m.inference_(db, synth.TEST_CFG)
+    n2 = _lib.load().rp_launch_count()
+    assert n1 - n0 < 4 < n2 - n1                       # decode only vs forward + decode
+    for x, y in zip(a, b):
+        assert torch.equal(x["labels"], y["labels"]) and torch.equal(x["segments"], y["segments"]) and torch.equal(x["scores"], y["scores"])
