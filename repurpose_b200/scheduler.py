@@ -96,7 +96,8 @@ def collate(videos: Sequence[dict], pin: bool = False) -> dict:
         if pin:
             x = x.pin_memory()
         for i, v in enumerate(videos):
-            x[i, :lens[i]] = torch.as_tensor(v[key], dtype=torch.float32)
+            src = torch.as_tensor(v[key], dtype=torch.float32)[:lens[i]]   # a shorter text track stays zero-padded
+            x[i, :src.shape[0]] = src
         batch[key] = x
     batch["masks"] = (torch.arange(T)[None, :] < torch.tensor(lens)[:, None])[:, None, :]
     batch["labels"] = torch.zeros(len(videos), T)
@@ -216,17 +217,21 @@ class InferencePipeline:
 
 
 def run_sharded_inference(model, videos: Sequence[dict], test_cfg: dict, batch_size: int = 32,
-                          kcap: int | None = None, group=None) -> list[dict]:
+                          kcap: int | None = None, group=None, return_slots: bool = False, shards=None):
     """Shard `videos` (list of per-video host dicts with visual_feats/audio_feats/text_feats [T,C])
     across the ranks of `group`, run inference on this rank's share, all-gather, and return one
-    result dict per video in the caller's order (identical on every rank)."""
+    result dict per video in the caller's order (identical on every rank).  return_slots=True also
+    returns the gathered `[n_videos, 1 + 4K]` slot tensor (device) for `metrics.atiou`.  `shards`: a shard map
+    every rank computed identically beforehand (e.g. to decide which feature files to load); entries of
+    `videos` this rank does not own are then never touched except for their length."""
     import numpy as np
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     lengths = [int(v["visual_feats"].shape[0]) for v in videos]
     if kcap is None:
         kcap = max(1, max(int(np.ceil((l // 60) * test_cfg["max_seg_per_min"])) for l in lengths))
-    shards = shard_videos(lengths, world)
+    if shards is None:
+        shards = shard_videos(lengths, world)
     owned = shards[rank]
     dev = model.device
     # this rank's share: length-bucketed batches through the pipelined host->device path; every video is
@@ -245,4 +250,4 @@ def run_sharded_inference(model, videos: Sequence[dict], test_cfg: dict, batch_s
     for i, o in enumerate(out):
         o["video_id"] = videos[i].get("video_id", i)
         o["duration"] = lengths[i]
-    return out
+    return (out, merged) if return_slots else out

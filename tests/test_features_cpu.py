@@ -58,3 +58,25 @@ def test_load_video_features_bf16(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         load_video_features(*paths, dtype="fp16")
+
+
+def test_infer_read_test_set_follows_reference_rules(tmp_path):
+    import json
+    from repurpose_b200.infer import read_test_set
+    dirs = {k: tmp_path / k for k in ("video_path", "audio_path", "text_path")}
+    for d in dirs.values():
+        d.mkdir()
+    for vid in ("a", "b"):                       # "c" lacks its audio file -> filtered out like the reference does
+        for d in dirs.values():
+            np.save(d / f"{vid}.npy", np.zeros((5, 4), dtype=np.float32))
+    np.save(dirs["video_path"] / "c.npy", np.zeros((5, 4), dtype=np.float32))
+    labels = [{"youtube_id": "a", "timeRange": [0, 99.5], "timeRangeOffset": [0, 99.5], "segmentsOffset": [[1.0, 20.0]]},
+              {"youtube_id": "c", "timeRange": [0, 10], "timeRangeOffset": [0, 10], "segmentsOffset": []},
+              {"youtube_id": "b", "timeRange": [30, 80.2], "timeRangeOffset": [0, 50.2], "segmentsOffset": [[2.0, 30.0], [31.0, 45.0]]}]
+    (tmp_path / "test.json").write_text(json.dumps(labels))
+    cfg = {"label_path": str(tmp_path / "test.json"), **{k: str(v) for k, v in dirs.items()}}
+    es = read_test_set(cfg)
+    assert [e["video_id"] for e in es] == ["a", "b"]
+    assert es[0]["n_labels"] == 100 and es[1]["n_labels"] == 51          # int(t1 - t0) + 1
+    assert es[1]["time_range"] == [30, 80.2] and es[1]["gt_segments"] == [[2.0, 30.0], [31.0, 45.0]]
+    assert es[0]["paths"][1].endswith("audio_path/a.npy")

@@ -573,3 +573,53 @@ def test_eval_loop_reuses_the_forward():
     assert n1 - n0 < 4 < n2 - n1                       # decode only vs forward + decode
     for x, y in zip(a, b):
         assert torch.equal(x["labels"], y["labels"]) and torch.equal(x["segments"], y["segments"]) and torch.equal(x["scores"], y["scores"])
+
+
+def test_infer_cli_matches_the_reference_style_loop(tmp_path, capsys):
+    """repurpose_b200.infer (sharded / pipelined / device AtIoU) vs the reference's flow: batch size 1,
+    inference_ per video, calculate_tiou on the host (inference.py:39-55)."""
+    import json
+    import yaml
+    from repurpose_b200 import infer
+    from repurpose_b200.features import load_video_features
+    from repurpose_b200.scheduler import collate
+    rng = np.random.default_rng(5)
+    dirs = {k: tmp_path / k for k in ("video_path", "audio_path", "text_path")}
+    for d in dirs.values():
+        d.mkdir()
+    dims = {"video_path": 512, "audio_path": 2048, "text_path": 384}
+    labels = []
+    for i, n in enumerate([420, 333, 250, 190, 301, 75]):
+        vid = f"vid{i}"
+        for k, d in dirs.items():
+            extra = {"video_path": 3, "audio_path": 0, "text_path": -2}[k]        # files of slightly different lengths
+            np.save(d / f"{vid}.npy", rng.normal(size=(n + extra, dims[k])).astype(np.float32))
+        gt = sorted([sorted(rng.uniform(0, n, size=2).tolist()) for _ in range(4)])
+        labels.append({"youtube_id": vid, "timeRange": [0, float(n - 1)], "timeRangeOffset": [0, float(n - 1)],
+                       "segments": gt, "segmentsOffset": gt})
+    (tmp_path / "test.json").write_text(json.dumps(labels))
+    model_cfg = dict(synth.MODEL_CFG, self_num_layers=2)
+    cfg = {"test_dataset": {"label_path": str(tmp_path / "test.json"), **{k: str(v) for k, v in dirs.items()}},
+           "model": model_cfg, "test_cfg": dict(synth.TEST_CFG)}
+    (tmp_path / "cfg.yaml").write_text(yaml.safe_dump(cfg))
+    torch.manual_seed(41)
+    m = MMCTransformer(**model_cfg)
+    sd = synth.bias_reg_head({k: v.clone() for k, v in m.state_dict().items()})
+    torch.save({"model": sd}, tmp_path / "ckpt.pth")
+
+    got = infer.main(["--config_path", str(tmp_path / "cfg.yaml"), "--resume", str(tmp_path / "ckpt.pth"), "--batch-size", "4"])
+    printed = capsys.readouterr().out
+    assert "average tIoU:" in printed
+
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    preds, gts = [], []
+    for e in infer.read_test_set(cfg["test_dataset"]):
+        v = load_video_features(*e["paths"], time_range=e["time_range"], n_labels=e["n_labels"])
+        r = m.inference_(collate([v]), cfg["test_cfg"], to_host=True)[0]          # batch size 1, like the reference
+        preds.append(r["segments"].tolist())
+        gts.append(e["gt_segments"])
+    want, _ = mmct.atiou(gts, preds)
+    assert abs(got - want) < 1e-12, (got, want)
+    got16 = infer.main(["--config_path", str(tmp_path / "cfg.yaml"), "--resume", str(tmp_path / "ckpt.pth"), "--bf16-features"])
+    assert got16 == got
