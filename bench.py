@@ -217,7 +217,7 @@ def run_ours(args, rank, world, local_rank):
     # DRAM bytes per FMHA launch at this shape from the committed `ncu --set full` capture
     # (profiles/r01_prof_fmha_final_summary.txt: 177.1 MB read + 42.0 MB written; algorithmic
     # 177 MB qkv in + 59 MB o out) — only valid for the default B=32, T=1801 workload
-    fmha_traffic = 219.86e6 if (BATCH, SEQ) == (32, 1801) else None
+    fmha_traffic = 220.34e6 if (BATCH, SEQ) == (32, 1801) else None
     roofline = {"kernel": "fmha_fwd_kernel<mask=0,emu=1,nq=1>", "bound": "tensor",
                 "achieved": fm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": fm_tflops / peaks["tflops_sustained"], "traffic": fmha_traffic,
