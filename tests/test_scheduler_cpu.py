@@ -80,7 +80,7 @@ def _worker(rank, world, port, n_videos, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_videos", [5, 64])
+@pytest.mark.parametrize("n_videos", [1, 5, 64])   # 1: one rank owns nothing
 def test_all_gather_reconstructs_global_order_world2(n_videos):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
