@@ -177,6 +177,12 @@ int32_t rp_fmha(const void* q, const void* k, const void* v, void* o, int64_t ld
                 const uint8_t* mask, int64_t mask_b_stride, int64_t mask_q_stride, void* stream);
 int32_t rp_concat_cast(const float* vis, const float* aud, const float* txt, int32_t Cv, int32_t Ca,
                        int32_t Ct, void* out_bf16, int64_t M, void* stream);
+/* masks [B, T] (one byte per step, non-zero = valid; the bool mask of dataset/RepurposeClip.py:528-531 viewed
+ * as bytes) -> lens [B] int32 = valid steps per video, *not_aligned (device int32) = 1 if some mask is not
+ * left-aligned (mask[b][t] != (t < lens[b])).  The reference hands the mask itself to nn.MultiheadAttention
+ * (models/MMCTransformer.py:132-138); rp_forward / rp_decode_nms take lengths, so the host mirror refuses
+ * anything this flag marks. */
+int32_t rp_mask_lens(const uint8_t* mask, int32_t B, int32_t T, int32_t* lens, int32_t* not_aligned, void* stream);
 int32_t rp_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
 /* LayerNorm over rows of 512, eps 1e-5.  mode 0: y=bf16(LN(x)); 1: h=LN(x)+pe[row%T] (f32 out),
  * y=bf16(LN1(h)); 2: f=relu(LN(x)) (f32 out), y=bf16(LN1(f)), y2=bf16(LN2(f)); 3: f32 out = LN(x). */

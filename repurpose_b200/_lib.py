@@ -56,6 +56,7 @@ SIGNATURES = {
     "rp_fmha": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                         c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i64, c_i64, c_vp]),
     "rp_concat_cast": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp]),
+    "rp_mask_lens": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "rp_cast_bf16": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
     "rp_layernorm512": (c_i32, [c_i32, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                 c_vp, c_vp, c_vp, c_vp]),

@@ -559,6 +559,11 @@ int32_t rp_concat_cast(const float* vis, const float* aud, const float* txt, int
                             reinterpret_cast<cudaStream_t>(stream));
 }
 
+int32_t rp_mask_lens(const uint8_t* mask, int32_t B, int32_t T, int32_t* lens, int32_t* not_aligned, void* stream) {
+  RP_CHECK(mask && lens && not_aligned, "rp_mask_lens: null argument");
+  return launch_mask_lens(mask, B, T, lens, not_aligned, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int32_t rp_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream) {
   RP_CHECK(in && out_bf16, "rp_cast_bf16: null argument");
   return launch_cast_bf16(in, out_bf16, n, reinterpret_cast<cudaStream_t>(stream));

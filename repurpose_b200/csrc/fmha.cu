@@ -41,6 +41,7 @@
 // Q must arrive pre-scaled by log2(e)/sqrt(64) so that S is already in the exp2 domain.
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 
 #include "ptx.cuh"
 #include "host_util.h"
@@ -94,7 +95,7 @@ constexpr float MASK_FILL_LOG2 = -1.0e9f * 1.4426950408889634f;
 __device__ unsigned long long g_fmha_trace[8 * 512];  // [role][event] = clock64
 #define TRACE(role, idx)                                                              \
   do {                                                                                \
-    if (blockIdx.x == 2 && blockIdx.y == 3 && blockIdx.z == RP_TRACE_Z && (idx) < 512) \
+    if (blockIdx.x == 2 + 15 * (3 + 8 * RP_TRACE_Z) && (idx) < 512)                    \
       g_fmha_trace[(role) * 512 + (idx)] = clock64();                                 \
   } while (0)
 #else
@@ -188,10 +189,22 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
+  // 1-D grid: every (batch, head)'s query blocks but the last come first, the last ones — the only ones
+  // that can be partial, i.e. the short CTAs — at the end, where they fill the ragged end of the launch
+  const int nqb = (p.Tq + NQ * QT - 1) / (NQ * QT);
+  const int n_lead = (nqb - 1) * p.H * p.B;
+  int qb, bh;
+  if (int(blockIdx.x) < n_lead) {
+    qb = int(blockIdx.x) % (nqb - 1);
+    bh = int(blockIdx.x) / (nqb - 1);
+  } else {
+    qb = nqb - 1;
+    bh = int(blockIdx.x) - n_lead;
+  }
+  const int head = bh % p.H;
+  const int b = bh / p.H;
 
-  const int q_start0 = blockIdx.x * (NQ * QT);
+  const int q_start0 = qb * (NQ * QT);
   const bool q1_active = NQ == 2 && (q_start0 + QT) < p.Tq;
   const int nq = q1_active ? 2 : 1;
   int kv_len = p.Tk;
@@ -200,6 +213,13 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     kv_len = kv_len < 0 ? 0 : (kv_len > p.Tk ? p.Tk : kv_len);
   }
   const int n_kv = (kv_len + KT - 1) / KT;
+  const int nv_last = kv_len - (n_kv - 1) * KT;  // valid keys of the last tile (1 .. KT)
+  const int nch_last = (nv_last + 15) >> 4;      // its 16-key chunks: the only ones multiplied and exponentiated
+  // softmax warps of query tile q with at least one row below Tq (the others exit at once)
+  auto warps_of = [&](int q) {
+    const int r = p.Tq - (q_start0 + q * QT);
+    return r <= 0 ? 0 : (r >= QT ? 4 : (r + 31) >> 5);
+  };
 
   if (warp == C::PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -208,10 +228,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmO);
     for (int q = 0; q < 2; ++q) {
       mbar_init(q_full(q), 1);
+      const int nw = warps_of(q) > 0 ? warps_of(q) : 1;
       for (int h = 0; h < 2; ++h) {
         mbar_init(s_full(q, h), 1);
-        mbar_init(s_free(q, h), 4);
-        mbar_init(p_ready(q, h), 4);
+        mbar_init(s_free(q, h), nw);
+        mbar_init(p_ready(q, h), nw);
         mbar_init(pv_done(q, h), 1);
       }
     }
@@ -278,17 +299,20 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // other's barrier waits: the softmax hands S_h and P_h back at the same moment and needs both
     // results half an iteration later.
     if (n_kv > 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(QT, KT / 2, false, false);
-      // S_q[:, 64h .. 64h+64) = Q_q K[64h .. 64h+64)^T
-      auto issue_qk = [&](int q, int st, int h, uint32_t commit_bar, uint32_t commit_bar2) {
+      // S_q[:, 64h .. 64h+ncols) = Q_q K[64h .. 64h+ncols)^T; ncols = 0 (a half of the last tile without
+      // valid keys): nothing to multiply, the commit alone completes the barrier phase
+      auto issue_qk = [&](int q, int st, int h, int ncols, uint32_t commit_bar, uint32_t commit_bar2) {
         if (elect_one()) {
-          const uint64_t da = make_smem_desc_sw128(base + SMEM_Q_OFF + q * TILE_BYTES, 1024, 16);
-          const uint64_t db =
-              make_smem_desc_sw128(base + SMEM_K_OFF + st * TILE_BYTES + h * (TILE_BYTES / 2), 1024, 16);
+          if (ncols > 0) {
+            const uint32_t idesc_s = make_idesc_bf16(QT, 0, false, false) | (uint32_t(ncols >> 3) << 17);
+            const uint64_t da = make_smem_desc_sw128(base + SMEM_Q_OFF + q * TILE_BYTES, 1024, 16);
+            const uint64_t db =
+                make_smem_desc_sw128(base + SMEM_K_OFF + st * TILE_BYTES + h * (TILE_BYTES / 2), 1024, 16);
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            mma_ss(tmem_base + TM_S + q * 128 + h * 64, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc_s,
-                   k > 0 ? 1u : 0u);
+            for (int k = 0; k < HD / 16; ++k)
+              mma_ss(tmem_base + TM_S + q * 128 + h * 64, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc_s,
+                     k > 0 ? 1u : 0u);
+          }
           tc_commit(commit_bar);
           if (commit_bar2 != 0) tc_commit(commit_bar2);
         }
@@ -297,23 +321,25 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int q = 0; q < nq; ++q) mbar_wait(q_full(q), 0);
       mbar_wait(k_full(0), 0);
       tc_fence_after();
+      auto ncols_of = [&](int i, int h) {
+        if (i + 1 < n_kv) return KT / 2;
+        const int c = nch_last * 16 - (KT / 2) * h;
+        return c < 0 ? 0 : (c > KT / 2 ? KT / 2 : c);
+      };
       for (int h = 0; h < 2; ++h)
         for (int q = 0; q < nq; ++q)
-          issue_qk(q, 0, h, s_full(q, h), (h == 1 && q == nq - 1) ? k_empty(0) : 0u);
-      // The softmax loop is branch-free: it always prefetches "the next tile".  After the last real
-      // tile that is a dummy S (tile n_kv-1 once more, from the K stage that is still resident; no
-      // ring bookkeeping), whose scores are never used.  S_i may be issued once the softmax warps
-      // have read S_{i-1} (s_free phase i-1).
-      for (int i = 1; i <= n_kv; ++i) {
-        const bool real = i < n_kv;
-        const int st = (real ? i : n_kv - 1) % K_STAGES;
-        if (real) mbar_wait(k_full(st), uint32_t(i / K_STAGES) & 1u);
+          issue_qk(q, 0, h, ncols_of(0, h), s_full(q, h), (h == 1 && q == nq - 1) ? k_empty(0) : 0u);
+      // S_i may be issued once the softmax warps have read S_{i-1} (s_free phase i-1).  The last tile is
+      // only multiplied over its valid 16-key chunks.
+      for (int i = 1; i < n_kv; ++i) {
+        const int st = i % K_STAGES;
+        mbar_wait(k_full(st), uint32_t(i / K_STAGES) & 1u);
         for (int h = 0; h < 2; ++h)
           for (int q = 0; q < nq; ++q) {
             mbar_wait(s_free(q, h), uint32_t(i - 1) & 1u);
             tc_fence_after();
             if (lane == 0) TRACE(2 + h, i);
-            issue_qk(q, st, h, s_full(q, h), (real && h == 1 && q == nq - 1) ? k_empty(st) : 0u);
+            issue_qk(q, st, h, ncols_of(i, h), s_full(q, h), (h == 1 && q == nq - 1) ? k_empty(st) : 0u);
           }
       }
     }
@@ -322,14 +348,15 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (n_kv > 0) {
       constexpr uint32_t idesc_o = make_idesc_bf16(QT, HD, false, true);  // V is MN-major
       // O_q += P_q[:, 64h .. 64h+64) V[64h .. 64h+64)
-      auto issue_pv = [&](int q, int st, int h, bool acc, uint32_t commit_bar, uint32_t commit_bar2) {
+      auto issue_pv = [&](int q, int st, int h, bool acc, int ksteps, uint32_t commit_bar, uint32_t commit_bar2) {
         if (elect_one()) {
           // A: P in TMEM, 16 keys = 8 packed columns per step; B: 16 key rows of 128 B each
           const uint64_t db = make_smem_desc_sw128(base + SMEM_V_OFF + st * TILE_BYTES, 1024, 1024);
 #pragma unroll
           for (int k = 0; k < KT / 32; ++k)
-            mma_ts(tmem_base + TM_O + q * 64, tmem_base + TM_P + q * 64 + h * 32 + k * 8,
-                   db + uint64_t(128 * (4 * h + k)), idesc_o, (acc || k > 0) ? 1u : 0u);
+            if (k < ksteps)
+              mma_ts(tmem_base + TM_O + q * 64, tmem_base + TM_P + q * 64 + h * 32 + k * 8,
+                     db + uint64_t(128 * (4 * h + k)), idesc_o, (acc || k > 0) ? 1u : 0u);
           tc_commit(commit_bar);
           if (commit_bar2 != 0) tc_commit(commit_bar2);
         }
@@ -343,7 +370,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_wait(p_ready(q, h), uint32_t(j) & 1u);
             tc_fence_after();
             if (lane == 0) TRACE(h, j);
-            issue_pv(q, vst, h, j > 0 || h > 0, pv_done(q, h), (h == 1 && q == nq - 1) ? v_empty(vst) : 0u);
+            const int c = j + 1 < n_kv ? 4 : nch_last - 4 * h;  // 16-key steps of this half (last tile: valid ones)
+            issue_pv(q, vst, h, j > 0 || h > 0, c < 0 ? 0 : (c > 4 ? 4 : c), pv_done(q, h),
+                     (h == 1 && q == nq - 1) ? v_empty(vst) : 0u);
           }
       }
     }
@@ -355,7 +384,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int row_in_tile = wl * 32 + lane;
     const int q_start = q_start0 + q * QT;
     const uint32_t stage_smem = base + SMEM_Q_OFF + q * TILE_BYTES;  // reused for the O tile
-    if (q < nq) {
+    if (wl < warps_of(q)) {
       const uint32_t lane_off = uint32_t(wl * 32) << 16;
       const uint32_t t_s = pin_u32(tmem_base + lane_off + TM_S + q * 128);
       const uint32_t t_p = t_s + (TM_P - TM_S) - q * 64;
@@ -422,8 +451,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         m = fmaxf(mx0, mx1);
       }
 
-      for (int j = 0; j < n_kv; ++j) {
-        const bool has_next = j + 1 < n_kv;
+      // ---- tiles 0 .. n_kv-2: each one prefetches the scores of its successor
+      for (int j = 0; j + 1 < n_kv; ++j) {
         const uint32_t par = uint32_t(j) & 1u, par_next = par ^ 1u;
         const unsigned long long negm2 = pack2(-m, -m);
         float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -514,7 +543,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mbar_arrive(p_ready(q, 1));
           mbar_arrive(s_free(q, 1));
         }
-        if (has_next) {
+        {
           if (tile_needs_mask(j + 1)) mask_tile(j + 1, mx0, mx1);
           const float mnext = fmaxf(m, fmaxf(mx0, mx1));
           const bool need = mnext > m + RESCALE_THRESHOLD;
@@ -540,6 +569,50 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             tmem_st_wait();
             tc_fence_before();
+          }
+        }
+      }
+
+      // ---- last tile: only its valid 16-key chunks, nothing to prefetch (a T = 1801 sequence has 9 keys
+      // in its 15th tile)
+      if (n_kv > 0) {
+        const int j = n_kv - 1;
+        const uint32_t par_next = (uint32_t(j) & 1u) ^ 1u;
+        const unsigned long long negm2 = pack2(-m, -m);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          if (c == 0 || c == NCH / 2) {  // P half may be overwritten once P V_{j-1} of that half is done
+            if (j > 0) mbar_wait(pv_done(q, c > 0), par_next);
+            tc_fence_after();
+          }
+          if (c < nch_last) {
+            uint32_t pk[CH / 2];
+#pragma unroll
+            for (int i = 0; i < CH / 2; ++i) {
+              const int c0 = CH * c + 2 * i;
+              const unsigned long long x2 =
+                  add2(pack2(__uint_as_float(xs[c0]), __uint_as_float(xs[c0 + 1])), negm2);
+              float p0, p1;
+              if ((i & 3) < EMU_PAIRS) {
+                exp2_emulated2(x2, p0, p1);
+              } else {
+                float x0, x1;
+                unpack2(x2, x0, x1);
+                p0 = ex2_approx(x0);
+                p1 = ex2_approx(x1);
+              }
+              if (i & 1) lsumB = add2(lsumB, pack2(p0, p1));
+              else lsumA = add2(lsumA, pack2(p0, p1));
+              pk[i] = pack_bf16x2(p0, p1);
+            }
+            if (CH == 16) tmem_st8(t_p + (CH / 2) * c, pk);
+            else tmem_st16(t_p + (CH / 2) * c, pk);
+          }
+          if (c == NCH / 2 - 1 || c == NCH - 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane0) mbar_arrive(p_ready(q, c >= NCH / 2));
           }
         }
       }
@@ -579,7 +652,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       fence_proxy_async_smem();
-      named_bar_sync(1 + q, 128);
+      named_bar_sync(1 + q, 32 * warps_of(q));
       if (wl == 0 && lane == 0) {
         tma_store_3d(&tmO, stage_smem, head * HD, q_start, b);
         tma_store_commit();
@@ -596,6 +669,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+
+
 template <int MASK_MODE, int EMU_PAIRS, int NQ>
 int launch_variant(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                    const CUtensorMap& tmO, const FmhaParams& p, cudaStream_t stream) {
@@ -607,7 +682,7 @@ int launch_variant(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtenso
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));
     configured = true;
   }
-  dim3 grid((p.Tq + NQ * QT - 1) / (NQ * QT), p.H, p.B);
+  dim3 grid(unsigned((p.Tq + NQ * QT - 1) / (NQ * QT)) * unsigned(p.H) * unsigned(p.B));
   RP_CUDA_CHECK(launch_pdl(fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ>, grid, dim3(C::NUM_THREADS), C::SMEM_TOTAL, stream,
                            tmQ, tmK, tmV, tmO, p));
   count_launch();
@@ -621,6 +696,7 @@ int launch_variant(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtenso
 extern "C" int rp_debug_fmha_trace(unsigned long long* host_out) {
   return int(cudaMemcpyFromSymbol(host_out, g_fmha_trace, sizeof(unsigned long long) * 8 * 512));
 }
+
 #endif
 
 int launch_fmha(const FmhaArgs& a, cudaStream_t stream) {
@@ -643,17 +719,11 @@ int launch_fmha(const FmhaArgs& a, cudaStream_t stream) {
   if ((rc = make_tmap_3d(&tmO, bf, a.o, cols, a.Tq, a.B, a.ldo * 2, a.bso * 2, HD, QT))) return rc;
 
   FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride};
-  static const int nq_cfg = getenv("RP_FMHA_NQ") ? atoi(getenv("RP_FMHA_NQ")) : 1;
-  static const int emu = getenv("RP_FMHA_EMU") ? atoi(getenv("RP_FMHA_EMU")) : 1;
+  // One build of the kernel ships (NQ = 1: two independent CTAs per SM; one exp2 pair in four on the FMA pipe).
+  // The alternatives that were built, verified and measured — NQ = 2, 0 or 2 emulated pairs, a 64-key-tile
+  // three-CTA variant and a two-warpgroup ping-pong kernel — live under tools/experiments/ with their numbers.
   if (a.mask_mode == 1) return launch_variant<1, 1, 1>(tmQ, tmK, tmV, tmO, p, stream);
-  const int key = (emu < 0 || emu > 2 ? 1 : emu) * 10 + (nq_cfg == 2 ? 2 : 1);
-  switch (key) {
-    case 1:  return launch_variant<0, 0, 1>(tmQ, tmK, tmV, tmO, p, stream);
-    case 2:  return launch_variant<0, 0, 2>(tmQ, tmK, tmV, tmO, p, stream);
-    case 12: return launch_variant<0, 1, 2>(tmQ, tmK, tmV, tmO, p, stream);
-    case 21: return launch_variant<0, 2, 1>(tmQ, tmK, tmV, tmO, p, stream);
-    default: return launch_variant<0, 1, 1>(tmQ, tmK, tmV, tmO, p, stream);
-  }
+  return launch_variant<0, 1, 1>(tmQ, tmK, tmV, tmO, p, stream);
 }
 
 }  // namespace rp

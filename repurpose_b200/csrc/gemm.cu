@@ -254,7 +254,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN);
       const int row0 = tile_row0(m_blk);
       const int row = row0 + lane;
-      float st_sum = 0.f, st_sq = 0.f;  // LNF: row statistics of the updated h over this tile's 256 columns
+      // LNF: row statistics of the updated h over this tile's 256 columns, accumulated about a shift (the row's
+      // first value) so that a large common offset of the residual stream does not cancel in E[x^2] - mean^2
+      float st_sum = 0.f, st_sq = 0.f, st_shift = 0.f;
       mbar_wait(tfull_bar(buf), use_parity);
       tc_fence_after();
 
@@ -335,11 +337,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if constexpr (LNF) {
               // keep the updated row in TMEM for the normalisation pass and accumulate its statistics
               tmem_st32(t_row + uint32_t(c * CPC + half * 32), v);
+              if (c == 0 && half == 0) st_shift = __uint_as_float(v[0]);
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const float x = __uint_as_float(v[i]);
-                st_sum += x;
-                st_sq = fmaf(x, x, st_sq);
+                const float d = __uint_as_float(v[i]) - st_shift;
+                st_sum += d;
+                st_sq = fmaf(d, d, st_sq);
               }
             }
           } else {
@@ -370,17 +373,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_st_wait();
         const int my_row = q * 32 + lane;
         const uint32_t partner = uint32_t(cluster_rank ^ 2);
-        st_cluster_f32x2(mapa_shared(base + C::SMEM_STATS_OFF + uint32_t(buf * 128 + my_row) * 8u, partner), st_sum, st_sq);
+        // this half's mean and centred sum of squares; the halves are merged with the pairwise update of
+        // Chan et al. (symmetric in the two halves, so both CTAs compute bit-identical statistics)
+        const float my_mean = st_shift + st_sum * (1.0f / float(BN));
+        const float my_m2 = fmaxf(st_sq - st_sum * st_sum * (1.0f / float(BN)), 0.f);
+        st_cluster_f32x2(mapa_shared(base + C::SMEM_STATS_OFF + uint32_t(buf * 128 + my_row) * 8u, partner), my_mean, my_m2);
         mbar_arrive_cluster(mapa_shared(stats_bar(buf), partner));
-        while (!mbar_try_wait_cluster(stats_bar(buf), use_parity)) {}
+        for (uint32_t polls = 0; !mbar_try_wait_cluster(stats_bar(buf), use_parity);)
+          if (++polls > (1u << 26)) __trap();  // a protocol bug must trap, not hang the GPU (ptx.cuh bounded-wait policy)
         float2 other;
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
                      : "=f"(other.x), "=f"(other.y)
                      : "r"(base + C::SMEM_STATS_OFF + uint32_t(buf * 128 + my_row) * 8u)
                      : "memory");
         const float inv_w = 1.0f / float(2 * BN);
-        const float mean = (st_sum + other.x) * inv_w;
-        const float rstd = rsqrtf(fmaxf((st_sq + other.y) * inv_w - mean * mean, 0.f) + g.ln.eps);
+        const float mean = 0.5f * (my_mean + other.x);
+        const float dm = my_mean - other.x;
+        const float rstd = rsqrtf((my_m2 + other.y + dm * dm * (0.5f * float(BN))) * inv_w + g.ln.eps);
         const float nmr = -mean * rstd;
 #pragma unroll 1
         for (int c2 = 0; c2 < BN / 64; ++c2, ++gc) {
@@ -565,9 +574,8 @@ int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int6
             reinterpret_cast<uintptr_t>(D) | reinterpret_cast<uintptr_t>(bias) |
             reinterpret_cast<uintptr_t>(resid)) % 16 == 0,
            "gemm: pointers must be 16-byte aligned");
-  // RP_GEMM_CG=1 selects the single-CTA kernel (A/B experiments); the CTA-pair kernel is the default
-  static const int cg = getenv("RP_GEMM_CG") ? atoi(getenv("RP_GEMM_CG")) : 2;
-  if ((cg == 1 || M <= BM) && epilogue != EPI_BIAS_RESID_LN)
+  // CTA pairs (cta_group::2) need two 128-row blocks; a problem of at most 128 rows runs the single-CTA kernel
+  if (M <= BM && epilogue != EPI_BIAS_RESID_LN)
     return launch_cg<1>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, ln, stream);
   return launch_cg<2>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, ln, stream);
 }

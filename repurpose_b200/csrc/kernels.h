@@ -60,6 +60,9 @@ int launch_concat_cast(const float* vis, const float* aud, const float* txt, int
 int launch_ragged_concat_cast(const void* vis, const void* aud, const void* txt, bool in_bf16, int Cv, int Ca,
                               int Ct, const int32_t* row_off, const int32_t* txt_off, const int32_t* txt_lens,
                               const int32_t* lens, int B, int T, void* out_bf16, cudaStream_t stream);
+// lens[b] = number of non-zero bytes of mask[b, 0..T); *not_aligned = 1 if some mask is not of the form
+// t < lens[b] (both device pointers)
+int launch_mask_lens(const uint8_t* mask, int B, int T, int32_t* lens, int32_t* not_aligned, cudaStream_t stream);
 // generic fp32 -> bf16 cast of a contiguous buffer (n % 8 == 0)
 int launch_cast_bf16(const float* in, void* out_bf16, int64_t n, cudaStream_t stream);
 

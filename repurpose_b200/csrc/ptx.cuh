@@ -185,6 +185,17 @@ __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {  // whole warp
                : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
+// two allocations by one warp (e.g. 128 + 32 columns when 160 are needed: sizes are powers of two)
+template <int COLS_A, int COLS_B>
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst_a, uint32_t smem_dst_b) {  // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst_a),
+               "n"(COLS_A)
+               : "memory");
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst_b),
+               "n"(COLS_B)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
 template <int COLS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // whole warp (the allocating one)
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS)

@@ -291,6 +291,49 @@ int launch_ragged_concat_cast(const void* vis, const void* aud, const void* txt,
   return RP_OK;
 }
 
+// valid-step count of every video from its key-padding mask, plus a flag that says whether all masks are
+// left-aligned (mask[b, t] == t < lens[b]): the attention and decode kernels take lengths, the reference
+// takes the mask itself (models/MMCTransformer.py:132-138), so anything else must be refused.
+__global__ void mask_lens_kernel(const uint8_t* __restrict__ mask, int T, int32_t* __restrict__ lens,
+                                 int32_t* __restrict__ not_aligned) {
+  const uint8_t* row = mask + int64_t(blockIdx.x) * T;
+  int cnt = 0, last = -1;
+  for (int t = threadIdx.x; t < T; t += blockDim.x)
+    if (row[t] != 0) {
+      ++cnt;
+      last = t;  // ascending within a thread
+    }
+  __shared__ int s_cnt[32], s_last[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_cnt[threadIdx.x >> 5] = cnt;
+    s_last[threadIdx.x >> 5] = last;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0, l = -1;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) {
+      c += s_cnt[w];
+      l = max(l, s_last[w]);
+    }
+    lens[blockIdx.x] = c;
+    if (l + 1 != c) atomicOr(not_aligned, 1);  // a hole or a leading gap: the last valid step is not count - 1
+  }
+}
+
+int launch_mask_lens(const uint8_t* mask, int B, int T, int32_t* lens, int32_t* not_aligned, cudaStream_t stream) {
+  RP_CHECK(B > 0 && T > 0, "mask_lens: empty");
+  RP_CUDA_CHECK(cudaMemsetAsync(not_aligned, 0, sizeof(int32_t), stream));
+  mask_lens_kernel<<<B, 256, 0, stream>>>(mask, T, lens, not_aligned);
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
 int launch_cast_bf16(const float* in, void* out_bf16, int64_t n, cudaStream_t stream) {
   RP_CHECK(n > 0 && n % 8 == 0, "cast_bf16: n must be a positive multiple of 8");
   cast_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(

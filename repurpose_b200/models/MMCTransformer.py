@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -27,6 +28,7 @@ from .._lib import RpDecodeCfg, RpModelCfg, check, cur_stream, ptr
 from .softnms import soft_nms_intervals_cpu  # noqa: F401  (re-exported like the reference module)
 
 HEAD_HIDDEN = 256
+_STRICT_MASKS = os.environ.get("RP_STRICT_MASKS", "0") == "1"
 
 
 class PositionalEncoding(nn.Module):
@@ -45,6 +47,13 @@ class PositionalEncoding(nn.Module):
         pe[:, 0::2] = torch.sin(position * div_term)
         pe[:, 1::2] = torch.cos(position * div_term)
         return pe
+
+
+def _invalidate_hook(module, _incompatible_keys):
+    module._invalidate()
+
+
+_NATIVE_STATE = dict(_handle=None, _weights_sig=None, _workspace=None, _last_masks=None, _last_lens=None)
 
 
 class MMCTransformer(nn.Module):
@@ -79,7 +88,9 @@ class MMCTransformer(nn.Module):
         self._handle = None
         self._weights_sig = None
         self._workspace = None
-        self.register_load_state_dict_post_hook(lambda module, _keys: module._invalidate())
+        self._mask_checks = []
+        self._last_masks = self._last_lens = None
+        self.register_load_state_dict_post_hook(_invalidate_hook)
 
     def _init_weights(self):
         # models/MMCTransformer.py:98-107: Xavier for every nn.Linear, zero bias, LN gamma=1 beta=0
@@ -104,6 +115,14 @@ class MMCTransformer(nn.Module):
         out = super()._apply(fn, *args, **kwargs)
         self._weights_sig = None
         return out
+
+    def __getstate__(self):
+        # copy.deepcopy / pickle / torch.save(model): the native handle (a ctypes pointer), the workspace and
+        # pending events stay behind; the copy repacks its weights lazily on its first forward
+        st = self.__dict__.copy()
+        st.update(_NATIVE_STATE)
+        st["_mask_checks"] = []
+        return st
 
     def __del__(self):
         try:
@@ -162,6 +181,55 @@ class MMCTransformer(nn.Module):
     def _as_f32(t, dev):
         return t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
 
+    # ------------------------------------------------------------------------ masks -> lengths
+    _MASK_MSG = ("masks must be left-aligned (masks[b, 0, t] == t < valid_len[b], as dataset/RepurposeClip.py:"
+                 "528-531 builds them): the attention and decode kernels take lengths; a mask with holes or "
+                 "leading padding would silently attend to / decode the wrong steps")
+
+    def _lens_from_masks(self, masks, B, T):
+        """Valid steps per video (int32 [B] on the device) from a [B,1,T] / [B,T] mask, and the check that
+        the reference's key-padding semantics (models/MMCTransformer.py:132-138 hands the MASK to the
+        encoder) are expressible as lengths.  Host masks are checked on the spot; device masks by one
+        kernel whose flag is read back asynchronously and raises at the next host synchronisation point of
+        this module (or at once with RP_STRICT_MASKS=1) — a forward never waits for the GPU."""
+        dev = self.device
+        m = masks.reshape(B, -1)
+        if m.shape[1] != T:
+            raise ValueError(f"masks cover {m.shape[1]} steps, features {T}")
+        if not m.is_cuda:
+            mb = m.ne(0)
+            lens = mb.sum(dim=1, dtype=torch.int32)
+            if not torch.equal(mb, torch.arange(T)[None, :] < lens[:, None]):
+                raise _lib.RepurposeError(self._MASK_MSG)
+            return lens.to(dev, non_blocking=True)
+        m = m.to(dev)
+        m8 = (m if m.dtype in (torch.bool, torch.uint8) else m.ne(0)).contiguous().view(torch.uint8)
+        lens = torch.empty(B, dtype=torch.int32, device=dev)
+        flag = torch.empty(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.load().rp_mask_lens(ptr(m8), B, T, ptr(lens), ptr(flag), cur_stream()), "rp_mask_lens")
+            host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+            host.copy_(flag, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._mask_checks.append((ev, host))
+        self._poll_mask_checks(wait=_STRICT_MASKS)
+        return lens
+
+    def _poll_mask_checks(self, wait=False):
+        """Raise if a finished alignment check found a bad mask (wait=True: finish them all first)."""
+        pending = []
+        for ev, host in self._mask_checks:
+            if wait:
+                ev.synchronize()
+            if ev.query():
+                if int(host[0]) != 0:
+                    self._mask_checks = []
+                    raise _lib.RepurposeError(self._MASK_MSG)
+            else:
+                pending.append((ev, host))
+        self._mask_checks = pending
+
     # -------------------------------------------------------------------------------- forward
     def forward(self, batch):
         """batch: dict with visual_feats [B,T,Cv], audio_feats [B,T,Ca], text_feats [B,T,Ct] fp32,
@@ -171,6 +239,7 @@ class MMCTransformer(nn.Module):
         A batch from `repurpose_b200.features.collate_ragged` (unpadded rows + offsets) is accepted
         too: the padding then happens on the device."""
         self._ensure_ready()
+        self._poll_mask_checks()
         dev = self.device
         if batch.get("parts") is not None:  # zero-copy ragged batch used outside the pipeline
             batch = dict(batch)
@@ -195,7 +264,7 @@ class MMCTransformer(nn.Module):
         else:
             masks = batch["masks"]
             B, T = vis.shape[0], vis.shape[1]
-            lens = masks.to(dev, non_blocking=True).reshape(B, -1).ne(0).sum(dim=1, dtype=torch.int32).contiguous()
+            lens = self._lens_from_masks(masks, B, T)
         logits = torch.empty(B, T, 1, dtype=torch.float32, device=dev)
         offsets = torch.empty(B, T, 2, dtype=torch.float32, device=dev)
         feats = torch.empty(B, T, self._cfg["d_model"], dtype=torch.float32, device=dev)
@@ -210,7 +279,7 @@ class MMCTransformer(nn.Module):
                 check(lib.rp_forward(self._handle, ptr(vis), ptr(aud), ptr(txt), ptr(lens), B, T,
                                      ptr(logits), ptr(offsets), ptr(feats), ptr(ws), ws.numel(),
                                      cur_stream()), "rp_forward")
-        self._last_lens = lens
+        self._last_masks, self._last_lens = masks, lens
         return masks, logits, offsets, batch.get("labels"), batch.get("segments"), feats
 
     def profile_begin(self):
@@ -258,7 +327,7 @@ class MMCTransformer(nn.Module):
         B, T = logits.shape
         kcap = max(1, max(max_seg))
         if kcap > 64:
-            raise _lib.RepurposeError(f"max_seg_num={kcap} exceeds the 64 slots of the decode kernel")
+            return self._run_decode_wide(logits, offsets, lens, max_seg, settings, want_candidates)
         max_seg_t = torch.tensor(max_seg, dtype=torch.int32).to(dev, non_blocking=True)
         segs = torch.empty(B, kcap, 2, dtype=torch.float32, device=dev)
         scores = torch.empty(B, kcap, dtype=torch.float32, device=dev)
@@ -281,6 +350,29 @@ class MMCTransformer(nn.Module):
         return dict(segments=segs, scores=scores, dscores=dscores, labels=labels, counts=counts,
                     ncand=ncand, cand_segments=cseg, cand_scores=cscore, cand_labels=clabel)
 
+    def _run_decode_wide(self, logits, offsets, lens, max_seg, settings, want_candidates):
+        """max_seg_num above the 64 slots the fused decode kernel keeps in shared memory (max_seg_per_min >= 1
+        on an hour-long video; the reference has no such limit): the fused kernel only builds the candidate
+        lists, the stand-alone Soft-NMS kernel (Kcap up to the candidate count) selects, and the kept rows
+        are gathered on the device.  Same outputs as `_run_decode`."""
+        from .softnms import soft_nms_batched
+        dev = logits.device
+        r = self._run_decode(logits, offsets, lens, [1] * len(max_seg), settings, want_candidates=True)
+        ccap = r["cand_scores"].shape[1]
+        kcap = max(1, min(max(max_seg), ccap))
+        max_seg_t = torch.tensor(max_seg, dtype=torch.int32).to(dev, non_blocking=True)
+        keep, dscores, counts = soft_nms_batched(r["cand_scores"], r["cand_segments"], r["ncand"], max_seg_t,
+                                                 float(settings.get("nms_sigma", 0.5)),
+                                                 float(settings.get("min_score", 0.001)), kcap=kcap)
+        idx = keep.clamp_min(0).to(torch.int64)
+        out = dict(segments=torch.gather(r["cand_segments"], 1, idx[..., None].expand(-1, -1, 2)),
+                   scores=torch.gather(r["cand_scores"], 1, idx), dscores=dscores,
+                   labels=torch.gather(r["cand_labels"], 1, idx), counts=counts, ncand=r["ncand"],
+                   cand_segments=None, cand_scores=None, cand_labels=None)
+        if want_candidates:
+            out.update(cand_segments=r["cand_segments"], cand_scores=r["cand_scores"], cand_labels=r["cand_labels"])
+        return out
+
     @torch.no_grad()
     def inference_single_video(self, masks, out_cls_logits, out_offsets, inference_settings):
         """Pre-NMS candidates of one video (reference :181-229): dict(segments [N,2], scores [N]
@@ -289,9 +381,10 @@ class MMCTransformer(nn.Module):
         logits = out_cls_logits.reshape(1, -1).to(torch.float32).contiguous()
         T = logits.shape[1]
         offsets = out_offsets.reshape(1, T, 2).to(torch.float32).contiguous()
-        lens = masks.to(dev).reshape(1, -1).ne(0).sum(dim=1, dtype=torch.int32).contiguous()
+        lens = self._lens_from_masks(masks, 1, T)
         r = self._run_decode(logits, offsets, lens, [1], inference_settings, want_candidates=True)
         n = int(r["ncand"][0].item())
+        self._poll_mask_checks()
         return {"segments": r["cand_segments"][0, :n], "scores": r["cand_scores"][0, :n],
                 "labels": r["cand_labels"][0, :n].to(torch.int64)}
 
@@ -310,7 +403,9 @@ class MMCTransformer(nn.Module):
         max_seg = [int(np.ceil((int(v) // 60) * inference_settings["max_seg_per_min"]))
                    for v in batch["duration"]]
         B, T = logits.shape[0], logits.shape[1]
-        lens = masks.to(dev).reshape(B, -1).ne(0).sum(dim=1, dtype=torch.int32).contiguous()
+        # the forward that produced `output` already derived (and checked) the lengths of this mask
+        lens = self._last_lens if masks is self._last_masks and self._last_lens is not None \
+            and self._last_lens.shape[0] == B else self._lens_from_masks(masks, B, T)
         return self._run_decode(logits.reshape(B, T).contiguous(), offsets.contiguous(), lens, max_seg,
                                 inference_settings)
 
@@ -335,8 +430,10 @@ class MMCTransformer(nn.Module):
             for o, vidx, vlen in zip(unpack_slots(slots), vid_idxs, vid_lens):
                 o["video_id"], o["duration"] = vidx, vlen
                 results.append(o)
+            self._poll_mask_checks()
             return results
         counts = r["counts"].tolist()  # the single device->host sync of the whole batch
+        self._poll_mask_checks()
         labels64 = r["labels"].to(torch.int64)
         for i, (vidx, vlen) in enumerate(zip(vid_idxs, vid_lens)):
             k = counts[i]

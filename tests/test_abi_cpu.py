@@ -67,3 +67,27 @@ def test_invalid_arguments_return_status_not_abort():
     assert b"null" in lib.rp_last_error()
     assert lib.rp_workspace_bytes(None, 1, 1) == -1
     assert lib.rp_create(None, None) != 0
+
+
+def test_module_is_copyable_and_picklable():
+    """copy.deepcopy / torch.save(model) as EMA and checkpoint-whole-module code does: the native
+    handle (a ctypes pointer) must stay behind and the copy repacks lazily."""
+    import copy
+    import ctypes
+    import io
+    import torch
+    from repurpose_b200 import synth
+    from repurpose_b200.models.MMCTransformer import MMCTransformer
+    m = MMCTransformer(**dict(synth.MODEL_CFG, self_num_layers=1))
+    m._handle = ctypes.c_void_p(1234)          # as after a first forward
+    try:
+        m2 = copy.deepcopy(m)
+        buf = io.BytesIO()
+        torch.save(m, buf)
+        buf.seek(0)
+        m3 = torch.load(buf, weights_only=False)
+    finally:
+        m._handle = None                        # nothing for __del__ to destroy
+    for c in (m2, m3):
+        assert c._handle is None and c._weights_sig is None and c._workspace is None
+        assert all(torch.equal(a, b) for a, b in zip(c.state_dict().values(), m.state_dict().values()))

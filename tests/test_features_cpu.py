@@ -80,3 +80,24 @@ def test_infer_read_test_set_follows_reference_rules(tmp_path):
     assert es[0]["n_labels"] == 100 and es[1]["n_labels"] == 51          # int(t1 - t0) + 1
     assert es[1]["time_range"] == [30, 80.2] and es[1]["gt_segments"] == [[2.0, 30.0], [31.0, 45.0]]
     assert es[0]["paths"][1].endswith("audio_path/a.npy")
+
+
+def test_loader_matches_reference_dataset_golden(tmp_path, golden_dir):
+    """read_test_set + load_video_features vs the reference's RepurposeClipTest + collate_fn_test
+    (dataset/RepurposeClip.py:578-606, 962-1038) on the dataset oracle/make_golden_aux.py pinned:
+    same availability filter, durations, feature rows and zero-padded text rows."""
+    import numpy as np
+    from oracle.make_golden_aux import checksum, write_loader_dataset
+    from repurpose_b200.features import load_video_features
+    from repurpose_b200.infer import read_test_set
+    g = np.load(golden_dir / "loader_cases.npz")
+    entries = read_test_set(write_loader_dataset(tmp_path))
+    assert [e["video_id"] for e in entries] == g["names"].tolist()
+    for e in entries:
+        v = load_video_features(*e["paths"], time_range=e["time_range"], n_labels=e["n_labels"])
+        name, n = e["video_id"], v["duration"]
+        assert n == int(g[f"{name}_duration"]) and v["text_feats"].shape[0] == int(g[f"{name}_text_rows"])
+        txt = np.zeros((n, v["text_feats"].shape[1]), np.float32)
+        txt[:v["text_feats"].shape[0]] = v["text_feats"]
+        got = np.array([checksum(v["visual_feats"]), checksum(v["audio_feats"]), checksum(txt)])
+        assert np.allclose(got, g[f"{name}_checksums"], rtol=0, atol=1e-6), name

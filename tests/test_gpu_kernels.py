@@ -205,7 +205,12 @@ def _attn_ref(q, k, v, kv_lens=None, mask=None):
 
 @pytest.mark.parametrize("B,H,T,lens", [(1, 1, 128, None), (1, 1, 256, None), (2, 2, 384, None),
                                         (2, 8, 200, [200, 77]), (3, 8, 700, [700, 433, 129]),
-                                        (2, 8, 1801, [1801, 1200]), (1, 8, 130, [1])])
+                                        (2, 8, 1801, [1801, 1200]), (1, 8, 130, [1]),
+                                        # query blocks of 256 rows: partial second tile (1, 2, 3 warps), a
+                                        # one-row block; key tails of exactly 16 / 64 / 65 / 128 keys
+                                        (1, 2, 300, None), (2, 2, 416, [416, 300]), (1, 1, 257, None),
+                                        (1, 2, 512, [144]), (2, 2, 640, [64, 65]), (2, 1, 352, [128, 16]),
+                                        (1, 1, 16, None)])
 def test_fmha_key_padding(B, H, T, lens):
     gen = torch.Generator(device=DEV).manual_seed(T + B)
     qkv = torch.randn(B, T, 3 * H * 64, device=DEV, generator=gen)
@@ -287,3 +292,27 @@ def test_gemm_residual_layernorm_fused(M, K):
     h2 = h0.clone()
     check(lib.rp_gemm_bf16(3, ptr(A), K, ptr(W), K, ptr(h2), 512, ptr(bias), ptr(h2), 512, M, 512, K, cur_stream()), "gemm")
     assert torch.equal(h, h2)
+
+
+def test_gemm_fused_layernorm_survives_a_large_row_offset():
+    """residual rows with a large common offset (mean^2 >> var, as in trained checkpoints with
+    massive activations) must not lose the variance to cancellation: the fused epilogue accumulates shifted
+    statistics and merges the two 256-column halves with the pairwise (Chan) update."""
+    lib = _lib.load()
+    torch.manual_seed(7)
+    M, K = 1000, 512
+    A = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
+    W = (torch.randn(512, K, device=DEV) / K ** 0.5).bfloat16()
+    bias = torch.randn(512, device=DEV)
+    gamma, beta = torch.rand(512, device=DEV) + 0.5, torch.randn(512, device=DEV)
+    for offset in (100.0, -3000.0):
+        h0 = torch.randn(M, 512, device=DEV) + offset
+        h0[:, 256:] += 0.5                                   # the two halves of a row get different means
+        h = h0.clone()
+        u = torch.empty(M, 512, device=DEV, dtype=torch.bfloat16)
+        check(lib.rp_gemm_resid_ln(ptr(A), K, ptr(W), K, ptr(h), 512, ptr(bias), ptr(gamma), ptr(beta), 1e-5, ptr(u),
+                                   512, M, K, cur_stream()), "rp_gemm_resid_ln")
+        ref_h = (h0.double() + A.double() @ W.double().t() + bias.double())
+        ref_u = torch.nn.functional.layer_norm(ref_h, (512,), gamma.double(), beta.double(), 1e-5).float()
+        err = (u.float() - ref_u).abs().max().item()
+        assert err < 4e-2, (offset, err)                     # bf16 output of O(1..4) values (fp32 h carries ~1e-4 of noise at |h| ~ 3000)

@@ -27,6 +27,23 @@ def _rel_err(got, ref):
     return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-6)).item()
 
 
+FLOOR_FRAC = 0.25
+
+
+def _elementwise_gate(name, got, ref, tol=REL_TOL):
+    """every element within tol * max(|ref|, floor), with the floor stated: a quarter of
+    the tensor's largest magnitude (the error of a bf16 pipeline is absolute — an output near zero is a sum
+    of cancelling O(1) terms — so below the floor the bound is tol * floor = 5e-3 of the tensor scale).
+    Prints p50 / p99 / max of the per-element ratio |got - ref| / max(|ref|, floor)."""
+    got, ref = torch.as_tensor(got).float().cpu().reshape(-1), torch.as_tensor(ref).float().cpu().reshape(-1)
+    floor = FLOOR_FRAC * ref.abs().max().clamp_min(1e-6)
+    ratio = (got - ref).abs() / torch.maximum(ref.abs(), floor)
+    q = torch.quantile(ratio[:: max(1, ratio.numel() // 1_000_000)], torch.tensor([0.5, 0.99]))
+    print(f"{name}: |d|/max(|ref|, {floor.item():.3g}) p50 {q[0].item():.2e} p99 {q[1].item():.2e} "
+          f"max {ratio.max().item():.2e} (gate {tol:g})")
+    assert ratio.max().item() <= tol, f"{name}: element off by {ratio.max().item():.4f} of max(|ref|, floor)"
+
+
 # ------------------------------------------------------------------------------------ Soft-NMS
 def test_softnms_golden_cases(golden_dir):
     g = np.load(golden_dir / "softnms_cases.npz")
@@ -131,6 +148,55 @@ def test_decode_edge_cases(tiny_model):
     assert r["cand_labels"][0, :100].tolist() == list(range(T - 1, T - 101, -1))
 
 
+def test_decode_more_than_64_segments_per_video(tiny_model):
+    """max_seg_num above the fused kernel's 64 slots (max_seg_per_min >= 1 on an hour-long video): the
+    decode falls back to candidates + stand-alone Soft-NMS and must still equal the oracle's loop
+    (models/MMCTransformer.py:255-269 has no such limit)."""
+    T, vlen, max_seg = 4000, 3900, 100
+    g = torch.Generator().manual_seed(17)
+    logits = torch.randn(1, T, generator=g) * 2.0
+    offsets = torch.rand(1, T, 2, generator=g) * 40.0 + 5.0
+    cfg = dict(synth.TEST_CFG, pre_nms_topk=2000)
+    r = _decode(tiny_model, logits, offsets, [vlen], [max_seg], cfg)
+    o = mmct.decode_single_video((torch.arange(T) < vlen)[None], logits[0], offsets[0], cfg)
+    keep = soft_nms_intervals_oracle(o["scores"].numpy().copy(), o["segments"].numpy().copy(),
+                                     cfg["nms_sigma"], cfg["min_score"], max_seg)
+    k = int(r["counts"][0])
+    assert 64 < k == len(keep) <= max_seg
+    assert np.array_equal(r["labels"][0, :k].cpu().numpy(), o["labels"].numpy()[keep])
+    np.testing.assert_allclose(r["segments"][0, :k].cpu().numpy(), o["segments"].numpy()[keep], atol=1e-4)
+    np.testing.assert_allclose(r["scores"][0, :k].cpu().numpy(), o["scores"].numpy()[keep], atol=1e-6)
+
+
+def test_masks_that_are_not_left_aligned_are_refused():
+    """The reference passes the mask itself to the encoder (models/MMCTransformer.py:132-138); this path
+    takes lengths, so a mask with a hole or leading padding must raise instead of silently decoding the
+    wrong steps."""
+    from repurpose_b200._lib import RepurposeError
+    torch.manual_seed(2)
+    m = MMCTransformer(512, 2048, 384, 512, 1, 3, 3, 8).to(DEV).eval()
+    batch = synth.make_batch([200, 150], seed=3)
+    dbatch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    m.inference_(dbatch, synth.TEST_CFG)                     # left-aligned: fine
+    for kind in ("hole", "right_aligned"):
+        bad = dict(dbatch)
+        mk = dbatch["masks"].clone()
+        if kind == "hole":
+            mk[1, 0, 40] = False
+        else:
+            mk[1, 0] = torch.arange(200, device=DEV) >= 50
+        bad["masks"] = mk
+        with pytest.raises(RepurposeError, match="left-aligned"):
+            m.inference_(bad, synth.TEST_CFG)                # device mask: raised at the host sync of this call
+        with pytest.raises(RepurposeError, match="left-aligned"):
+            m({**bad, "masks": mk.cpu()})                    # host mask: raised before anything is launched
+        with pytest.raises(RepurposeError, match="left-aligned"):
+            m(bad)                                           # forward only never waits for the GPU:
+            torch.cuda.synchronize()
+            m(dbatch)                                        # ... the next call reports it
+    m.inference_(dbatch, synth.TEST_CFG)                     # and the module keeps working afterwards
+
+
 # ------------------------------------------------------------------------------------ model
 @pytest.fixture(scope="module")
 def full_model():
@@ -153,6 +219,7 @@ def test_forward_matches_reference_golden(full_model, golden_dir):
         ref_v = torch.from_numpy(ref)[valid]
         err = _rel_err(got_v, ref_v)
         assert err < REL_TOL, f"{name}: relative error {err:.4f} vs reference golden (valid steps)"
+        _elementwise_gate(f"golden T=700 {name}", got_v, ref_v)
 
 
 def test_inference_matches_reference_golden(full_model, golden_dir):
@@ -166,6 +233,8 @@ def test_inference_matches_reference_golden(full_model, golden_dir):
         valid = batch["masks"][:, 0, :]
         assert _rel_err(logits.cpu()[valid], torch.from_numpy(g["regbias_logits"])[valid]) < REL_TOL
         assert _rel_err(offsets.cpu()[valid], torch.from_numpy(g["regbias_offsets"])[valid]) < REL_TOL
+        _elementwise_gate("golden regbias logits", logits.cpu()[valid], torch.from_numpy(g["regbias_logits"])[valid])
+        _elementwise_gate("golden regbias offsets", offsets.cpu()[valid], torch.from_numpy(g["regbias_offsets"])[valid])
         res = full_model.inference_(dbatch, synth.TEST_CFG)
         assert [r["video_id"] for r in res] == batch["video_id"]
         assert [r["duration"] for r in res] == batch["duration"]
@@ -259,6 +328,22 @@ def test_multi_head_attention_module(kind):
     assert _rel_err(got, ref) < REL_TOL, f"{kind}: {_rel_err(got, ref)}"
 
 
+def test_multi_head_attention_matches_reference_golden(golden_dir):
+    """MultiHeadAttention (a10) vs the outputs of the reference's models/transformer.py:37-81 module itself
+    (tests/golden/mha_cases.npz, oracle/make_golden_aux.py): self / padding / band / cross / fully masked row."""
+    from oracle.make_golden_aux import mha_cases, mha_weights
+    g = np.load(golden_dir / "mha_cases.npz")
+    mha = MultiHeadAttention(512, 8)
+    missing = mha.load_state_dict(mha_weights(), strict=False)
+    assert set(missing.missing_keys) <= {"scale"} and not missing.unexpected_keys
+    mha = mha.to(DEV)
+    for name, q, k, v, mask in mha_cases():
+        got = mha(q.to(DEV), k.to(DEV), v.to(DEV), None if mask is None else mask.to(DEV))
+        ref = torch.from_numpy(g[f"{name}_out_sub"])
+        assert _rel_err(got[..., ::8], ref) < REL_TOL, f"{name}: {_rel_err(got[..., ::8], ref)}"
+        _elementwise_gate(f"mha golden {name}", got[..., ::8], ref)
+
+
 # ------------------------------------------------------------------------------------ pipeline (f1)
 def test_inference_pipeline_matches_inference_():
     from repurpose_b200.scheduler import InferencePipeline, collate
@@ -323,20 +408,24 @@ def test_long_video_stress_config4():
 
 
 def test_atiou_parity_on_a_synthetic_set():
-    """AtIoU (inference.py:45-55) of our segments vs the fp32 oracle's on 48 ragged videos, 3-layer
-    model.  With random-init weights the per-step probabilities of neighbouring candidates differ by
-    ~1e-3, i.e. less than the bf16 noise on the logits, so a minority of videos legitimately select a
-    different (equally scored) candidate; the metric difference is zero-mean noise of size
-    ~(#differing videos / #videos) * (1 / segments per video).  The north-star bound of 0.1 point is
-    asserted exactly where it is well defined — identical fp32 candidates give the identical kept
-    list (tests above) — and statistically here."""
+    """AtIoU (inference.py:45-55) of our segments vs the fp32 oracle's on 96 ragged videos, 3-layer model:
+    the north-star bound |dAtIoU| <= 0.1 point is asserted on the measured difference, and the bootstrap
+    interval of that difference over videos is reported (gpurun_out/atiou_parity.json -> profiles/).
+    With random-init weights the probabilities of neighbouring candidates differ by ~1e-3, less than the
+    bf16 noise on the logits, so a minority of videos select a different, equally scored candidate: those
+    per-video differences are zero-mean and the interval shows it.  Identical fp32 candidates give the
+    identical kept list (tests above): that is where the bound is exact."""
+    import json
+    import os
+    from pathlib import Path
     torch.manual_seed(31)
     m = MMCTransformer(512, 2048, 384, 512, 3, 3, 3, 8)
     sd = synth.bias_reg_head({k: v.clone() for k, v in m.state_dict().items()})
     m.load_state_dict(sd)
     m = m.to(DEV).eval()
-    n_videos = 48
+    n_videos = 96
     lens = synth.sample_lengths(n_videos, seed=5, t_max=900)
+    thr = (0.5, 0.6, 0.7, 0.8, 0.9)
     gts, ours, refs, same = [], [], [], 0
     for b0 in range(0, n_videos, 8):
         batch = synth.make_batch(lens[b0:b0 + 8], seed=40 + b0)
@@ -351,11 +440,20 @@ def test_atiou_parity_on_a_synthetic_set():
             same += int(g["labels"].tolist() == w["labels"].tolist())
     a_ours, _ = mmct.atiou(gts, ours)
     a_ref, _ = mmct.atiou(gts, refs)
-    differing = n_videos - same
-    tol_points = 0.1 + 100.0 * differing / n_videos * 0.25
-    print(f"AtIoU ours {100 * a_ours:.3f} oracle {100 * a_ref:.3f}; identical kept lists {same}/{n_videos}")
-    assert abs(a_ours - a_ref) * 100 <= tol_points, \
-        f"AtIoU {100 * a_ours:.3f} vs oracle {100 * a_ref:.3f} (tolerance {tol_points:.2f}, {differing} differing videos)"
+    # per-video contribution: mean over thresholds of that video's precision; AtIoU is their mean
+    per = lambda preds: np.array([np.mean([mmct.calculate_tiou(g, p, thr)[t] for t in thr]) for g, p in zip(gts, preds)])
+    d = (per(ours) - per(refs)) * 100.0
+    rng = np.random.default_rng(0)
+    boot = np.sort([d[rng.integers(0, n_videos, n_videos)].mean() for _ in range(4000)])
+    lo, hi = float(boot[100]), float(boot[3899])   # 95 %
+    delta = float((a_ours - a_ref) * 100.0)
+    out = {"videos": n_videos, "atiou_ours_pts": 100 * a_ours, "atiou_oracle_pts": 100 * a_ref, "delta_pts": delta,
+           "bootstrap95_pts": [lo, hi], "identical_kept_lists": same, "videos_with_nonzero_delta": int((d != 0).sum())}
+    print("AtIoU parity:", json.dumps(out))
+    o = Path(os.environ.get("GRAFT_REPO_ROOT", Path(__file__).resolve().parent.parent)) / "gpurun_out"
+    o.mkdir(exist_ok=True)
+    (o / "atiou_parity.json").write_text(json.dumps(out))
+    assert abs(delta) <= 0.1, f"AtIoU {100 * a_ours:.3f} vs oracle {100 * a_ref:.3f}: {delta:+.3f} points (95 % [{lo:+.3f}, {hi:+.3f}])"
     assert same >= n_videos * 0.6, f"only {same}/{n_videos} videos keep the identical segment list"
 
 
@@ -384,6 +482,29 @@ def test_atiou_on_device_is_bit_exact_vs_python_metric():
     assert avg == ref_avg, (avg, ref_avg)
     assert all(by_thr[t] == ref_by[t] for t in ref_by), (by_thr, ref_by)
     assert per_video.shape == (n, 5)
+
+
+def test_atiou_on_device_matches_reference_golden(golden_dir):
+    """rp_atiou (f4) vs the values the reference's utils/metrics.py:82-111 calculate_tiou and the averaging
+    of inference.py:45-55 produced (tests/golden/tiou_cases.npz): per-video precision, per-threshold mean and
+    AtIoU identical to the last bit (predictions are fp32-representable, as the model's segments are)."""
+    from oracle.make_golden_aux import THRESHOLDS, tiou_cases
+    from repurpose_b200.metrics import atiou
+    from repurpose_b200.scheduler import pack_slots
+    g = np.load(golden_dir / "tiou_cases.npz")
+    cases = tiou_cases(int(g["seed"]), int(g["n_cases"]))
+    n, K = len(cases), max(1, max(len(p) for _, p in cases))
+    segs = torch.zeros(n, K, 2)
+    counts = torch.zeros(n, dtype=torch.int32)
+    for i, (_, pred) in enumerate(cases):
+        counts[i] = len(pred)
+        if pred:
+            segs[i, :len(pred)] = torch.tensor(pred, dtype=torch.float32)
+    slots = pack_slots(segs, torch.zeros(n, K), torch.zeros(n, K, dtype=torch.int32), counts).to(DEV)
+    avg, by_thr, per_video = atiou(slots, [c[0] for c in cases], tuple(THRESHOLDS))
+    assert np.array_equal(per_video.cpu().numpy(), g["per_video"])
+    assert [by_thr[t] for t in THRESHOLDS] == g["by_threshold"].tolist()
+    assert avg == float(g["average"])
 
 
 # ------------------------------------------------------------------------------------ GPU collate (f2)
@@ -623,3 +744,24 @@ def test_infer_cli_matches_the_reference_style_loop(tmp_path, capsys):
     assert abs(got - want) < 1e-12, (got, want)
     got16 = infer.main(["--config_path", str(tmp_path / "cfg.yaml"), "--resume", str(tmp_path / "ckpt.pth"), "--bf16-features"])
     assert got16 == got
+
+
+# ------------------------------------------------------------------------------------ run-time switches
+@pytest.mark.parametrize("env", [{"RP_LN_IN_GEMM": "0"}, {"RP_PDL": "0"}, {"RP_STRICT_MASKS": "1"}],
+                         ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_runtime_switches_keep_parity(env):
+    """The switches the library reads from the environment (stand-alone LayerNorm kernels instead of the
+    GEMM-fused epilogue, no programmatic dependent launch, synchronous mask check) select code that ships in
+    the .so: the golden forward / inference_ tests must pass under each of them (a fresh process, because the
+    library reads them once)."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "pytest", str(root / "tests" / "test_gpu_model.py"), "-q", "-m", "gpu",
+                        "-p", "no:cacheprovider", "-k",
+                        "forward_matches_reference_golden or inference_matches_reference_golden or "
+                        "forward_matches_oracle_ragged_small or masks_that_are_not"],
+                       env={**os.environ, **env}, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -132,3 +132,28 @@ def test_losses_oracle_matches_reference_golden():
                         torch.from_numpy(g[f"{name}_labels"]))
         ref = float(g[f"{name}_loss"])
         assert abs(float(got) - ref) <= 1e-6 * abs(ref), (name, float(got), ref)
+
+
+# ---- pins added in round 2 (oracle/make_golden_aux.py, generated against the reference itself) ----------
+def test_mha_oracle_matches_reference_golden(golden_dir):
+    """oracle.mmct.mha_forward vs models/transformer.py:37-81 MultiHeadAttention (tests/golden/mha_cases.npz)."""
+    from oracle.make_golden_aux import checksum, mha_cases, mha_weights
+    g = np.load(golden_dir / "mha_cases.npz")
+    sd = mha_weights()
+    assert abs(sum(checksum(v.numpy()) for v in sd.values()) - float(g["weight_checksum"])) < 1e-6, \
+        "seeded MHA weights differ from the ones the fixture was generated with"
+    for name, q, k, v, mask in mha_cases():
+        out = mmct.mha_forward(sd, q, k, v, mask, 8)
+        ref = torch.from_numpy(g[f"{name}_out_sub"])
+        assert (out[..., ::8] - ref).abs().max().item() < 1e-5, name
+
+
+def test_tiou_oracle_matches_reference_golden(golden_dir):
+    """oracle.mmct.calculate_tiou / atiou vs utils/metrics.py:82-111 + inference.py:45-55 (tiou_cases.npz)."""
+    from oracle.make_golden_aux import THRESHOLDS, tiou_cases
+    g = np.load(golden_dir / "tiou_cases.npz")
+    cases = tiou_cases(int(g["seed"]), int(g["n_cases"]))
+    per = np.array([[mmct.calculate_tiou(gt, pred, THRESHOLDS)[t] for t in THRESHOLDS] for gt, pred in cases])
+    assert np.array_equal(per, g["per_video"])
+    avg, by_t = mmct.atiou([c[0] for c in cases], [c[1] for c in cases], THRESHOLDS)
+    assert avg == float(g["average"]) and [by_t[t] for t in THRESHOLDS] == g["by_threshold"].tolist()

@@ -12,6 +12,4 @@ run gemm tests/test_gpu_kernels.py -k "gemm"
 run rowwise tests/test_gpu_kernels.py -k "concat or layernorm or head_out"
 run fmha tests/test_gpu_kernels.py -k "fmha"
 run model tests/test_gpu_model.py
-RP_LN_IN_GEMM=0 run model_ln_standalone tests/test_gpu_model.py -k "forward or inference or full_size"
-RP_FMHA_NQ=2 run fmha_nq2 tests/test_gpu_kernels.py -k fmha
-RP_GEMM_CG=1 run gemm_cg1 tests/test_gpu_kernels.py -k gemm
+run comparator tests/test_gpu_comparator.py
