@@ -134,6 +134,45 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def stress_t8192(model, dev, peaks, B=4, T=8192, iters=5):
+    """BASELINE.json configs[3]: T = 8192 feature steps, 4096 pre-NMS candidates per video (device-resident inputs,
+    CUDA events).  The positional table is extended past the reference's 5000 (same formula)."""
+    from repurpose_b200 import synth
+    from repurpose_b200.models.MMCTransformer import MMCTransformer
+    cfg = dict(synth.TEST_CFG, pre_nms_topk=4096)
+    sd = {k: v for k, v in model.state_dict().items() if not k.endswith("positional_encoding.pe")}
+    m = MMCTransformer(**synth.MODEL_CFG, max_len=T)
+    m.load_state_dict(sd, strict=False)
+    m = m.to(dev).eval()
+    host = synth.make_batch([T] * B, seed=77, T=T)
+    devb = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
+    out = m(devb)
+    r = m.decode_device(out, devb, cfg)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    fwd_ms = dec_ms = 0.0
+    for _ in range(iters):
+        e[0].record()
+        out = m(devb)
+        e[1].record()
+        r = m.decode_device(out, devb, cfg)
+        e[2].record()
+        torch.cuda.synchronize()
+        fwd_ms += e[0].elapsed_time(e[1]) / iters
+        dec_ms += e[1].elapsed_time(e[2]) / iters
+    m.profile_begin()
+    for _ in range(2):
+        m(devb)
+    prof = m.profile_end()
+    fm_ms, fm_n = prof["fmha"]
+    fm_tflops = 4.0 * B * 8 * T * T * 64 / (fm_ms / fm_n * 1e-3) / 1e12
+    return {"batch": B, "seq_len": T, "pre_nms_topk": 4096, "max_seg_num": synth.max_seg_num(T, cfg["max_seg_per_min"]),
+            "videos_per_s": B / ((fwd_ms + dec_ms) * 1e-3), "forward_ms": fwd_ms, "decode_nms_us_per_video": dec_ms * 1e3 / B,
+            "candidates_per_video": [int(x) for x in r["ncand"].tolist()], "segments": int(r["counts"].sum().item()),
+            "fmha_tflops": fm_tflops, "fmha_frac_of_sustained_peak": fm_tflops / peaks["tflops_sustained"],
+            "model_tflops": B * algorithmic_flops_per_video(T) / (fwd_ms * 1e-3) / 1e12}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from repurpose_b200 import synth  # synthetic inputs (the oracle is only used by the cpu_baseline leg)
@@ -219,21 +258,31 @@ def run_ours(args, rank, world, local_rank):
     # 177 MB qkv in + 59 MB o out) — only valid for the default B=32, T=1801 workload
     fmha_traffic = 220.34e6 if (BATCH, SEQ) == (32, 1801) else None
     roofline = {"kernel": "fmha_fwd_kernel<mask=0,emu=1,nq=1>", "bound": "tensor",
+                "algorithmic": "4*B*H*T^2*64 FLOP per launch (SURVEY.md 8d: 32,768*T^2 per video over 16 layers), padded rows/keys excluded",
                 "achieved": fm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": fm_tflops / peaks["tflops_sustained"], "traffic": fmha_traffic,
                 "flops_per_launch": fmha_flops, "launch_ms": fm_ms / fm_n,
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside the step)",
                 "share_of_step": kern["fmha"]["share"]}
     ln_ms, ln_n = prof["layernorm"]
-    # 31 of the 34 LayerNorm launches are mode 0 (read fp32 2048 B + write bf16 1024 B per row)
+    # the two stand-alone LayerNorm launches left in a step (the 32 per-layer ones run inside GEMM epilogues):
+    # mode 1 after the input projection (read x 2048 B, write h fp32 2048 B + u bf16 1024 B per row) and
+    # mode 2 after feature_map (read 2048 B, write feats fp32 2048 B + two bf16 head inputs 2 x 1024 B)
     gemm_flops = {"gemm_in": 2.0 * M * 512 * 2944, "gemm_qkv": 2.0 * M * 1536 * 512, "gemm_out": 2.0 * M * 512 * 512,
                   "gemm_ff1": 2.0 * M * 2048 * 512, "gemm_ff2": 2.0 * M * 512 * 2048}
     for tag, fl in gemm_flops.items():
         ms, n = prof[tag]
         kern[tag]["tflops"] = fl / (ms / n * 1e-3) / 1e12
     kern["fmha"]["tflops"] = fm_tflops
-    kern["layernorm"]["gbs_lower_bound"] = (M * 3072.0) / (ln_ms / ln_n * 1e-3) / 1e9
-    kern["layernorm"]["hbm_peak_gbs"] = peaks["hbm_gbs"]
+    ln_bytes = M * (5120.0 + 6144.0) if ln_n == 2 * prof_steps else M * 3072.0 * (ln_n / prof_steps)
+    kern["layernorm"]["gbs"] = ln_bytes / (ln_ms / prof_steps * 1e-3) / 1e9
+    kern["layernorm"]["hbm_frac"] = kern["layernorm"]["gbs"] / peaks["hbm_gbs"]
+    ho_ms, ho_n = prof["head_out"]
+    kern["head_out"]["gbs"] = M * (2 * 512 + 12.0) / (ho_ms / ho_n * 1e-3) / 1e9   # two bf16 [M,256] in, 3 fp32 out
+    kern["head_out"]["hbm_frac"] = kern["head_out"]["gbs"] / peaks["hbm_gbs"]
+    ca_ms, ca_n = prof["cast"]
+    kern["cast"]["gbs"] = M * 2944 * 6.0 / (ca_ms / ca_n * 1e-3) / 1e9                # fp32 in, bf16 out
+    kern["cast"]["hbm_frac"] = kern["cast"]["gbs"] / peaks["hbm_gbs"]
 
     # ---- end to end through the public API with HOST inputs ----------------------------------------
     from repurpose_b200.scheduler import InferencePipeline
@@ -299,6 +348,25 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base, _ = cpu_reference_run(steps=2, warmup=1)
 
+    # ---- BASELINE.json configs 3 and 4, where the driver sees them ----------------
+    extra = {}
+    if not args.no_extras:
+        del pipe
+        sys.path.insert(0, str(ROOT / "tools"))
+        from bench_10k import run_config3
+        n10k = 10000
+        for tag, bf in (("fp32_rows", False), ("bf16_rows", True)):
+            r = run_config3(model, n10k, BATCH, bf, False, rank, world, dev, placement)
+            if rank == 0:
+                extra.setdefault("config3_10k", {"videos": n10k, "n_gpus": world, "mean_len": r["mean_len"],
+                                                 "padding_efficiency": r["padding_efficiency"],
+                                                 "what": "10,000 synthetic videos with the test-split length distribution, "
+                                                         "LPT-sharded per video, length-bucketed ragged batches from pinned "
+                                                         "host rows, one all-gather of the segment slots; host wall clock, max over ranks"})
+                extra["config3_10k"][tag] = {"videos_per_s": r["value"], "seconds": r["seconds"], "segments": r["segments"]}
+        if world == 1:
+            extra["stress_T8192"] = stress_t8192(model, dev, peaks)
+
     if rank == 0:
         flops_step = BATCH * algorithmic_flops_per_video(SEQ)
         line = {"metric": "videos/s", "value": value, "unit": "videos/s", "n_gpus": world,
@@ -311,7 +379,7 @@ def run_ours(args, rank, world, local_rank):
                            "weights": "random init (manual_seed 0), reg_head.7 scaled/biased so Soft-NMS sees candidates"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu_base,
-                "model_tflops": flops_step / (ms_step * 1e-3) / 1e12, "kernels": kern}
+                "model_tflops": flops_step / (ms_step * 1e-3) / 1e12, "kernels": kern, "extra": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -324,6 +392,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-3 (10 K videos) and config-4 (T=8192) blocks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -49,11 +49,89 @@ class PositionalEncoding(nn.Module):
         return pe
 
 
+class _GraphedInference:
+    """forward -> decode -> Soft-NMS -> slot packing of one (batch, padded length, decode settings) shape as ONE
+    CUDA graph over static buffers: the reference's call pattern is batch size 1 with a host synchronisation per
+    video (inference.py:31, 39-47), where the ~125 kernel launches and the Python around them — not the GPU —
+    set the latency.  T is padded to a multiple of 128 (15 shapes cover every length up to 1801); rows beyond a
+    video's length never reach a valid row (keys are masked by length, everything else is row-wise)."""
+
+    def __init__(self, model, B, Tp, settings):
+        from ..scheduler import pack_slots
+        dev = model.device
+        c = model._cfg
+        self.B, self.Tp = B, Tp
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.vis = torch.zeros(B, Tp, c["vis_dim"], **f32)
+        self.aud = torch.zeros(B, Tp, c["aud_dim"], **f32)
+        self.txt = torch.zeros(B, Tp, c["text_dim"], **f32)
+        self.mask8 = torch.zeros(B, Tp, dtype=torch.uint8, device=dev)
+        self.max_seg = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.lens = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.logits = torch.empty(B, Tp, 1, **f32)
+        self.offsets = torch.empty(B, Tp, 2, **f32)
+        self.feats = torch.empty(B, Tp, c["d_model"], **f32)
+        self.kcap = kcap = max(1, int(np.ceil((Tp // 60) * settings["max_seg_per_min"])))
+        self.segs = torch.zeros(B, kcap, 2, **f32)
+        self.scores = torch.zeros(B, kcap, **f32)
+        self.dscores = torch.zeros(B, kcap, **f32)
+        self.labels = torch.zeros(B, kcap, dtype=torch.int32, device=dev)
+        self.counts = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.ncand = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.slots_host = torch.zeros(B, 1 + 4 * kcap, dtype=torch.float32).pin_memory()
+        self.flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.max_seg_host = torch.zeros(B, dtype=torch.int32).pin_memory()
+        cfg = model._decode_cfg(settings)
+        lib = _lib.load()
+        ws = model._get_workspace(B, Tp)
+
+        def launch():
+            st = cur_stream()
+            check(lib.rp_mask_lens(ptr(self.mask8), B, Tp, ptr(self.lens), ptr(self.flag), st), "rp_mask_lens")
+            check(lib.rp_forward(model._handle, ptr(self.vis), ptr(self.aud), ptr(self.txt), ptr(self.lens), B, Tp,
+                                 ptr(self.logits), ptr(self.offsets), ptr(self.feats), ptr(ws), ws.numel(), st),
+                  "rp_forward")
+            check(lib.rp_decode_nms(ptr(self.logits), ptr(self.offsets), ptr(self.lens), ptr(self.max_seg), B, Tp,
+                                    C.byref(cfg), kcap, ptr(self.segs), ptr(self.scores), ptr(self.dscores),
+                                    ptr(self.labels), ptr(self.counts), ptr(self.ncand), 0, 0, 0, st), "rp_decode_nms")
+            self.slots_host.copy_(pack_slots(self.segs, self.scores, self.labels, self.counts), non_blocking=True)
+            self.flag_host.copy_(self.flag, non_blocking=True)
+
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                launch()                       # warm-up outside the capture (lazy kernel configuration)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                launch()
+        self.workspace = ws                    # the graph holds its address
+
+    def run(self, vis, aud, txt, masks, max_seg):
+        """copies the inputs into the static buffers (H2D or D2D), replays and waits; -> host slots [B, 1+4K]"""
+        T = vis.shape[1]
+        self.vis[:, :T].copy_(vis, non_blocking=True)
+        self.aud[:, :T].copy_(aud, non_blocking=True)
+        self.txt[:, :T].copy_(txt, non_blocking=True)
+        self.mask8.zero_()
+        self.mask8[:, :T].copy_(masks.reshape(self.B, T), non_blocking=True)
+        self.max_seg_host.copy_(torch.as_tensor(max_seg, dtype=torch.int32))
+        self.max_seg.copy_(self.max_seg_host, non_blocking=True)
+        self.graph.replay()
+        torch.cuda.current_stream(self.vis.device).synchronize()
+        if int(self.flag_host[0]) != 0:
+            raise _lib.RepurposeError(MMCTransformer._MASK_MSG)
+        return self.slots_host
+
+
 def _invalidate_hook(module, _incompatible_keys):
     module._invalidate()
 
 
-_NATIVE_STATE = dict(_handle=None, _weights_sig=None, _workspace=None, _last_masks=None, _last_lens=None)
+_NATIVE_STATE = dict(_handle=None, _weights_sig=None, _workspace=None, _last_masks=None, _last_lens=None, _graphs=None)
 
 
 class MMCTransformer(nn.Module):
@@ -90,6 +168,9 @@ class MMCTransformer(nn.Module):
         self._workspace = None
         self._mask_checks = []
         self._last_masks = self._last_lens = None
+        self._graphs = None
+        # "auto": CUDA-graph replay for launch-bound calls (at most GRAPH_MAX_BATCH videos); True / False force it
+        self.cuda_graphs = "auto" if os.environ.get("RP_CUDA_GRAPHS", "1") != "0" else False
         self.register_load_state_dict_post_hook(_invalidate_hook)
 
     def _init_weights(self):
@@ -176,6 +257,25 @@ class MMCTransformer(nn.Module):
         if ws is None or ws.numel() < need or ws.device != self.device:
             self._workspace = ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return ws
+
+    GRAPH_MAX_BATCH = 4
+
+    def _graphed(self, B, T, settings):
+        """the CUDA-graph entry for this shape, or None when the call is not launch-bound / graphs are off"""
+        if self.cuda_graphs is False or (self.cuda_graphs == "auto" and B > self.GRAPH_MAX_BATCH):
+            return None
+        Tp = -(-T // 128) * 128
+        if Tp > self._cfg["max_len"] or int(np.ceil((Tp // 60) * settings["max_seg_per_min"])) > 64:
+            return None
+        key = (B, Tp, tuple(sorted((k, float(v)) for k, v in settings.items())))
+        if self._graphs is None:
+            self._graphs = {}
+        e = self._graphs.get(key)
+        if e is None:
+            if len(self._graphs) >= 64:         # a pathological mix of shapes: start over rather than grow
+                self._graphs.clear()
+            e = self._graphs[key] = _GraphedInference(self, B, Tp, settings)
+        return e
 
     @staticmethod
     def _as_f32(t, dev):
@@ -419,11 +519,26 @@ class MMCTransformer(nn.Module):
         CPU tensors taken from one packed device->host copy, which is what callers that immediately
         do `.tolist()` (inference.py:47, main.py:689) want.  `output` (extension): a `forward(batch)` result to
         decode instead of running the forward again."""
-        r = (self.inference_device(batch, inference_settings) if output is None
-             else self.decode_device(output, batch, inference_settings))
         vid_idxs = batch["video_id"]
         vid_lens = batch["duration"]
         results = []
+        if output is None and not batch.get("ragged") and batch.get("parts") is None:
+            self._ensure_ready()
+            vis = batch["visual_feats"]
+            g = self._graphed(int(vis.shape[0]), int(vis.shape[1]), inference_settings)
+            if g is not None:
+                from ..scheduler import unpack_slots
+                max_seg = [int(np.ceil((int(v) // 60) * inference_settings["max_seg_per_min"])) for v in vid_lens]
+                with torch.cuda.device(self.device):
+                    host = g.run(vis, batch["audio_feats"], batch["text_feats"], batch["masks"], max_seg)
+                for o, vidx, vlen in zip(unpack_slots(host), vid_idxs, vid_lens):
+                    if not to_host:             # like the reference: tensors on the model's device
+                        o = {k: v.to(self.device) for k, v in o.items()}
+                    o["video_id"], o["duration"] = vidx, vlen
+                    results.append(o)
+                return results
+        r = (self.inference_device(batch, inference_settings) if output is None
+             else self.decode_device(output, batch, inference_settings))
         if to_host:
             from ..scheduler import pack_slots, unpack_slots
             slots = pack_slots(r["segments"], r["scores"], r["labels"], r["counts"])

@@ -29,9 +29,11 @@ def sample_lengths(n: int, seed: int, t_max: int = MAX_SEQ_LEN) -> list[int]:
     return [int(max(1, min(t_max, round(x)))) for x in v]
 
 
-def make_batch(lens, seed: int, T: int | None = None, cfg=MODEL_CFG, pin: bool = False):
+def make_batch(lens, seed: int, T: int | None = None, cfg=MODEL_CFG, pin: bool = False, smooth: int = 0):
     """Collated batch on the host: feats ~ N(0,1) fp32 (zero in padded steps like preprocessing()),
-    masks [B,1,T] bool left-aligned, labels/segments zeros, video_id, duration = lens."""
+    masks [B,1,T] bool left-aligned, labels/segments zeros, video_id, duration = lens.
+    smooth = W > 1: the features are a W-step moving average of white noise (unit variance kept), i.e.
+    temporally correlated like real 1-fps CLIP / PANNs / MiniLM features, instead of independent per step."""
     lens = [int(x) for x in lens]
     B = len(lens)
     T = int(T if T is not None else max(lens))
@@ -41,6 +43,10 @@ def make_batch(lens, seed: int, T: int | None = None, cfg=MODEL_CFG, pin: bool =
     for key, dim in (("visual_feats", cfg["vis_dim"]), ("audio_feats", cfg["aud_dim"]),
                      ("text_feats", cfg["text_dim"])):
         x = torch.randn(B, T, dim, generator=g, dtype=torch.float32)
+        if smooth > 1:
+            w = int(smooth) | 1
+            x = torch.nn.functional.avg_pool1d(x.transpose(1, 2), w, 1, w // 2, count_include_pad=True)
+            x = (x.transpose(1, 2) * (w ** 0.5)).contiguous()
         x = x * valid[:, :, None]
         batch[key] = x.pin_memory() if pin else x
     batch["masks"] = valid[:, None, :].clone()

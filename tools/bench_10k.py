@@ -24,27 +24,11 @@ from repurpose_b200.features import ragged_batch  # noqa: E402
 from repurpose_b200.models.MMCTransformer import MMCTransformer  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--videos", type=int, default=10000)
-    ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--bf16", action="store_true", help="feature rows pre-converted to bf16 (half the H2D bytes)")
-    ap.add_argument("--padded", action="store_true", help="host-side padding (reference-style collate) instead of the GPU collate")
-    a = ap.parse_args()
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    lr = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(lr)
-    dev = torch.device("cuda", lr)
-    from repurpose_b200.affinity import bind_to_gpu_numa
-    placement = bind_to_gpu_numa(lr)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(0)
-    m = MMCTransformer(**synth.MODEL_CFG)
-    m.load_state_dict(synth.bias_reg_head({k: v.clone() for k, v in m.state_dict().items()}))
-    m = m.to(dev).eval()
-
-    lens = synth.sample_lengths(a.videos, seed=1)
+def run_config3(m, videos=10000, batch=32, bf16=False, padded=False, rank=0, world=1, dev=None, placement=None):
+    """One timed pass over `videos` synthetic videos with the model `m` of this rank; returns the result
+    dict on rank 0 (None elsewhere).  Collective: the one all-gather of the segment slots."""
+    dev = dev or m.device
+    lens = synth.sample_lengths(videos, seed=1)
     shards = S.shard_videos(lens, world)
     owned = shards[rank]
     kcap = max(1, max(synth.max_seg_num(l, synth.TEST_CFG["max_seg_per_min"]) for l in lens))
@@ -54,8 +38,7 @@ def main():
     pool = {"visual_feats": torch.randn(POOL, 512, generator=g).pin_memory(),
             "audio_feats": torch.randn(POOL, 2048, generator=g).pin_memory(),
             "text_feats": torch.randn(POOL, 384, generator=g).pin_memory()}
-
-    if a.bf16:
+    if bf16:
         pool = {k: v.to(torch.bfloat16).pin_memory() for k, v in pool.items()}
 
     def video(i):
@@ -63,8 +46,8 @@ def main():
         off = (i * 37) % (POOL - synth.MAX_SEQ_LEN)
         return {k: v[off:off + t] for k, v in pool.items()} | {"video_id": i}
 
-    batches_idx = S.make_batches(owned, a.batch)
-    collate = (lambda vs: S.collate(vs, pin=True)) if a.padded else ragged_batch
+    batches_idx = S.make_batches(owned, batch)
+    collate = (lambda vs: S.collate(vs, pin=True)) if padded else ragged_batch
 
     def host_batches():
         for idxs in batches_idx:
@@ -92,15 +75,41 @@ def main():
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    counts = merged[:, 0]
+    pad_eff = sum(lens) / sum(max(lens[i] for i in b) * len(b) for sh in shards for b in S.make_batches(sh, batch))
+    return {"metric": "videos/s", "value": videos / dt.item(), "n_gpus": world, "videos": videos,
+            "seconds": dt.item(), "mean_len": float(np.mean(lens)), "batch": batch,
+            "collate": "host-padded" if padded else "gpu (ragged rows over PCIe)", "feature_dtype": "bf16" if bf16 else "fp32",
+            "padding_efficiency": pad_eff, "segments": int(counts.sum().item()),
+            "videos_with_segments": int((counts > 0).sum().item()),
+            "host_numa_node_rank0": None if placement is None else placement.get("numa_node"),
+            "timing": "host wall clock around pipeline + all-gather, max over ranks; includes host collation and H2D"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--videos", type=int, default=10000)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--bf16", action="store_true", help="feature rows pre-converted to bf16 (half the H2D bytes)")
+    ap.add_argument("--padded", action="store_true", help="host-side padding (reference-style collate) instead of the GPU collate")
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    lr = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(lr)
+    dev = torch.device("cuda", lr)
+    from repurpose_b200.affinity import bind_to_gpu_numa
+    placement = bind_to_gpu_numa(lr)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    m = MMCTransformer(**synth.MODEL_CFG)
+    m.load_state_dict(synth.bias_reg_head({k: v.clone() for k, v in m.state_dict().items()}))
+    m = m.to(dev).eval()
+    res = run_config3(m, a.videos, a.batch, a.bf16, a.padded, rank, world, dev, placement)
     if rank == 0:
-        counts = merged[:, 0]
-        pad_eff = sum(lens) / sum(max(lens[i] for i in b) * len(b) for sh in shards for b in S.make_batches(sh, a.batch))
-        print(json.dumps({"metric": "videos/s", "value": a.videos / dt.item(), "n_gpus": world, "videos": a.videos,
-                          "seconds": dt.item(), "mean_len": float(np.mean(lens)), "batch": a.batch,
-                          "collate": "host-padded" if a.padded else "gpu (ragged rows over PCIe)", "feature_dtype": "bf16" if a.bf16 else "fp32",
-                          "padding_efficiency": pad_eff, "segments": int(counts.sum().item()),
-                          "videos_with_segments": int((counts > 0).sum().item()), "host_numa_node_rank0": placement["numa_node"],
-                          "timing": "host wall clock around pipeline + all-gather, max over ranks; includes host collation and H2D"}))
+        print(json.dumps(res))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
