@@ -154,6 +154,22 @@ int32_t rp_atiou(const float* slots, int32_t n_videos, int32_t K, const double* 
 int32_t rp_focal_loss_sum(const float* logits, const float* targets, const uint8_t* mask, int64_t n, float alpha,
                           float gamma, double* scratch, float* out, void* stream);
 
+/* ---- first pieces of the training step (reference main.py:294-409) ------------------------
+ * rp_focal_loss_grad      <- autograd of sigmoid_focal_loss(...).sum() / batch_size   models/losses.py:5-53,
+ *                            models/MMCTransformer.py:159-179, main.py:326-333: dlogits[i] = mask[i] ? scale * dL_i/dx_i : 0
+ * rp_layernorm512_bwd     <- autograd of nn.LayerNorm(512) (models/MMCTransformer.py:46-58 norm1/norm2/encoder_norm...):
+ *                            dx [M,512], dgamma [512], dbeta [512]; scratch: rp_layernorm512_bwd_scratch_bytes()
+ * rp_adam_step            <- optim.Adam(model.parameters(), lr, weight_decay).step()   main.py:190-191, :368;
+ *                            flat fp32 buffers, step >= 1, optional bf16 copy of the updated parameters */
+int32_t rp_focal_loss_grad(const float* logits, const float* targets, const uint8_t* mask, int64_t n, float alpha,
+                           float gamma, float scale, float* dlogits, void* stream);
+int64_t rp_layernorm512_bwd_scratch_bytes(void);
+int32_t rp_layernorm512_bwd(const float* x, const float* dy, const float* gamma, int64_t M, float eps, float* dx,
+                            float* dgamma, float* dbeta, void* scratch, int64_t scratch_bytes, void* stream);
+int32_t rp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int32_t step, void* param_bf16,
+                     void* stream);
+
 /* ---- building blocks (also what the unit tests drive) ---------------------------------------- */
 /* D[M,N] = A[M,K] * W[N,K]^T + bias (+ReLU | +residual); A, W bf16 row-major with pitches lda/ldw
  * (elements); epilogue: 0 bf16 out, 1 bf16 out + ReLU, 2 f32 out, 3 f32 out + residual (may alias D).

@@ -33,19 +33,28 @@ def main(ref_dir="/root/reference"):
         lens = torch.randint(1, T + 1, (B,), generator=g)
         lens[0] = T
         masks = (torch.arange(T)[None, :] < lens[:, None])[:, None, :]
+        logits = logits.requires_grad_(True)
         ref = RefModel.losses(None, masks, logits, None, labels, None, None)["cls_loss"]
+        (ref / B).backward()                      # main.py:326-333: final_loss = cls_loss / batch_size
+        cases[f"{name}_dlogits"] = logits.grad.numpy().copy()
+        logits = logits.detach()
         ours = oracle_losses.losses(masks, logits, labels)
+        dl = oracle_losses.losses_grad(masks, logits, labels, B)
+        gerr = float((dl - torch.from_numpy(cases[f"{name}_dlogits"])).abs().max())
+        assert gerr < 1e-6, (name, gerr)
         rel = abs(float(ours) - float(ref)) / max(abs(float(ref)), 1e-12)
         assert rel < 1e-6, (name, float(ref), float(ours))
-        report.append(f"losses[{name}]: B={B} T={T} cls_loss={float(ref):.6f}; oracle rel. diff {rel:.1e}")
+        report.append(f"losses[{name}]: B={B} T={T} cls_loss={float(ref):.6f}; oracle rel. diff {rel:.1e}; "
+                      f"d(cls_loss/B)/dlogits from the reference's autograd stored, oracle max|diff| {gerr:.1e}")
         cases[f"{name}_logits"] = logits.numpy()
         cases[f"{name}_labels"] = labels.numpy()
         cases[f"{name}_masks"] = masks.numpy()
         cases[f"{name}_loss"] = np.array(float(ref), dtype=np.float64)
     cases["names"] = np.array([s[0] for s in specs])
     np.savez_compressed(GOLD / "losses_cases.npz", **cases)
-    with open(GOLD / "PIN_REPORT.txt", "a") as f:
-        f.write("\n".join(report) + "\n")
+    pin = GOLD / "PIN_REPORT.txt"
+    old = [l for l in pin.read_text().splitlines() if not l.startswith("losses[")]
+    pin.write_text("\n".join(old + report) + "\n")
     print("\n".join(report))
 
 

@@ -42,6 +42,10 @@ SIGNATURES = {
     "rp_forward_ragged": (c_i32, [c_vp] * 8 + [c_i32, c_i32] + [c_vp] * 4 + [c_i64, c_vp]),
     "rp_forward_ragged_bf16": (c_i32, [c_vp] * 8 + [c_i32, c_i32] + [c_vp] * 4 + [c_i64, c_vp]),
     "rp_focal_loss_sum": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_vp]),
+    "rp_focal_loss_grad": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_vp, c_vp]),
+    "rp_layernorm512_bwd_scratch_bytes": (c_i64, []),
+    "rp_layernorm512_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "rp_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_vp]),
     "rp_gemm_resid_ln": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64,
                                  c_i32, c_i32, c_vp]),
     "rp_profile_begin": (c_i32, [c_vp]),

@@ -520,6 +520,31 @@ int32_t rp_focal_loss_sum(const float* logits, const float* targets, const uint8
                                reinterpret_cast<cudaStream_t>(stream));
 }
 
+int32_t rp_focal_loss_grad(const float* logits, const float* targets, const uint8_t* mask, int64_t n, float alpha,
+                           float gamma, float scale, float* dlogits, void* stream) {
+  RP_CHECK(logits && targets && mask && dlogits, "rp_focal_loss_grad: null argument");
+  return launch_focal_loss_grad(logits, targets, mask, n, alpha, gamma, scale, dlogits,
+                                reinterpret_cast<cudaStream_t>(stream));
+}
+
+int64_t rp_layernorm512_bwd_scratch_bytes(void) { return layernorm512_bwd_scratch_floats() * int64_t(sizeof(float)); }
+
+int32_t rp_layernorm512_bwd(const float* x, const float* dy, const float* gamma, int64_t M, float eps, float* dx,
+                            float* dgamma, float* dbeta, void* scratch, int64_t scratch_bytes, void* stream) {
+  RP_CHECK(x && dy && gamma && dx && dgamma && dbeta && scratch, "rp_layernorm512_bwd: null argument");
+  RP_CHECK(scratch_bytes >= rp_layernorm512_bwd_scratch_bytes(), "rp_layernorm512_bwd: scratch too small");
+  return launch_layernorm512_bwd(x, dy, gamma, M, eps, dx, dgamma, dbeta, reinterpret_cast<float*>(scratch),
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int32_t step, void* param_bf16,
+                     void* stream) {
+  RP_CHECK(param && grad && exp_avg && exp_avg_sq, "rp_adam_step: null argument");
+  return launch_adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, param_bf16,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
 int32_t rp_gemm_bf16(int32_t epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
                      int64_t ldd, const float* bias, const float* resid, int64_t ldr, int32_t M,
                      int32_t N, int32_t K, void* stream) {

@@ -118,4 +118,17 @@ int launch_atiou(const float* slots, int n_videos, int K, const double* gt, cons
 int launch_focal_loss_sum(const float* logits, const float* targets, const uint8_t* mask, int64_t n, float alpha,
                           float gamma, double* scratch, float* out, cudaStream_t stream);
 
+// ---- first pieces of the training step: see train.cu ------------------------------------
+// dlogits[i] = mask[i] ? scale * d focal(logits[i], targets[i]) / d logits[i] : 0
+int launch_focal_loss_grad(const float* logits, const float* targets, const uint8_t* mask, int64_t n, float alpha,
+                           float gamma, float scale, float* dlogits, cudaStream_t stream);
+// LayerNorm over rows of 512: dx [M,512], dgamma [512], dbeta [512] from x, dy, gamma; scratch: fp32,
+// layernorm512_bwd_scratch_floats() values
+int64_t layernorm512_bwd_scratch_floats();
+int launch_layernorm512_bwd(const float* x, const float* dy, const float* gamma, int64_t M, float eps, float* dx,
+                            float* dgamma, float* dbeta, float* scratch, cudaStream_t stream);
+// one torch.optim.Adam step (L2 weight decay added to the gradient) on a flat fp32 buffer; p_bf16 (optional): bf16 copy
+int launch_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int step, void* p_bf16, cudaStream_t stream);
+
 }  // namespace rp
