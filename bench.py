@@ -182,10 +182,12 @@ def run_ours(args, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    # a job on fewer GPUs than the box has spreads over both halves of the host (affinity.pick_device:
+    # GPUs 0-3 of these boxes share a ~116 GB/s path to the pinned host memory, profiles/r02_topo_probe.json)
+    from repurpose_b200.affinity import bind_to_gpu_numa, pick_device
+    local_rank = pick_device(local_rank, world)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    # pinned host buffers on the GPU's own NUMA node (matters for the end-to-end arm at N > 1)
-    from repurpose_b200.affinity import bind_to_gpu_numa
     placement = bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -341,8 +343,12 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([ms_e2e16], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e16 = float(t.item())
-    e2e["bf16_feature_rows"] = {"value": world * BATCH * args.steps / (ms_e2e16 / 1e3), "ms_per_step": ms_e2e16 / args.steps,
-                                "h2d_bytes_per_step": int(sum(v.numel() * 2 for v in host16.values()))}
+    e2e_bf16 = {"value": world * BATCH * args.steps / (ms_e2e16 / 1e3), "unit": "videos/s", "ms_per_step": ms_e2e16 / args.steps,
+                "h2d_bytes_per_step": int(sum(v.numel() * 2 for v in host16.values())), "d2h_bytes_per_step": int(BATCH * slot * 4),
+                "what": "secondary: the same end-to-end call fed with feature rows converted ONCE to bf16 (features.to_bf16 / "
+                        "load_video_features(dtype='bf16')); bit-identical results, half the upload; fp32 `e2e` stays the headline"}
+    e2e["bf16_feature_rows"] = e2e_bf16
+    e2e["cuda_device"] = local_rank
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -377,7 +383,7 @@ def run_ours(args, rank, world, local_rank):
                            "parallelism": f"per-video sharding x{world}, one all-gather of segment slots",
                            "l2": "inputs (680 MB/step) and activations (650 MB) exceed the 126 MB L2",
                            "weights": "random init (manual_seed 0), reg_head.7 scaled/biased so Soft-NMS sees candidates"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "e2e": e2e, "e2e_bf16": e2e_bf16, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu_base,
                 "model_tflops": flops_step / (ms_step * 1e-3) / 1e12, "kernels": kern, "extra": extra}
         print(json.dumps(line), flush=True)

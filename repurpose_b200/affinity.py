@@ -52,3 +52,41 @@ def bind_to_gpu_numa(device_index: int) -> dict:
     except Exception:
         pass
     return info
+
+
+def _pci_bus_numbers() -> list[int] | None:
+    """PCI bus number of every visible GPU in CUDA order, or None when NVML is not usable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        n = pynvml.nvmlDeviceGetCount()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        order = [int(x) for x in visible.split(",")] if visible and all(x.strip().isdigit() for x in visible.split(",")) \
+            else list(range(n))
+        return [int(pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(i)).bus) for i in order]
+    except Exception:
+        return None
+
+
+def pick_device(local_rank: int, world_size: int, buses: list[int] | None = None) -> int:
+    """CUDA device for `local_rank` when a job uses fewer GPUs than the box has.
+
+    On the 8-GPU boxes of this pool the guest shows ONE NUMA node, but the four GPUs on PCI buses below 0x80
+    share a ~116 GB/s path to the pinned host memory while the other four do not (profiles/r02_topo_probe.json:
+    {0,1,2,3} 116 GB/s aggregate, {4,5,6,7} 209, {0,1,4,5} 213).  A 2- or 4-rank job therefore spreads its ranks
+    over both halves instead of taking devices 0..N-1.  With every GPU in use (or no PCI information) the
+    mapping is the identity."""
+    buses = _pci_bus_numbers() if buses is None else buses
+    if not buses or world_size >= len(buses) or local_rank >= world_size:
+        return local_rank
+    lo = [i for i, b in enumerate(buses) if b < 0x80]
+    hi = [i for i, b in enumerate(buses) if b >= 0x80]
+    if not lo or not hi:
+        return local_rank
+    order = []
+    for k in range(max(len(lo), len(hi))):          # 0, 4, 1, 5, ... : alternate between the two halves
+        if k < len(lo):
+            order.append(lo[k])
+        if k < len(hi):
+            order.append(hi[k])
+    return sorted(order[:world_size])[local_rank]

@@ -63,9 +63,9 @@ def main(argv=None):
         cfg = yaml.load(f, Loader=yaml.FullLoader)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from .affinity import bind_to_gpu_numa, pick_device
+    local_rank = pick_device(int(os.environ.get("LOCAL_RANK", "0")), world)
     torch.cuda.set_device(local_rank)
-    from .affinity import bind_to_gpu_numa
     bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

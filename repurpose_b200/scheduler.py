@@ -21,18 +21,60 @@ def video_cost(T: int) -> float:
     return 104_989_696.0 * T + 32_768.0 * T * T
 
 
-def shard_videos(lengths: Sequence[int], world_size: int) -> list[list[int]]:
+MODEL_FLOPS_PER_S = 7.5e14       # what one B200 sustains on this path (bench.py `model_tflops`)
+FEATURE_BYTES_PER_STEP = 11776   # fp32 visual 512 + audio 2048 + text 384 per feature step
+
+
+def shard_videos(lengths: Sequence[int], world_size: int, h2d_gbs: Sequence[float] | None = None,
+                 bytes_per_step: int = FEATURE_BYTES_PER_STEP) -> list[list[int]]:
     """Greedy longest-processing-time assignment of whole videos to ranks; deterministic (ties by
     video index).  Returns, per rank, the global video indices it owns (sorted by length, longest
-    first, so consecutive videos make low-padding batches)."""
+    first, so consecutive videos make low-padding batches).
+
+    h2d_gbs: measured host->device bandwidth of every rank (`measure_h2d_gbs`, all-gathered).  A video then
+    costs a rank max(compute time, upload time): on boxes where some GPUs reach the pinned host memory over a
+    slower path (profiles/r02_topo_probe.json: 23 vs 36 GB/s per GPU with all eight active) the faster ranks
+    take more videos instead of waiting for the slow ones at the all-gather.  Every rank must pass the same list."""
     order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
     load = [0.0] * world_size
     shards: list[list[int]] = [[] for _ in range(world_size)]
+
+    def seconds(i, r):
+        t = video_cost(int(lengths[i])) / MODEL_FLOPS_PER_S
+        if h2d_gbs is not None:
+            t = max(t, int(lengths[i]) * bytes_per_step / (float(h2d_gbs[r]) * 1e9))
+        return t
+
     for i in order:
-        r = min(range(world_size), key=lambda k: (load[k], k))
+        r = min(range(world_size), key=lambda k: (load[k] + seconds(i, k), k))
         shards[r].append(i)
-        load[r] += video_cost(int(lengths[i]))
+        load[r] += seconds(i, r)
     return shards
+
+
+def measure_h2d_gbs(device, mb: int = 256, reps: int = 4, group=None) -> list[float]:
+    """Pinned-host -> device bandwidth of every rank, measured with all ranks copying at the same time (that is
+    when shared paths show), all-gathered: the `h2d_gbs` argument of `shard_videos`.  ~50 ms."""
+    n = mb * 1024 * 1024 // 4
+    src = torch.empty(n, dtype=torch.float32).pin_memory()
+    dst = torch.empty(n, dtype=torch.float32, device=device)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize(device)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        dist.barrier(group)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(device)
+    mine = torch.tensor([n * 4 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9], dtype=torch.float32, device=device)
+    if world == 1:
+        return [float(mine[0])]
+    out = torch.empty(world, dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return [float(x) for x in out.tolist()]
 
 
 def make_batches(indices: Sequence[int], batch_size: int) -> list[list[int]]:

@@ -94,3 +94,27 @@ def test_all_gather_reconstructs_global_order_world2(n_videos):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     assert sum(n for _, _, n in res) == n_videos
+
+
+def test_bandwidth_weighted_sharding_and_device_picking():
+    """Boxes whose GPUs reach the pinned host memory at different speeds (profiles/r02_topo_probe.json): upload-bound
+    videos go preferentially to the fast ranks, every video is owned exactly once, and a job on fewer GPUs than
+    the box has spreads over both halves of the host."""
+    import numpy as np
+    from repurpose_b200.affinity import pick_device
+    from repurpose_b200.scheduler import shard_videos
+    lens = [int(x) for x in np.random.default_rng(0).integers(100, 1801, 999)]
+    speeds = [23.0] * 4 + [36.0] * 4
+    plain, weighted = shard_videos(lens, 8), shard_videos(lens, 8, speeds)
+    for shards in (plain, weighted):
+        assert sorted(i for sh in shards for i in sh) == list(range(len(lens)))
+    steps = lambda sh: sum(lens[i] for i in sh)
+    slow, fast = steps(weighted[0]), steps(weighted[7])
+    assert 1.35 < fast / slow < 1.75                        # ~36 / 23
+    assert max(map(steps, plain)) / min(map(steps, plain)) < 1.05
+    assert shard_videos(lens, 8, speeds) == weighted        # deterministic: every rank builds the same map
+    buses = [0x1b, 0x40, 0x53, 0x66, 0x9c, 0xc0, 0xd1, 0xe5]
+    assert [pick_device(r, 4, buses) for r in range(4)] == [0, 1, 4, 5]
+    assert [pick_device(r, 2, buses) for r in range(2)] == [0, 4]
+    assert [pick_device(r, 8, buses) for r in range(8)] == list(range(8))
+    assert pick_device(0, 1, buses) == 0 and pick_device(3, 4, []) == 3

@@ -24,12 +24,15 @@ from repurpose_b200.features import ragged_batch  # noqa: E402
 from repurpose_b200.models.MMCTransformer import MMCTransformer  # noqa: E402
 
 
-def run_config3(m, videos=10000, batch=32, bf16=False, padded=False, rank=0, world=1, dev=None, placement=None):
+def run_config3(m, videos=10000, batch=32, bf16=False, padded=False, rank=0, world=1, dev=None, placement=None,
+                balance=True):
     """One timed pass over `videos` synthetic videos with the model `m` of this rank; returns the result
     dict on rank 0 (None elsewhere).  Collective: the one all-gather of the segment slots."""
     dev = dev or m.device
     lens = synth.sample_lengths(videos, seed=1)
-    shards = S.shard_videos(lens, world)
+    # fp32 rows are upload-bound: ranks with a faster path to the pinned host memory take more videos
+    h2d = S.measure_h2d_gbs(dev) if (world > 1 and balance) else None
+    shards = S.shard_videos(lens, world, h2d, bytes_per_step=S.FEATURE_BYTES_PER_STEP // (2 if bf16 else 1))
     owned = shards[rank]
     kcap = max(1, max(synth.max_seg_num(l, synth.TEST_CFG["max_seg_per_min"]) for l in lens))
     # pool of feature rows; a video of length t views rows [off, off + t)
@@ -85,6 +88,8 @@ def run_config3(m, videos=10000, batch=32, bf16=False, padded=False, rank=0, wor
             "padding_efficiency": pad_eff, "segments": int(counts.sum().item()),
             "videos_with_segments": int((counts > 0).sum().item()),
             "host_numa_node_rank0": None if placement is None else placement.get("numa_node"),
+            "h2d_gbs_per_rank": None if h2d is None else [round(x, 1) for x in h2d],
+            "videos_per_rank": [len(sh) for sh in shards],
             "timing": "host wall clock around pipeline + all-gather, max over ranks; includes host collation and H2D"}
 
 
@@ -94,12 +99,13 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--bf16", action="store_true", help="feature rows pre-converted to bf16 (half the H2D bytes)")
     ap.add_argument("--padded", action="store_true", help="host-side padding (reference-style collate) instead of the GPU collate")
+    ap.add_argument("--no-balance", action="store_true", help="equal-cost sharding (ignore the measured per-rank H2D bandwidth)")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    lr = int(os.environ.get("LOCAL_RANK", 0))
+    from repurpose_b200.affinity import bind_to_gpu_numa, pick_device
+    lr = pick_device(int(os.environ.get("LOCAL_RANK", 0)), world)
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
-    from repurpose_b200.affinity import bind_to_gpu_numa
     placement = bind_to_gpu_numa(lr)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -107,7 +113,7 @@ def main():
     m = MMCTransformer(**synth.MODEL_CFG)
     m.load_state_dict(synth.bias_reg_head({k: v.clone() for k, v in m.state_dict().items()}))
     m = m.to(dev).eval()
-    res = run_config3(m, a.videos, a.batch, a.bf16, a.padded, rank, world, dev, placement)
+    res = run_config3(m, a.videos, a.batch, a.bf16, a.padded, rank, world, dev, placement, not a.no_balance)
     if rank == 0:
         print(json.dumps(res))
     if world > 1:
