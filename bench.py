@@ -10,8 +10,8 @@ Repurpose.yaml model, batch 32 at max_seq_len) per GPU through forward -> decode
 resident in HBM; `e2e` = the same through the public `scheduler.InferencePipeline.run` call with pinned
 HOST inputs (H2D of the features and D2H of the segment slots inside the timed region, overlapped with
 the compute of neighbouring steps); `e2e.bf16_feature_rows` = the same with feature rows pre-converted to bf16.
-`--impl reference` times the reference algorithm's CPU path (the oracle port; the reference is pure
-Python/PyTorch and cannot travel to the GPU box) on the host cores.
+`--impl reference` times the reference's own CPU implementation of the path on the host cores (its
+unmodified modules staged under oracle/_ref by oracle/build_ref.py; the oracle port if that copy is missing).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -98,24 +98,40 @@ def measured_peaks():
 
 
 def cpu_reference_run(steps: int, warmup: int):
-    """The reference algorithm on the host cores: oracle port of forward + decode + Soft-NMS on a
-    bounded sample (batch 2 at T=1801, BASELINE.json configs[0]) per step."""
-    from oracle import mmct, synth
+    """The reference algorithm on the host cores, on a bounded sample (batch 2 at T=1801, BASELINE.json
+    configs[0]) per step: the reference's OWN modules staged unmodified under oracle/_ref by
+    oracle/build_ref.py (`kind: "reference"`: MMCTransformer.inference_ = forward + per-video decode +
+    soft_nms_intervals_cpu); the oracle port only if that copy is missing (`kind: "port"`)."""
+    from oracle import build_ref, mmct, synth
     from repurpose_b200.models.MMCTransformer import MMCTransformer
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
     sd = {k: v.clone() for k, v in MMCTransformer(**synth.MODEL_CFG).state_dict().items()}
     sd = synth.bias_reg_head(sd)
     batch = synth.make_batch([SEQ] * CPU_SAMPLE_B, seed=0)
+    ref = build_ref.import_reference()
+    if ref is not None:
+        model = ref.MMCTransformer(**synth.MODEL_CFG)
+        model.load_state_dict(sd)
+        model.eval()
+        kind, what = "reference", "the reference's own models/MMCTransformer.py inference_ from oracle/_ref, unmodified"
+
+        def run():
+            return model.inference_(batch, synth.TEST_CFG)
+    else:
+        kind, what = "port", "oracle port of the reference"
+
+        def run():
+            return mmct.inference(sd, batch, synth.TEST_CFG)
     for _ in range(warmup):
-        mmct.inference(sd, batch, synth.TEST_CFG)
+        run()
     t0 = time.perf_counter()
     for _ in range(steps):
-        mmct.inference(sd, batch, synth.TEST_CFG)
+        run()
     dt = time.perf_counter() - t0
     return {"value": CPU_SAMPLE_B * steps / dt, "unit": "videos/s", "cores": torch.get_num_threads(),
-            "kind": "port",
-            "sample": f"{steps} step(s) of batch {CPU_SAMPLE_B} x T={SEQ} (oracle port of the reference, "
+            "kind": kind,
+            "sample": f"{steps} step(s) of batch {CPU_SAMPLE_B} x T={SEQ} ({what}, "
                       f"fp32 torch CPU, {warmup} warm-up)"}, dt / max(1, steps) * 1e3
 
 

@@ -170,6 +170,41 @@ int32_t rp_adam_step(float* param, const float* grad, float* exp_avg, float* exp
                      float beta1, float beta2, float eps, float weight_decay, int32_t step, void* param_bf16,
                      void* stream);
 
+/* ---- backward pass of the training step (reference main.py:326-333 `final_loss.backward()`,
+ *      i.e. torch.autograd over models/MMCTransformer.py:109-151).  bf16 tensor-core GEMMs with fp32 accumulation,
+ *      fp32 gradients, every reduction in a fixed order (no atomics).
+ * rp_train_scratch_bytes   size of the scratch buffer the two-stage reductions below need
+ * rp_layernorm512_bwd_acc  autograd of nn.LayerNorm(512) on a pre-LN branch: dh_inout += dx; dh_bf16 (optional) =
+ *                          bf16 copy of the updated dh (the operand of the next dgrad / wgrad GEMMs)
+ * rp_gemm_bwd              autograd of nn.Linear: kind 1 (dgrad) D[M,N] = A[M,K] B[K,N] with B the weight [out=K, in=N]
+ *                          as stored; kind 3 (wgrad) D[M,N] = A[K,M]^T B[K,N] with A = dY [tokens, out], B = X [tokens, in]
+ *                          (K = tokens, any count); out_f32 != 0: fp32 D, else bf16; splits > 1: split-K partials
+ *                          stacked in D [splits * M, N] (M % 256 == 0), to be summed by rp_splitk_reduce
+ * rp_colsum_bf16           bias gradient: out[N] = column sums of bf16 x[M, N]
+ * rp_relu_bwd              autograd of nn.ReLU: dy = act > 0 ? dy : 0 in place (bf16/bf16 or fp32/fp32)
+ * rp_head_out_bwd          autograd of cls_head.7 (Linear 256 -> 1) and the ReLU in front of it
+ *                          (models/MMCTransformer.py:71-80): da2 [M,256] bf16, dw [256], db [1]
+ * rp_fmha_train            rp_fmha (key-padding mode) that also writes the log2-domain log-sum-exp [B,H,T]
+ * rp_fmha_bwd              autograd of the attention inside nn.MultiheadAttention (models/MMCTransformer.py:41-55,
+ *                          132-138): dq (w.r.t. the unscaled q), dk, dv; dsum = scratch [B,H,T] fp32 */
+int64_t rp_train_scratch_bytes(void);
+int32_t rp_layernorm512_bwd_acc(const float* x, const float* dy, const float* gamma, int64_t M, float eps,
+                                float* dh_inout, void* dh_bf16, float* dgamma, float* dbeta, void* scratch,
+                                int64_t scratch_bytes, void* stream);
+int32_t rp_gemm_bwd(int32_t kind, int32_t out_f32, const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
+                    int64_t ldd, int32_t M, int32_t N, int32_t K, int32_t splits, void* stream);
+int32_t rp_splitk_reduce(const float* partials, int32_t splits, int64_t n, float* out, void* stream);
+int32_t rp_colsum_bf16(const void* x, int64_t M, int32_t N, float* out, void* scratch, int64_t scratch_bytes,
+                       void* stream);
+int32_t rp_relu_bwd(void* dy, const void* act, int64_t n, int32_t is_f32, void* stream);
+int32_t rp_head_out_bwd(const float* dlogits, const void* a2_bf16, const float* w, int64_t M, void* da2_bf16,
+                        float* dw, float* db, void* scratch, int64_t scratch_bytes, void* stream);
+int32_t rp_fmha_train(const void* q, const void* k, const void* v, void* o, int64_t ld_qkv, int64_t ld_o, int32_t B,
+                      int32_t H, int32_t T, const int32_t* kv_lens, float* lse, void* stream);
+int32_t rp_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                    float* dsum, void* dq, void* dk, void* dv, int64_t ld_qkv, int64_t ld_o, int64_t ld_dqkv,
+                    int32_t B, int32_t H, int32_t T, const int32_t* kv_lens, void* stream);
+
 /* ---- building blocks (also what the unit tests drive) ---------------------------------------- */
 /* D[M,N] = A[M,K] * W[N,K]^T + bias (+ReLU | +residual); A, W bf16 row-major with pitches lda/ldw
  * (elements); epilogue: 0 bf16 out, 1 bf16 out + ReLU, 2 f32 out, 3 f32 out + residual (may alias D).

@@ -19,7 +19,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 BUILD_DIR = PKG_DIR / "_build"
 LIB_PATH = PKG_DIR / "librepurpose_b200.so"
-SOURCES = ["host_util.cu", "gemm.cu", "fmha.cu", "rowwise.cu", "decode_nms.cu", "metrics.cu", "train.cu", "api.cu"]
+SOURCES = ["host_util.cu", "gemm.cu", "fmha.cu", "fmha_bwd.cu", "rowwise.cu", "decode_nms.cu", "metrics.cu", "train.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -537,6 +537,68 @@ int32_t rp_layernorm512_bwd(const float* x, const float* dy, const float* gamma,
                                  reinterpret_cast<cudaStream_t>(stream));
 }
 
+int64_t rp_train_scratch_bytes(void) { return train_scratch_floats() * int64_t(sizeof(float)); }
+
+int32_t rp_layernorm512_bwd_acc(const float* x, const float* dy, const float* gamma, int64_t M, float eps,
+                                float* dh_inout, void* dh_bf16, float* dgamma, float* dbeta, void* scratch,
+                                int64_t scratch_bytes, void* stream) {
+  RP_CHECK(x && dy && gamma && dh_inout && dgamma && dbeta && scratch, "rp_layernorm512_bwd_acc: null argument");
+  RP_CHECK(scratch_bytes >= rp_train_scratch_bytes(), "rp_layernorm512_bwd_acc: scratch too small");
+  return launch_layernorm512_bwd(x, dy, gamma, M, eps, dh_inout, dgamma, dbeta, reinterpret_cast<float*>(scratch),
+                                 reinterpret_cast<cudaStream_t>(stream), true, dh_bf16);
+}
+
+int32_t rp_gemm_bwd(int32_t kind, int32_t out_f32, const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
+                    int64_t ldd, int32_t M, int32_t N, int32_t K, int32_t splits, void* stream) {
+  RP_CHECK(A && B && D, "rp_gemm_bwd: null argument");
+  return launch_gemm_bwd(kind, out_f32 != 0, A, lda, B, ldb, D, ldd, M, N, K, splits,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_splitk_reduce(const float* partials, int32_t splits, int64_t n, float* out, void* stream) {
+  RP_CHECK(partials && out, "rp_splitk_reduce: null argument");
+  return launch_splitk_reduce(partials, splits, n, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_colsum_bf16(const void* x, int64_t M, int32_t N, float* out, void* scratch, int64_t scratch_bytes,
+                       void* stream) {
+  RP_CHECK(x && out && scratch, "rp_colsum_bf16: null argument");
+  RP_CHECK(scratch_bytes >= rp_train_scratch_bytes(), "rp_colsum_bf16: scratch too small");
+  return launch_colsum_bf16(x, M, N, out, reinterpret_cast<float*>(scratch), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_relu_bwd(void* dy, const void* act, int64_t n, int32_t is_f32, void* stream) {
+  RP_CHECK(dy && act, "rp_relu_bwd: null argument");
+  return launch_relu_bwd(dy, act, n, is_f32 != 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_head_out_bwd(const float* dlogits, const void* a2_bf16, const float* w, int64_t M, void* da2_bf16,
+                        float* dw, float* db, void* scratch, int64_t scratch_bytes, void* stream) {
+  RP_CHECK(dlogits && a2_bf16 && w && da2_bf16 && dw && db && scratch, "rp_head_out_bwd: null argument");
+  RP_CHECK(scratch_bytes >= rp_train_scratch_bytes(), "rp_head_out_bwd: scratch too small");
+  return launch_head_out_bwd(dlogits, a2_bf16, w, M, da2_bf16, dw, db, reinterpret_cast<float*>(scratch),
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_fmha_train(const void* q, const void* k, const void* v, void* o, int64_t ld_qkv, int64_t ld_o, int32_t B,
+                      int32_t H, int32_t T, const int32_t* kv_lens, float* lse, void* stream) {
+  RP_CHECK(q && k && v && o && lse, "rp_fmha_train: null argument");
+  FmhaArgs a{};
+  a.q = q; a.k = k; a.v = v; a.o = o;
+  a.ldq = a.ldk = a.ldv = ld_qkv; a.ldo = ld_o;
+  a.bsq = a.bsk = a.bsv = int64_t(T) * ld_qkv; a.bso = int64_t(T) * ld_o;
+  a.B = B; a.H = H; a.Tq = T; a.Tk = T; a.kv_lens = kv_lens; a.mask_mode = 0;
+  a.lse = lse;
+  return launch_fmha(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                    float* dsum, void* dq, void* dk, void* dv, int64_t ld_qkv, int64_t ld_o, int64_t ld_dqkv,
+                    int32_t B, int32_t H, int32_t T, const int32_t* kv_lens, void* stream) {
+  FmhaBwdArgs a{q, k, v, o, d_o, lse, dsum, dq, dk, dv, ld_qkv, ld_o, ld_dqkv, B, H, T, kv_lens};
+  return launch_fmha_bwd(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int32_t rp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                      float beta1, float beta2, float eps, float weight_decay, int32_t step, void* param_bf16,
                      void* stream) {

@@ -107,6 +107,7 @@ struct FmhaParams {
   const int32_t* kv_lens;
   const uint8_t* mask;
   int64_t mask_b_stride, mask_q_stride;
+  float* lse;  // optional [B, H, Tq]: log2-domain log-sum-exp of every score row (what the backward pass recomputes P from)
 };
 
 // ---- packed f32x2 helpers (sm_100 FFMA2/FADD2) ---------------------------------------------------
@@ -620,11 +621,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // ---- epilogue: O / l -> bf16 -> swizzled smem (the Q tile's slot) -> TMA store
       const uint32_t row_addr = stage_smem + uint32_t(row_in_tile) * 128u;
       float inv_l = 0.0f;
+      if (n_kv == 0 && p.lse != nullptr && q_start + row_in_tile < p.Tq)
+        p.lse[(int64_t(b) * p.H + head) * p.Tq + q_start + row_in_tile] = INFINITY;  // no keys: P = 0 in the backward pass
       if (n_kv > 0) {
         float a0, a1, b0, b1;
         unpack2(lsumA, a0, a1);
         unpack2(lsumB, b0, b1);
-        inv_l = 1.0f / ((a0 + a1) + (b0 + b1));
+        const float l_row = (a0 + a1) + (b0 + b1);
+        inv_l = 1.0f / l_row;
+        if (p.lse != nullptr && q_start + row_in_tile < p.Tq)
+          p.lse[(int64_t(b) * p.H + head) * p.Tq + q_start + row_in_tile] = m + log2f(l_row);
         mbar_wait(pv_done(q, 0), uint32_t(n_kv - 1) & 1u);
         mbar_wait(pv_done(q, 1), uint32_t(n_kv - 1) & 1u);
         tc_fence_after();
@@ -718,7 +724,7 @@ int launch_fmha(const FmhaArgs& a, cudaStream_t stream) {
   if ((rc = make_tmap_3d(&tmV, bf, a.v, cols, a.Tk, a.B, a.ldv * 2, a.bsv * 2, HD, KT))) return rc;
   if ((rc = make_tmap_3d(&tmO, bf, a.o, cols, a.Tq, a.B, a.ldo * 2, a.bso * 2, HD, QT))) return rc;
 
-  FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride};
+  FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride, a.lse};
   // One build of the kernel ships (NQ = 1: two independent CTAs per SM; one exp2 pair in four on the FMA pipe).
   // The alternatives that were built, verified and measured — NQ = 2, 0 or 2 emulated pairs, a 64-key-tile
   // three-CTA variant and a two-warpgroup ping-pong kernel — live under tools/experiments/ with their numbers.

@@ -1,0 +1,547 @@
+// Attention backward for sm_100a (training step): head dim 64, bf16 operands, fp32 accumulation in
+// TMEM, key-padding mask from kv_lens — the autograd of the forward in fmha.cu, i.e. of nn.MultiheadAttention inside
+// nn.TransformerEncoderLayer (reference models/MMCTransformer.py:41-55, 132-138; main.py:326-333 loss.backward()).
+//
+// With S2 = Q' K^T (Q' = q log2(e)/8 as the forward stores it), P = 2^(S2 - lse2) and Dsum = rowsum(dO o O):
+//     dSt = P o (dO V^T - Dsum)            gradient w.r.t. the true logits q.k/8
+//     dV  = P^T dO        dK = ln2 dSt^T Q'  (= dSt^T q / 8)        dQ = dSt K / 8   (w.r.t. the UNSCALED q)
+// P is recomputed from the log-sum-exp the forward wrote (FmhaArgs::lse); nothing of size T x T is stored.
+//
+// Two kernels, both deterministic (no atomics):
+//   fmha_bwd_dq_kernel    one CTA per (batch, head, 128 queries), two CTAs per SM, walks the key tiles (64 keys):
+//                         S = Q K_j^T and dP = dO V_j^T (SS MMAs) -> softmax warps (thread <-> query row) -> dSt as bf16
+//                         A operand in TMEM -> dQ += dSt K_j (K_j as MN-major B operand, like V in the forward)
+//   fmha_bwd_dkdv_kernel  one CTA per (batch, head, 128 keys), walks the query tiles (64 queries):
+//                         S^T = K Q_i^T and dP^T = V dO_i^T (double-buffered in TMEM) -> softmax warps (thread <-> key
+//                         row; lse / Dsum of the tile's 64 queries staged in shared memory) -> P^T, dSt^T as bf16 A
+//                         operands in TMEM -> dV += P^T dO_i, dK += dSt^T Q_i (Q_i / dO_i as MN-major B operands)
+// S and dP are computed twice (once per kernel): 7 MMAs per tile pair instead of 5, in exchange for no atomics on dQ.
+// Roles per CTA (192 threads): warps 0-3 softmax (TMEM lane quarter = warp), warp 4 TMA producer, warp 5 MMA issuer.
+#include <math.h>
+#include <stdlib.h>
+
+#include "ptx.cuh"
+#include "host_util.h"
+#include "kernels.h"
+
+namespace rp {
+
+namespace {
+
+constexpr int HD = 64;
+constexpr float LN2 = 0.6931471805599453f;
+
+struct BwdParams {
+  int B, H, T;
+  const int32_t* kv_lens;
+  const float* lse;    // [B, H, T] log2-domain log-sum-exp from the forward
+  const float* dsum;   // [B, H, T] rowsum(dO o O)
+};
+
+// bf16 rows of 128 bytes -> swizzled (SWIZZLE_128B) staging tile for a TMA store: row r, 16-byte chunk c
+__device__ __forceinline__ uint32_t swz(uint32_t tile, int r, int c) {
+  return tile + uint32_t(r) * 128u + (uint32_t(c ^ (r & 7)) << 4);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// 64 fp32 accumulator columns of this thread's TMEM lane -> bf16 -> one swizzled 128-byte row
+__device__ __forceinline__ void store_acc_row(uint32_t taddr, uint32_t tile, int row) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t o[32];
+    tmem_ld32(taddr + 32 * half, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      st_shared_v4(swz(tile, row, 4 * half + i),
+                   pack_bf16x2(__uint_as_float(o[8 * i + 0]), __uint_as_float(o[8 * i + 1])),
+                   pack_bf16x2(__uint_as_float(o[8 * i + 2]), __uint_as_float(o[8 * i + 3])),
+                   pack_bf16x2(__uint_as_float(o[8 * i + 4]), __uint_as_float(o[8 * i + 5])),
+                   pack_bf16x2(__uint_as_float(o[8 * i + 6]), __uint_as_float(o[8 * i + 7])));
+  }
+}
+
+// ============================================================================================================
+// dQ
+// ============================================================================================================
+namespace dq {
+constexpr int QT = 128, KT = 64, STAGES = 3;
+constexpr int Q_BYTES = QT * HD * 2, KV_BYTES = KT * HD * 2;
+constexpr int SMEM_Q = 0, SMEM_DO = Q_BYTES, SMEM_K = 2 * Q_BYTES, SMEM_V = SMEM_K + STAGES * KV_BYTES;
+constexpr int SMEM_BAR = SMEM_V + STAGES * KV_BYTES;
+constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;
+constexpr int TM_S = 0, TM_DP = 64, TM_DS = 128, TM_DQ = 160, TMEM_COLS = 256;
+}  // namespace dq
+
+__global__ void __launch_bounds__(192, 2)
+fmha_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                   const __grid_constant__ CUtensorMap tmdQ, const BwdParams p) {
+  using namespace dq;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t bar = base + SMEM_BAR;
+  const uint32_t qdo_full = bar, sdp_full = bar + 56, sdp_free = bar + 64, ds_ready = bar + 72, dq_done = bar + 80;
+  auto kv_full = [&](int s) { return bar + 8u + 8u * s; };
+  auto kv_empty = [&](int s) { return bar + 32u + 8u * s; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 96);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqb = (p.T + QT - 1) / QT;
+  const int qb = int(blockIdx.x) % nqb, bh = int(blockIdx.x) / nqb;
+  const int head = bh % p.H, b = bh / p.H;
+  const int q_start = qb * QT;
+  int kv_len = p.kv_lens != nullptr ? p.kv_lens[b] : p.T;
+  kv_len = kv_len < 0 ? 0 : (kv_len > p.T ? p.T : kv_len);
+  const int n_kv = (kv_len + KT - 1) / KT;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmdQ);
+    mbar_init(qdo_full, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_free, 4);
+    mbar_init(ds_ready, 4);
+    mbar_init(dq_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc<TMEM_COLS>(base + SMEM_BAR + 96);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+  const int col = head * HD;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (n_kv > 0) {
+      if (elect_one()) {
+        mbar_expect_tx(qdo_full, 2 * Q_BYTES);
+        tma_load_3d(base + SMEM_Q, &tmQ, qdo_full, col, q_start, b);
+        tma_load_3d(base + SMEM_DO, &tmdO, qdo_full, col, q_start, b);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % STAGES;
+        mbar_wait(kv_empty(st), (uint32_t(j / STAGES) & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(kv_full(st), 2 * KV_BYTES);
+          tma_load_3d(base + SMEM_K + st * KV_BYTES, &tmK, kv_full(st), col, j * KT, b);
+          tma_load_3d(base + SMEM_V + st * KV_BYTES, &tmV, kv_full(st), col, j * KT, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (n_kv > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(QT, KT, false, false);
+      constexpr uint32_t idesc_q = make_idesc_bf16(QT, HD, false, true);  // K_j as MN-major B
+      auto issue_dq = [&](int jj) {
+        const int st = jj % STAGES;
+        mbar_wait(ds_ready, uint32_t(jj) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t db = make_smem_desc_sw128(base + SMEM_K + st * KV_BYTES, 1024, 1024);
+#pragma unroll
+          for (int k = 0; k < KT / 16; ++k)
+            mma_ts(tmem + TM_DQ, tmem + TM_DS + 8 * k, db + uint64_t(128 * k), idesc_q, (jj > 0 || k > 0) ? 1u : 0u);
+          tc_commit(dq_done);
+          tc_commit(kv_empty(st));
+        }
+        __syncwarp();
+      };
+      mbar_wait(qdo_full, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j % STAGES;
+        mbar_wait(kv_full(st), uint32_t(j / STAGES) & 1u);
+        if (j > 0) mbar_wait(sdp_free, uint32_t(j - 1) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t dq_ = make_smem_desc_sw128(base + SMEM_Q, 1024, 16);
+          const uint64_t ddo = make_smem_desc_sw128(base + SMEM_DO, 1024, 16);
+          const uint64_t dk = make_smem_desc_sw128(base + SMEM_K + st * KV_BYTES, 1024, 16);
+          const uint64_t dv = make_smem_desc_sw128(base + SMEM_V + st * KV_BYTES, 1024, 16);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            mma_ss(tmem + TM_S, dq_ + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            mma_ss(tmem + TM_DP, ddo + uint64_t(2 * k), dv + uint64_t(2 * k), idesc_s, k > 0 ? 1u : 0u);
+          tc_commit(sdp_full);
+        }
+        __syncwarp();
+        if (j > 0) issue_dq(j - 1);
+      }
+      issue_dq(n_kv - 1);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps: thread <-> query row
+    const int row = warp * 32 + lane;
+    const int qrow = q_start + row;
+    const bool valid = qrow < p.T;
+    const int64_t stat = (int64_t(b) * p.H + head) * p.T + qrow;
+    const float lse_r = valid ? p.lse[stat] : INFINITY;
+    const float dsum_r = valid ? p.dsum[stat] : 0.0f;
+    const uint32_t t_lane = tmem + (uint32_t(warp * 32) << 16);
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(sdp_full, uint32_t(j) & 1u);
+      tc_fence_after();
+      const int nv = kv_len - j * KT;  // valid keys in this tile (>= KT: all)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t s[32], dp[32], pk[16];
+        tmem_ld32(t_lane + TM_S + 32 * half, s);
+        tmem_ld32(t_lane + TM_DP + 32 * half, dp);
+        tmem_ld_wait();
+        if (half == 1) {  // S and dP of this tile are in registers: the next tile's MMAs may overwrite them
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sdp_free);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float d2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 32 * half + 2 * i + e;
+            const float pr = c < nv ? ex2_approx(__uint_as_float(s[2 * i + e]) - lse_r) : 0.0f;
+            d2[e] = pr * (__uint_as_float(dp[2 * i + e]) - dsum_r) * 0.125f;
+          }
+          pk[i] = pack_bf16x2(d2[0], d2[1]);
+        }
+        if (half == 0 && j > 0) {  // dQ += dSt_{j-1} K_{j-1} must have read the previous dSt
+          mbar_wait(dq_done, uint32_t(j - 1) & 1u);
+          tc_fence_after();
+        }
+        tmem_st16(t_lane + TM_DS + 16 * half, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_ready);
+    }
+    // ---- epilogue: dQ -> bf16 -> swizzled smem (the Q tile's slot) -> TMA store
+    const uint32_t tile = base + SMEM_Q;
+    if (n_kv > 0) {
+      mbar_wait(dq_done, uint32_t(n_kv - 1) & 1u);
+      tc_fence_after();
+      store_acc_row(t_lane + TM_DQ, tile, row);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) st_shared_v4(swz(tile, row, c), 0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (threadIdx.x == 0) {
+      tma_store_3d(&tmdQ, tile, col, q_start, b);
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem);
+  }
+}
+
+// ============================================================================================================
+// dK, dV
+// ============================================================================================================
+namespace dkv {
+constexpr int KT = 128, QT = 64, STAGES = 3;
+constexpr int KV_BYTES = KT * HD * 2, Q_BYTES = QT * HD * 2;
+constexpr int SMEM_K = 0, SMEM_V = KV_BYTES, SMEM_RING = 2 * KV_BYTES;  // stage s: Q_i at +2 s Q_BYTES, dO_i after it
+constexpr int SMEM_STAT = SMEM_RING + STAGES * 2 * Q_BYTES;             // [2 buffers][lse 64 | dsum 64] floats
+constexpr int SMEM_BAR = SMEM_STAT + 2 * 128 * 4;
+constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;
+constexpr int TM_ST = 0, TM_DPT = 128, TM_PT = 256, TM_DST = 288, TM_DV = 320, TM_DK = 384, TMEM_COLS = 512;
+}  // namespace dkv
+
+__global__ void __launch_bounds__(192, 1)
+fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                     const __grid_constant__ CUtensorMap tmdK, const __grid_constant__ CUtensorMap tmdV,
+                     const BwdParams p) {
+  using namespace dkv;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t bar = base + SMEM_BAR;
+  const uint32_t kv_full = bar, p_ready = bar + 88, p_free = bar + 96;
+  auto q_full = [&](int s) { return bar + 8u + 8u * s; };
+  auto q_empty = [&](int s) { return bar + 32u + 8u * s; };
+  auto st_full = [&](int f) { return bar + 56u + 8u * f; };
+  auto st_free = [&](int f) { return bar + 72u + 8u * f; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 112);
+  float* stat = reinterpret_cast<float*>(smem + SMEM_STAT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (p.T + KT - 1) / KT;
+  const int kb = int(blockIdx.x) % nkb, bh = int(blockIdx.x) / nkb;
+  const int head = bh % p.H, b = bh / p.H;
+  const int k_start = kb * KT;
+  const int col = head * HD;
+  int kv_len = p.kv_lens != nullptr ? p.kv_lens[b] : p.T;
+  kv_len = kv_len < 0 ? 0 : (kv_len > p.T ? p.T : kv_len);
+  const int n_q = (p.T + QT - 1) / QT;
+
+  if (k_start >= kv_len) {
+    // every key of this tile is padding: its K / V rows receive no gradient
+    pdl_wait();
+    for (int i = threadIdx.x; i < KV_BYTES / 16; i += blockDim.x) st_shared_v4(base + SMEM_K + 16 * i, 0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tma_store_3d(&tmdK, base + SMEM_K, col, k_start, b);
+      tma_store_3d(&tmdV, base + SMEM_K, col, k_start, b);
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+    return;
+  }
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmdK);
+    tma_prefetch_desc(&tmdV);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 1);
+    }
+    for (int f = 0; f < 2; ++f) {
+      mbar_init(st_full(f), 1);
+      mbar_init(st_free(f), 4);
+    }
+    mbar_init(p_ready, 4);
+    mbar_init(p_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc<TMEM_COLS>(base + SMEM_BAR + 112);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_expect_tx(kv_full, 2 * KV_BYTES);
+      tma_load_3d(base + SMEM_K, &tmK, kv_full, col, k_start, b);
+      tma_load_3d(base + SMEM_V, &tmV, kv_full, col, k_start, b);
+    }
+    __syncwarp();
+    for (int i = 0; i < n_q; ++i) {
+      const int st = i % STAGES;
+      mbar_wait(q_empty(st), (uint32_t(i / STAGES) & 1u) ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(q_full(st), 2 * Q_BYTES);
+        tma_load_3d(base + SMEM_RING + st * 2 * Q_BYTES, &tmQ, q_full(st), col, i * QT, b);
+        tma_load_3d(base + SMEM_RING + st * 2 * Q_BYTES + Q_BYTES, &tmdO, q_full(st), col, i * QT, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_t = make_idesc_bf16(KT, QT, false, false);  // S^T / dP^T: [128 keys, 64 queries]
+    constexpr uint32_t idesc_o = make_idesc_bf16(KT, HD, false, true);   // dV / dK: B = dO_i / Q_i, MN-major
+    auto issue_dkdv = [&](int ii) {
+      const int st = ii % STAGES;
+      mbar_wait(p_ready, uint32_t(ii) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dq_mn = make_smem_desc_sw128(base + SMEM_RING + st * 2 * Q_BYTES, 1024, 1024);
+        const uint64_t ddo_mn = make_smem_desc_sw128(base + SMEM_RING + st * 2 * Q_BYTES + Q_BYTES, 1024, 1024);
+#pragma unroll
+        for (int k = 0; k < QT / 16; ++k)
+          mma_ts(tmem + TM_DV, tmem + TM_PT + 8 * k, ddo_mn + uint64_t(128 * k), idesc_o, (ii > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < QT / 16; ++k)
+          mma_ts(tmem + TM_DK, tmem + TM_DST + 8 * k, dq_mn + uint64_t(128 * k), idesc_o, (ii > 0 || k > 0) ? 1u : 0u);
+        tc_commit(p_free);
+        tc_commit(q_empty(st));
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    for (int i = 0; i < n_q; ++i) {
+      const int st = i % STAGES, bf = i & 1;
+      mbar_wait(q_full(st), uint32_t(i / STAGES) & 1u);
+      if (i >= 2) mbar_wait(st_free(bf), (uint32_t(i >> 1) + 1u) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dk = make_smem_desc_sw128(base + SMEM_K, 1024, 16);
+        const uint64_t dv = make_smem_desc_sw128(base + SMEM_V, 1024, 16);
+        const uint64_t dq_ = make_smem_desc_sw128(base + SMEM_RING + st * 2 * Q_BYTES, 1024, 16);
+        const uint64_t ddo = make_smem_desc_sw128(base + SMEM_RING + st * 2 * Q_BYTES + Q_BYTES, 1024, 16);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          mma_ss(tmem + TM_ST + 64 * bf, dk + uint64_t(2 * k), dq_ + uint64_t(2 * k), idesc_t, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          mma_ss(tmem + TM_DPT + 64 * bf, dv + uint64_t(2 * k), ddo + uint64_t(2 * k), idesc_t, k > 0 ? 1u : 0u);
+        tc_commit(st_full(bf));
+      }
+      __syncwarp();
+      if (i > 0) issue_dkdv(i - 1);
+    }
+    issue_dkdv(n_q - 1);
+  } else {
+    // ------------------------------------------------------------------ softmax warps: thread <-> key row
+    const int row = warp * 32 + lane;
+    const bool kvalid = k_start + row < kv_len;
+    const uint32_t t_lane = tmem + (uint32_t(warp * 32) << 16);
+    const int tid = threadIdx.x;  // 0..127
+    const int64_t stat_base = (int64_t(b) * p.H + head) * p.T;
+    // lse (threads 0-63) / Dsum (threads 64-127) of the tile's queries, fetched one tile ahead
+    auto fetch_stat = [&](int i) {
+      const int qi = i * QT + (tid & 63);
+      if (tid < 64) return qi < p.T ? p.lse[stat_base + qi] : INFINITY;
+      return qi < p.T ? p.dsum[stat_base + qi] : 0.0f;
+    };
+    stat[tid] = fetch_stat(0);
+    for (int i = 0; i < n_q; ++i) {
+      const int bf = i & 1;
+      const float nxt = i + 1 < n_q ? fetch_stat(i + 1) : 0.0f;
+      named_bar_sync(1, 128);  // buffer bf is complete (written at the end of the previous iteration)
+      const float4* lse4 = reinterpret_cast<const float4*>(stat + 128 * bf);
+      const float4* ds4 = reinterpret_cast<const float4*>(stat + 128 * bf + 64);
+      mbar_wait(st_full(bf), uint32_t(i >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t s[32], dp[32], pp[16], pd[16];
+        tmem_ld32(t_lane + TM_ST + 64 * bf + 32 * half, s);
+        tmem_ld32(t_lane + TM_DPT + 64 * bf + 32 * half, dp);
+        tmem_ld_wait();
+        if (half == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(st_free(bf));
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 l4 = lse4[8 * half + g];
+          const float4 d4 = ds4[8 * half + g];
+          const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq_[4] = {d4.x, d4.y, d4.z, d4.w};
+          float pr[4], dsv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            pr[e] = kvalid ? ex2_approx(__uint_as_float(s[4 * g + e]) - lq[e]) : 0.0f;
+            dsv[e] = pr[e] * (__uint_as_float(dp[4 * g + e]) - dq_[e]) * LN2;
+          }
+          pp[2 * g] = pack_bf16x2(pr[0], pr[1]);
+          pp[2 * g + 1] = pack_bf16x2(pr[2], pr[3]);
+          pd[2 * g] = pack_bf16x2(dsv[0], dsv[1]);
+          pd[2 * g + 1] = pack_bf16x2(dsv[2], dsv[3]);
+        }
+        if (half == 0 && i > 0) {  // dV / dK MMAs of the previous tile must have read P^T / dSt^T
+          mbar_wait(p_free, uint32_t(i - 1) & 1u);
+          tc_fence_after();
+        }
+        tmem_st16(t_lane + TM_PT + 16 * half, pp);
+        tmem_st16(t_lane + TM_DST + 16 * half, pd);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      stat[128 * (bf ^ 1) + tid] = nxt;
+    }
+    // ---- epilogue: dV, dK -> bf16 -> swizzled smem (the K / V tiles' slots) -> TMA stores
+    mbar_wait(p_free, uint32_t(n_q - 1) & 1u);
+    tc_fence_after();
+    store_acc_row(t_lane + TM_DV, base + SMEM_K, row);
+    store_acc_row(t_lane + TM_DK, base + SMEM_V, row);
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (threadIdx.x == 0) {
+      tma_store_3d(&tmdV, base + SMEM_K, col, k_start, b);
+      tma_store_3d(&tmdK, base + SMEM_V, col, k_start, b);
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem);
+  }
+}
+
+}  // namespace
+
+int launch_attn_bwd_dsum(const void* o, const void* d_o, int B, int T, int H, float* dsum, cudaStream_t stream);
+
+int launch_fmha_bwd(const FmhaBwdArgs& a, cudaStream_t stream) {
+  RP_CHECK(a.B > 0 && a.H > 0 && a.T > 0, "fmha_bwd: empty problem");
+  RP_CHECK(a.q && a.k && a.v && a.o && a.d_o && a.lse && a.dsum && a.dq && a.dk && a.dv, "fmha_bwd: null argument");
+  RP_CHECK(a.ld_qkv % 8 == 0 && a.ld_o % 8 == 0 && a.ld_dqkv % 8 == 0, "fmha_bwd: pitches must be multiples of 8 elements");
+  RP_CHECK(a.H % 8 == 0 && a.ld_o == int64_t(a.H) * HD, "fmha_bwd: o / dO must be dense [B, T, H*64] with H %% 8 == 0");
+  const uint64_t cols = uint64_t(a.H) * HD;
+  const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  int rc;
+  if ((rc = launch_attn_bwd_dsum(a.o, a.d_o, a.B, a.T, a.H, a.dsum, stream))) return rc;
+  BwdParams p{a.B, a.H, a.T, a.kv_lens, a.lse, a.dsum};
+  const uint64_t T = a.T, B = a.B;
+  {
+    CUtensorMap tmQ, tmK, tmV, tmdO, tmdQ;
+    if ((rc = make_tmap_3d(&tmQ, bf, a.q, cols, T, B, a.ld_qkv * 2, T * a.ld_qkv * 2, HD, dq::QT))) return rc;
+    if ((rc = make_tmap_3d(&tmK, bf, a.k, cols, T, B, a.ld_qkv * 2, T * a.ld_qkv * 2, HD, dq::KT))) return rc;
+    if ((rc = make_tmap_3d(&tmV, bf, a.v, cols, T, B, a.ld_qkv * 2, T * a.ld_qkv * 2, HD, dq::KT))) return rc;
+    if ((rc = make_tmap_3d(&tmdO, bf, a.d_o, cols, T, B, a.ld_o * 2, T * a.ld_o * 2, HD, dq::QT))) return rc;
+    if ((rc = make_tmap_3d(&tmdQ, bf, a.dq, cols, T, B, a.ld_dqkv * 2, T * a.ld_dqkv * 2, HD, dq::QT))) return rc;
+    static bool configured_on[kMaxDevices];
+    bool& configured = configured_on[current_device()];
+    if (!configured) {
+      RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dq::SMEM_TOTAL));
+      configured = true;
+    }
+    const unsigned grid = unsigned((a.T + dq::QT - 1) / dq::QT) * unsigned(a.H) * unsigned(a.B);
+    RP_CUDA_CHECK(launch_pdl(fmha_bwd_dq_kernel, dim3(grid), dim3(192), dq::SMEM_TOTAL, stream, tmQ, tmK, tmV, tmdO, tmdQ, p));
+    count_launch();
+  }
+  {
+    CUtensorMap tmQ, tmK, tmV, tmdO, tmdK, tmdV;
+    if ((rc = make_tmap_3d(&tmQ, bf, a.q, cols, T, B, a.ld_qkv * 2, T * a.ld_qkv * 2, HD, dkv::QT))) return rc;
+    if ((rc = make_tmap_3d(&tmK, bf, a.k, cols, T, B, a.ld_qkv * 2, T * a.ld_qkv * 2, HD, dkv::KT))) return rc;
+    if ((rc = make_tmap_3d(&tmV, bf, a.v, cols, T, B, a.ld_qkv * 2, T * a.ld_qkv * 2, HD, dkv::KT))) return rc;
+    if ((rc = make_tmap_3d(&tmdO, bf, a.d_o, cols, T, B, a.ld_o * 2, T * a.ld_o * 2, HD, dkv::QT))) return rc;
+    if ((rc = make_tmap_3d(&tmdK, bf, a.dk, cols, T, B, a.ld_dqkv * 2, T * a.ld_dqkv * 2, HD, dkv::KT))) return rc;
+    if ((rc = make_tmap_3d(&tmdV, bf, a.dv, cols, T, B, a.ld_dqkv * 2, T * a.ld_dqkv * 2, HD, dkv::KT))) return rc;
+    static bool configured_on[kMaxDevices];
+    bool& configured = configured_on[current_device()];
+    if (!configured) {
+      RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dkv::SMEM_TOTAL));
+      configured = true;
+    }
+    const unsigned grid = unsigned((a.T + dkv::KT - 1) / dkv::KT) * unsigned(a.H) * unsigned(a.B);
+    RP_CUDA_CHECK(launch_pdl(fmha_bwd_dkdv_kernel, dim3(grid), dim3(192), dkv::SMEM_TOTAL, stream, tmQ, tmK, tmV, tmdO, tmdK,
+                             tmdV, p));
+    count_launch();
+  }
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+}  // namespace rp

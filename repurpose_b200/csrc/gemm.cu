@@ -40,21 +40,20 @@ constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int SLAB_BYTES = 32 * 128;   // 32 rows x 128 B: one TMA box of the output / residual
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int MAX_SLABS = 5;
-#ifndef RP_RESID_SLABS
-#define RP_RESID_SLABS 4
-#endif
+constexpr int MAX_SLABS = 8;  // barriers reserved per epilogue warp
 
 // Shared-memory budget per (epilogue kind, CTA-group size): the residual epilogue trades operand
 // stages for a deeper slab ring (loads and stores both live there).
-template <int EPI, int CG>
+// RS = slabs per epilogue warp of the residual epilogues (4, 6 or 8): RS - 2 residual chunks of 4 KB are in
+// flight per warp.  A memory-bound problem (K = 512: out-proj) wants the deeper ring more than operand stages.
+template <int EPI, int CG, int RS = 4>
 struct Cfg {
   static constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_LN);
   static constexpr bool LNF = (EPI == EPI_BIAS_RESID_LN);   // LayerNorm of the updated rows fused in (cluster of 4)
   static constexpr int B_ROWS = BN / CG;               // rows of W staged by each CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;      // 32 KB (CG=1) / 16 KB (CG=2)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SLABS = RESID ? RP_RESID_SLABS : 2;          // per epilogue warp
+  static constexpr int SLABS = RESID ? RS : 2;          // per epilogue warp
   static constexpr int LOOKAHEAD = SLABS - 2;          // residual chunks in flight per warp
   static constexpr int STAGES = (229376 - 4 * SLABS * SLAB_BYTES) / STAGE_BYTES;  // CG1: 4/3, CG2: 6/5
   static constexpr int SMEM_A_OFF = 0;
@@ -72,18 +71,29 @@ struct GemmArgs {
   int M, N, K;
   const float* bias;
   GemmLnFusion ln;
+  int splits = 1;        // split-K: split s reduces k-blocks [s * kb_per_split, ...) and writes rows [s*M, (s+1)*M) of D
+  int kb_per_split = 0;  // (0 = all)
 };
 
-template <int EPI, int CG>
+// TR selects the operand layouts (the backward GEMMs of the training step):
+//   0  A [M,K] and W [N,K] both K-major (forward: y = x W^T)
+//   1  A K-major, B MN-major: B is stored [K,N] (dgrad: dX[M,Kin] = dY[M,Nout] W[Nout,Kin], W as nn.Linear keeps it)
+//   3  A and B MN-major: A stored [K,M], B stored [K,N] (wgrad: dW[Nout,Kin] = dY[tok,Nout]^T X[tok,Kin], reduction
+//      over the tokens; rows beyond K are zero-filled by TMA)
+// An MN-major operand tile is staged as 64-column blocks of BK rows x 128 B (one TMA box each); the UMMA descriptor
+// walks them with LBO = BK * 128 (stride between 64-wide MN blocks) and SBO = 1024 (8 K indices).
+template <int EPI, int CG, int RS, int TR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                  const __grid_constant__ CUtensorMap tmU, const GemmArgs g) {
-  using C = Cfg<EPI, CG>;
+  using C = Cfg<EPI, CG, RS>;
   constexpr int STAGES = C::STAGES;
   constexpr int SLABS = C::SLABS;
   constexpr bool OUT_F32 = (EPI == EPI_BIAS_F32 || C::RESID);
   constexpr bool LNF = C::LNF;
+  constexpr bool A_MN = (TR & 2) != 0, B_MN = (TR & 1) != 0;
+  static_assert(TR == 0 || (CG == 2 && !C::RESID), "transposed operands: CTA pairs, plain epilogues");
   constexpr int CPC = OUT_F32 ? 32 : 64;  // output columns per 128-byte slab row
   constexpr int CHUNKS = BN / CPC;        // slab-sized chunks per tile and warp
 
@@ -94,14 +104,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (LNF && base - raw_addr > 512u) __trap();  // the LNF budget only leaves 512 bytes of alignment slack
 
   // barrier map (bytes from bar_base): full[8] @0, empty[8] @64, tfull[2] @128, tempty[2] @144,
-  // tmem slot @160, resid[4][5] @192
+  // tmem slot @160, resid[4][8] @192, stats[2] @448
   const uint32_t bar_base = base + C::SMEM_BAR_OFF;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
   auto tfull_bar = [&](int b) { return bar_base + 128u + 8u * b; };
   auto tempty_bar = [&](int b) { return bar_base + 144u + 8u * b; };
   auto resid_bar = [&](int ew, int s) { return bar_base + 192u + 8u * (ew * MAX_SLABS + s); };
-  auto stats_bar = [&](int b) { return bar_base + 352u + 8u * b; };  // LNF: partner pair's row statistics have landed
+  auto stats_bar = [&](int b) { return bar_base + 448u + 8u * b; };  // LNF: partner pair's row statistics have landed
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::SMEM_BAR_OFF + 160);
 
   const int warp = threadIdx.x >> 5;
@@ -113,9 +123,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_groups = gridDim.x / CG;
 
   const int m_tiles = (g.M + BM * CG - 1) / (BM * CG);
-  const int n_tiles = g.N / BN;
-  const int total_tiles = m_tiles * n_tiles;
-  const int k_blocks = g.K / BK;
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int tiles_per_split = m_tiles * n_tiles;
+  const int total_tiles = tiles_per_split * g.splits;
+  const int k_blocks = (g.K + BK - 1) / BK;
+  const int kbps = g.kb_per_split > 0 ? g.kb_per_split : k_blocks;
+  // tile index -> (split, m block, n block, k-block range)
+  auto decode = [&](int tile, int& sp, int& m_blk, int& n_blk, int& kb0, int& kb1) {
+    sp = tile / tiles_per_split;
+    const int t2 = tile - sp * tiles_per_split;
+    m_blk = t2 / n_tiles;
+    n_blk = t2 - m_blk * n_tiles;
+    kb0 = sp * kbps;
+    kb1 = kb0 + kbps < k_blocks ? kb0 + kbps : k_blocks;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -151,11 +172,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = group; tile < total_tiles; tile += num_groups) {
-      const int m_blk = tile / n_tiles;
-      const int n_blk = tile - m_blk * n_tiles;
+      int sp, m_blk, n_blk, kb0, kb1;
+      decode(tile, sp, m_blk, n_blk, kb0, kb1);
       const int a_row = (m_blk * CG + cta_rank) * BM;
       const int b_row = n_blk * BN + cta_rank * C::B_ROWS;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         if (elect_one()) {
           const uint32_t sa = base + C::SMEM_A_OFF + stage * A_BYTES;
@@ -163,8 +184,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if constexpr (CG == 2) {
             // both CTAs' bytes are credited to the leader's barrier, which the leader arms
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-            tma_load_2d_cg2(sa, &tmA, full_bar(stage), kb * BK, a_row);
-            tma_load_2d_cg2(sb, &tmB, full_bar(stage), kb * BK, b_row);
+            if constexpr (A_MN) {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d_cg2(sa + j * (BK * 128), &tmA, full_bar(stage), a_row + 64 * j, kb * BK);
+            } else {
+              tma_load_2d_cg2(sa, &tmA, full_bar(stage), kb * BK, a_row);
+            }
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int j = 0; j < C::B_ROWS / 64; ++j)
+                tma_load_2d_cg2(sb + j * (BK * 128), &tmB, full_bar(stage), b_row + 64 * j, kb * BK);
+            } else {
+              tma_load_2d_cg2(sb, &tmB, full_bar(stage), kb * BK, b_row);
+            }
           } else {
             mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
             tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, a_row);
@@ -180,35 +213,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // Converged control flow keeps the descriptors in uniform registers; a divergent
     // single-thread loop costs ~100 cycles per tcgen05.mma issue.
     if (cta_rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, false, false);
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, A_MN, B_MN);
+      constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, B_LBO = B_MN ? BK * 128 : 16;
+      constexpr uint64_t A_KSTEP = A_MN ? 128 : 2, B_KSTEP = B_MN ? 128 : 2;  // 16 K indices, in 16-byte units
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int tile = group; tile < total_tiles; tile += num_groups, ++it) {
+        int sp, m_blk, n_blk, kb0, kb1;
+        decode(tile, sp, m_blk, n_blk, kb0, kb1);
         const int buf = it & 1;
         const uint32_t use_parity = (uint32_t(it) >> 1) & 1u;
         mbar_wait(tempty_bar(buf), use_parity ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(buf * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t da = make_smem_desc_sw128(base + C::SMEM_A_OFF + stage * A_BYTES, 1024, 16);
-            const uint64_t db = make_smem_desc_sw128(base + C::SMEM_B_OFF + stage * C::B_BYTES, 1024, 16);
+            const uint64_t da = make_smem_desc_sw128(base + C::SMEM_A_OFF + stage * A_BYTES, 1024, A_LBO);
+            const uint64_t db = make_smem_desc_sw128(base + C::SMEM_B_OFF + stage * C::B_BYTES, 1024, B_LBO);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {  // +32 bytes along K per step = +2 in the address field
+            for (int k = 0; k < BK / 16; ++k) {  // K-major: +32 bytes along K per step; MN-major: +16 rows of 128 B
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
               if constexpr (CG == 2)
-                mma_ss_cg2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                mma_ss_cg2(d_tmem, da + A_KSTEP * uint64_t(k), db + B_KSTEP * uint64_t(k), idesc, acc);
               else
-                mma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                mma_ss(d_tmem, da + A_KSTEP * uint64_t(k), db + B_KSTEP * uint64_t(k), idesc, acc);
             }
             if constexpr (CG == 2) {
               tc_commit_cg2(empty_bar(stage), pair_mask);  // frees the slot in BOTH CTAs once these MMAs retire
-              if (kb == k_blocks - 1) tc_commit_cg2(tfull_bar(buf), pair_mask);
+              if (kb == kb1 - 1) tc_commit_cg2(tfull_bar(buf), pair_mask);
             } else {
               tc_commit(empty_bar(stage));
-              if (kb == k_blocks - 1) tc_commit(tfull_bar(buf));
+              if (kb == kb1 - 1) tc_commit(tfull_bar(buf));
             }
           }
           __syncwarp();
@@ -224,7 +262,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int my_tiles = group < total_tiles ? (total_tiles - group + num_groups - 1) / num_groups : 0;
     // Slab uses per tile: CHUNKS residual/output chunks, then (LNF) 4 chunks of normalised bf16 rows.
     constexpr int UPT = CHUNKS + (LNF ? BN / 64 : 0);
-    static_assert(!LNF || (SLABS == 4 && UPT % SLABS == 0 && CHUNKS == 8), "LNF slab ring bookkeeping");
+    static_assert(!LNF || CHUNKS == 8, "LNF: 8 fp32 chunks of 32 columns per 256-column tile");
     const int total_chunks = my_tiles * UPT;
     auto tile_row0 = [&](int m_blk) { return (m_blk * CG + cta_rank) * BM + q * 32; };
 
@@ -233,27 +271,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int c = gc % UPT;
       if (c >= CHUNKS) return;  // a LayerNorm output chunk: nothing to load
       const int tile = group + (gc / UPT) * num_groups;
-      const int m_blk = tile / n_tiles;
+      const int m_blk = tile / n_tiles;  // (residual epilogues never run split-K)
       const int n_blk = tile - m_blk * n_tiles;
       const int s = gc % SLABS;
       mbar_expect_tx(resid_bar(ew, s), SLAB_BYTES);
       tma_load_2d(slab0 + s * SLAB_BYTES, &tmR, resid_bar(ew, s), n_blk * BN + c * CPC, tile_row0(m_blk));
     };
     if constexpr (C::RESID) {
+      // (an L2 prefetch of the next tiles' residual rows was tried and measured slower: out-proj 61 -> 71 us, +35 %
+      // DRAM reads — profiles/r02_notes.md)
       if (lane == 0)
         for (int gc = 0; gc < C::LOOKAHEAD && gc < total_chunks; ++gc) issue_resid_load(gc);
     }
 
     int it = 0;
     int gc = 0;  // chunks processed so far by this warp
+    uint32_t resid_phase = 0;  // bit s = parity of the next residual load to complete in slab s
     for (int tile = group; tile < total_tiles; tile += num_groups, ++it) {
-      const int m_blk = tile / n_tiles;
-      const int n_blk = tile - m_blk * n_tiles;
+      int sp, m_blk, n_blk, kb0, kb1;
+      decode(tile, sp, m_blk, n_blk, kb0, kb1);
       const int buf = it & 1;
       const uint32_t use_parity = (uint32_t(it) >> 1) & 1u;
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN);
-      const int row0 = tile_row0(m_blk);
-      const int row = row0 + lane;
+      const int row0 = tile_row0(m_blk) + sp * g.M;  // split-K partials are stacked along the rows of D
       // LNF: row statistics of the updated h over this tile's 256 columns, accumulated about a shift (the row's
       // first value) so that a large common offset of the residual stream does not cancel in E[x^2] - mean^2
       float st_sum = 0.f, st_sq = 0.f, st_shift = 0.f;
@@ -281,8 +321,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_store_wait_read<1>();
             issue_resid_load(gc + C::LOOKAHEAD);
           }
-          // completed loads into this slab so far: every use (plain) / two of its three uses per tile (LNF)
-          mbar_wait(resid_bar(ew, s), LNF ? uint32_t(c / SLABS) & 1u : uint32_t(gc / SLABS) & 1u);
+          mbar_wait(resid_bar(ew, s), (resid_phase >> s) & 1u);
+          resid_phase ^= 1u << s;
         } else {
           // the TMA store that last read this slab (SLABS chunks ago) must have drained it
           if (lane == 0) tma_store_wait_read<SLABS - 1>();
@@ -463,18 +503,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int EPI, int CG>
+template <int EPI, int CG, int RS = 4, int TR = 0>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                const CUtensorMap& tmR, const CUtensorMap& tmU, const GemmArgs& g, int groups,
                cudaStream_t stream) {
-  using C = Cfg<EPI, CG>;
+  using C = Cfg<EPI, CG, RS>;
   constexpr int CLUSTER = C::LNF ? 4 : CG;  // LNF: two CTA pairs per cluster share full 512-column rows
   static bool configured_on[kMaxDevices];
   static int max_clusters_on[kMaxDevices];
   bool& configured = configured_on[current_device()];
   int& max_clusters = max_clusters_on[current_device()];
   if (!configured) {
-    RP_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, CG>,
+    RP_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, CG, RS, TR>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));
     configured = true;
   }
@@ -497,7 +537,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
     // co-resident (33 clusters = 132 SMs on B200).  Pairs 2c / 2c+1 walk tiles (m, 0) / (m, 1) in step.
     if (max_clusters == 0) {
       cfg.gridDim = dim3(unsigned(num_sms() / 4 * 4));
-      RP_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters, gemm_bf16_kernel<EPI, CG>, &cfg));
+      RP_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters, gemm_bf16_kernel<EPI, CG, RS, TR>, &cfg));
       RP_CHECK(max_clusters > 0, "gemm: no cluster of 4 CTAs fits");
     }
     const int m_tiles = (g.M + BM * CG - 1) / (BM * CG);
@@ -505,10 +545,18 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
     cfg.gridDim = dim3(unsigned(clusters * 4));
   }
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  RP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, CG>, tmA, tmB, tmD, tmR, tmU, g));
+  RP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, CG, RS, TR>, tmA, tmB, tmD, tmR, tmU, g));
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;
+}
+
+// Slabs per epilogue warp of the residual epilogues.  RP_RESID_SLABS (4 / 6 / 8) overrides the choice for A/B runs.
+int resid_slabs_for(int K) {
+  static const int env = getenv("RP_RESID_SLABS") ? atoi(getenv("RP_RESID_SLABS")) : 0;
+  if (env == 4 || env == 6 || env == 8) return env;
+  (void)K;
+  return 4;  // measured (profiles/r02_notes.md): 6 / 8 slabs cost operand stages and buy nothing, even at K = 512
 }
 
 template <int CG>
@@ -544,16 +592,72 @@ int launch_cg(int epilogue, const void* A, int64_t lda, const void* W, int64_t l
     case EPI_BIAS_BF16: return launch_one<EPI_BIAS_BF16, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
     case EPI_BIAS_RELU_BF16: return launch_one<EPI_BIAS_RELU_BF16, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
     case EPI_BIAS_F32: return launch_one<EPI_BIAS_F32, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
-    case EPI_BIAS_RESID_F32: return launch_one<EPI_BIAS_RESID_F32, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
+    case EPI_BIAS_RESID_F32:
+      if constexpr (CG == 2) {
+        if (resid_slabs_for(K) >= 6) return launch_one<EPI_BIAS_RESID_F32, 2, 6>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
+      }
+      return launch_one<EPI_BIAS_RESID_F32, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
     case EPI_BIAS_RESID_LN:
-      if constexpr (CG == 2) return launch_one<EPI_BIAS_RESID_LN, 2>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
+      if constexpr (CG == 2) {
+        switch (resid_slabs_for(K)) {
+          case 8: return launch_one<EPI_BIAS_RESID_LN, 2, 8>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
+          case 6: return launch_one<EPI_BIAS_RESID_LN, 2, 6>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
+          default: return launch_one<EPI_BIAS_RESID_LN, 2, 4>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
+        }
+      }
       set_last_error("gemm: the LayerNorm-fused epilogue needs CTA pairs");
       return RP_ERR_INVALID;
     default: set_last_error("gemm: unknown epilogue %d", epilogue); return RP_ERR_INVALID;
   }
 }
 
+// Backward GEMMs (operand layouts TR = 1 / 3, see the kernel): plain fp32 / bf16 epilogues, no bias, CTA pairs,
+// optional split-K whose partial results are stacked along the rows of D ([splits * M, N]).
+int launch_tr(int tr, bool out_f32, const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
+              int M, int N, int K, int splits, cudaStream_t stream) {
+  CUtensorMap tmA, tmB, tmD;
+  int rc;
+  const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  if (tr & 2) rc = make_tmap_2d(&tmA, bf, A, M, K, lda * 2, 64, BK);   // stored [K, M]
+  else rc = make_tmap_2d(&tmA, bf, A, K, M, lda * 2, BK, BM);          // stored [M, K]
+  if (rc) return rc;
+  if ((rc = make_tmap_2d(&tmB, bf, B, N, K, ldb * 2, 64, BK))) return rc;  // stored [K, N]
+  if (out_f32)
+    rc = make_tmap_2d(&tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, D, N, uint64_t(M) * splits, ldd * 4, 32, 32);
+  else
+    rc = make_tmap_2d(&tmD, bf, D, N, uint64_t(M) * splits, ldd * 2, 64, 32);
+  if (rc) return rc;
+  GemmArgs g{M, N, K, nullptr, GemmLnFusion{}};
+  const int k_blocks = (K + BK - 1) / BK;
+  g.splits = splits;
+  g.kb_per_split = (k_blocks + splits - 1) / splits;
+  const int total_tiles = ((M + BM * 2 - 1) / (BM * 2)) * ((N + BN - 1) / BN) * splits;
+  const int sms = num_sms();
+  if (sms <= 0) return RP_ERR_NO_DEVICE;
+  const int groups = total_tiles < sms / 2 ? total_tiles : sms / 2;
+  if (tr == 1) {
+    if (out_f32) return launch_one<EPI_BIAS_F32, 2, 4, 1>(tmA, tmB, tmD, tmD, tmD, g, groups, stream);
+    return launch_one<EPI_BIAS_BF16, 2, 4, 1>(tmA, tmB, tmD, tmD, tmD, g, groups, stream);
+  }
+  if (out_f32) return launch_one<EPI_BIAS_F32, 2, 4, 3>(tmA, tmB, tmD, tmD, tmD, g, groups, stream);
+  return launch_one<EPI_BIAS_BF16, 2, 4, 3>(tmA, tmB, tmD, tmD, tmD, g, groups, stream);
+}
+
 }  // namespace
+
+int launch_gemm_bwd(int kind, bool out_f32, const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
+                    int64_t ldd, int M, int N, int K, int splits, cudaStream_t stream) {
+  RP_CHECK(kind == 1 || kind == 3, "gemm_bwd: kind must be 1 (dgrad) or 3 (wgrad)");
+  RP_CHECK(M > BM && N > 0 && K > 0, "gemm_bwd: needs more than %d output rows (M=%d N=%d K=%d)", BM, M, N, K);
+  RP_CHECK(N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && (ldd * (out_f32 ? 4 : 2)) % 16 == 0,
+           "gemm_bwd: N and the pitches must keep rows 16-byte aligned");
+  RP_CHECK(kind == 3 || K % BK == 0, "gemm_bwd: dgrad needs K %% %d == 0", BK);
+  RP_CHECK(splits >= 1 && splits <= (K + BK - 1) / BK, "gemm_bwd: bad split count %d", splits);
+  RP_CHECK(splits == 1 || M % (2 * BM) == 0, "gemm_bwd: split-K needs M %% %d == 0", 2 * BM);
+  RP_CHECK((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(D)) % 16 == 0,
+           "gemm_bwd: pointers must be 16-byte aligned");
+  return launch_tr(kind, out_f32, A, lda, B, ldb, D, ldd, M, N, K, splits, stream);
+}
 
 int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
                    int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,

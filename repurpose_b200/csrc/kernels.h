@@ -32,6 +32,15 @@ int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int6
                    int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
                    const GemmLnFusion& ln, cudaStream_t stream);
 
+// Backward GEMMs of the training step, bf16 operands, fp32 accumulation, no bias:
+//   kind 1 (dgrad)  D[M,N] = A[M,K] * B[K,N]      A row-major [M,K] (dY), B row-major [K,N] (an nn.Linear weight
+//                                                  [out=K, in=N] as stored) -> dX
+//   kind 3 (wgrad)  D[M,N] = A[K,M]^T * B[K,N]    A row-major [K,M] (dY over K tokens), B row-major [K,N] (X) -> dW;
+//                                                  K need not be a multiple of 64 (TMA zero-fills the tail)
+// out_f32: D fp32, else bf16.  splits > 1: split-K, D must hold [splits * M, N]; partial s in rows [s*M, (s+1)*M).
+int launch_gemm_bwd(int kind, bool out_f32, const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
+                    int64_t ldd, int M, int N, int K, int splits, cudaStream_t stream);
+
 // ---- fused multi-head attention (d_k = 64) -----------------------------------------------------
 // q/k/v: bf16, row pitch ld* elements, batch pitch bs* elements; head h occupies columns
 // [h*64, h*64+64) of each row.  q is expected pre-scaled by log2(e)/sqrt(d_k).
@@ -47,6 +56,7 @@ struct FmhaArgs {
   const int32_t* kv_lens;
   int mask_mode;
   const uint8_t* mask; int64_t mask_b_stride, mask_q_stride;
+  float* lse = nullptr;  // optional output [B, H, Tq] fp32: log2-domain log-sum-exp per score row (training forward)
 };
 int launch_fmha(const FmhaArgs& a, cudaStream_t stream);
 
@@ -125,10 +135,36 @@ int launch_focal_loss_grad(const float* logits, const float* targets, const uint
 // LayerNorm over rows of 512: dx [M,512], dgamma [512], dbeta [512] from x, dy, gamma; scratch: fp32,
 // layernorm512_bwd_scratch_floats() values
 int64_t layernorm512_bwd_scratch_floats();
+// accumulate: dx += (the residual stream's gradient); dx_bf16 (optional): bf16 copy of the final dx
 int launch_layernorm512_bwd(const float* x, const float* dy, const float* gamma, int64_t M, float eps, float* dx,
-                            float* dgamma, float* dbeta, float* scratch, cudaStream_t stream);
+                            float* dgamma, float* dbeta, float* scratch, cudaStream_t stream, bool accumulate = false,
+                            void* dx_bf16 = nullptr);
 // one torch.optim.Adam step (L2 weight decay added to the gradient) on a flat fp32 buffer; p_bf16 (optional): bf16 copy
 int launch_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                      float eps, float weight_decay, int step, void* p_bf16, cudaStream_t stream);
+
+
+// ---- the rest of the training step's backward pass (train.cu, fmha_bwd.cu, gemm.cu) ---------------------------
+// out[i] = sum_s part[s * n + i] in order (split-K partials of launch_gemm_bwd -> gradient)
+int launch_splitk_reduce(const float* part, int splits, int64_t n, float* out, cudaStream_t stream);
+// out[N] = column sums of bf16 x[M, N] (bias gradients); scratch: train_scratch_floats() fp32 values
+int64_t train_scratch_floats();
+int launch_colsum_bf16(const void* x, int64_t M, int N, float* out, float* scratch, cudaStream_t stream);
+// dy = act > 0 ? dy : 0, in place; f32: both fp32, else both bf16; n % 8 == 0
+int launch_relu_bwd(void* dy, const void* act, int64_t n, bool f32, cudaStream_t stream);
+// last cls_head layer: da2[M,256] bf16 = dlogit[m] w[c] where a2 > 0, dw[256], db[1]
+int launch_head_out_bwd(const float* dlogit, const void* a2, const float* w, int64_t M, void* da2, float* dw, float* db,
+                        float* scratch, cudaStream_t stream);
+// attention backward: q/k/v [B,T,ld_qkv] (head h in columns h*64..), o / dO dense [B,T,H*64], lse from the forward,
+// dsum scratch [B,H,T]; writes dq (w.r.t. the unscaled q), dk, dv with row pitch ld_dqkv
+struct FmhaBwdArgs {
+  const void* q; const void* k; const void* v; const void* o; const void* d_o;
+  const float* lse; float* dsum;
+  void* dq; void* dk; void* dv;
+  int64_t ld_qkv, ld_o, ld_dqkv;
+  int B, H, T;
+  const int32_t* kv_lens;
+};
+int launch_fmha_bwd(const FmhaBwdArgs& a, cudaStream_t stream);
 
 }  // namespace rp

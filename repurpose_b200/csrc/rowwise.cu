@@ -137,12 +137,11 @@ __device__ __forceinline__ void row_store_bf16(const Row& r, __nv_bfloat16* __re
     *reinterpret_cast<uint2*>(p + 128 * i + 4 * lane) =
         pack4_bf16(r.v[4 * i], r.v[4 * i + 1], r.v[4 * i + 2], r.v[4 * i + 3]);
 }
-__device__ __forceinline__ void row_norm(Row& out, const Row& in, const float* __restrict__ g,
-                                         const float* __restrict__ b, float eps, int lane) {
+__device__ __forceinline__ void row_stats(const Row& in, float& mean, float& rstd, float eps) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) s += in.v[i];
-  const float mean = warp_sum(s) * (1.0f / 512.0f);
+  mean = warp_sum(s) * (1.0f / 512.0f);
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -150,7 +149,10 @@ __device__ __forceinline__ void row_norm(Row& out, const Row& in, const float* _
     ss += d * d;
   }
   const float var = warp_sum(ss) * (1.0f / 512.0f);
-  const float rstd = rsqrtf(var + eps);
+  rstd = rsqrtf(var + eps);
+}
+__device__ __forceinline__ void row_apply(Row& out, const Row& in, float mean, float rstd,
+                                          const float* __restrict__ g, const float* __restrict__ b, int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + 128 * i + 4 * lane));
@@ -161,9 +163,15 @@ __device__ __forceinline__ void row_norm(Row& out, const Row& in, const float* _
     out.v[4 * i + 3] = (in.v[4 * i + 3] - mean) * rstd * g4.w + b4.w;
   }
 }
+__device__ __forceinline__ void row_norm(Row& out, const Row& in, const float* __restrict__ g,
+                                         const float* __restrict__ b, float eps, int lane) {
+  float mean, rstd;
+  row_stats(in, mean, rstd, eps);
+  row_apply(out, in, mean, rstd, g, b, lane);
+}
 
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 layernorm512_kernel(const LnArgs a) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -171,11 +179,9 @@ layernorm512_kernel(const LnArgs a) {
   // Rows are visited from the END of the buffer: the producer GEMM wrote its last tiles most
   // recently, so those rows are still L2-resident, and this kernel in turn finishes on row 0,
   // where the consumer GEMM starts.
-  for (int64_t it = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5); it < a.M;
-       it += warps_total) {
-    const int64_t row = a.M - 1 - it;
-    Row x, y;
-    row_load(x, a.x + row * 512, lane);
+  // Two rows per warp and pass: both rows' loads are issued before either row's reduction chain starts.
+  auto finish_row = [&](const Row& x, int64_t row) {
+    Row y;
     row_norm(y, x, a.g0, a.b0, a.eps, lane);
     if constexpr (MODE == 0) {
       row_store_bf16(y, reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + row * 512, lane);
@@ -194,17 +200,34 @@ layernorm512_kernel(const LnArgs a) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) y.v[i] = fmaxf(y.v[i], 0.0f);
       row_store_f32(y, a.out_f32 + row * 512, lane);
+      // both head LayerNorms normalise the same row: one set of statistics, two affine maps
+      float mean, rstd;
+      row_stats(y, mean, rstd, a.eps);
       Row u;
-      row_norm(u, y, a.g1, a.b1, a.eps, lane);
+      row_apply(u, y, mean, rstd, a.g1, a.b1, lane);
       row_store_bf16(u, reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + row * 512, lane);
-      row_norm(u, y, a.g2, a.b2, a.eps, lane);
+      row_apply(u, y, mean, rstd, a.g2, a.b2, lane);
       row_store_bf16(u, reinterpret_cast<__nv_bfloat16*>(a.y2_bf16) + row * 512, lane);
     }
+  };
+  constexpr int ROWS = MODE == 2 ? 1 : 2;  // mode 2 (three normalisations per row) has no registers for a second row
+  for (int64_t it = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5); it < a.M;
+       it += ROWS * warps_total) {
+    const int64_t row_a = a.M - 1 - it;
+    const int64_t row_b = row_a - warps_total;
+    Row xa, xb;
+    row_load(xa, a.x + row_a * 512, lane);
+    if (ROWS == 2 && row_b >= 0) row_load(xb, a.x + row_b * 512, lane);
+    finish_row(xa, row_a);
+    if (ROWS == 2 && row_b >= 0) finish_row(xb, row_b);
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// head outputs: one warp per row, 256-wide dot products against 3 weight rows held in registers
+// head outputs: eight lanes per row (four rows per warp and pass, two passes in flight), 256-wide dot
+// products against the 3 weight rows held in registers.  Lane l of a row group reads the 16-byte pieces
+// {8 j + l} of the row, so every group access is one contiguous 128-byte line; the reduction is three
+// shuffle steps per value instead of a full warp tree per row.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 head_out_kernel(const __nv_bfloat16* __restrict__ ac, const __nv_bfloat16* __restrict__ ar,
@@ -212,37 +235,65 @@ head_out_kernel(const __nv_bfloat16* __restrict__ ac, const __nv_bfloat16* __res
                 const float* __restrict__ wr, const float* __restrict__ br,
                 float* __restrict__ logits, float* __restrict__ offsets, int64_t M) {
   const int lane = threadIdx.x & 31;
-  float w0[8], w1[8], w2[8];
+  const int sub = lane & 7;   // position inside the row group
+  const int grp = lane >> 3;  // row of the warp's four
+  float w0[32], w1[32], w2[32];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    w0[i] = wc[8 * lane + i];
-    w1[i] = wr[8 * lane + i];
-    w2[i] = wr[256 + 8 * lane + i];
-  }
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = 8 * (8 * j + sub) + i;
+      w0[8 * j + i] = wc[col];
+      w1[8 * j + i] = wr[col];
+      w2[8 * j + i] = wr[256 + col];
+    }
   const float bias_c = bc[0], bias_r0 = br[0], bias_r1 = br[1];
   const int64_t warps_total = int64_t(gridDim.x) * (blockDim.x >> 5);
-  for (int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5); row < M;
-       row += warps_total) {
-    const uint4 c4 = *reinterpret_cast<const uint4*>(ac + row * 256 + 8 * lane);
-    const uint4 r4 = *reinterpret_cast<const uint4*>(ar + row * 256 + 8 * lane);
-    const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
-    const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  const int64_t warp_id = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_wait();
+  for (int64_t row0 = warp_id * 8; row0 < M; row0 += warps_total * 8) {
+    uint4 c4[2][4], r4[2][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float c_lo = __uint_as_float(cw[i] << 16), c_hi = __uint_as_float(cw[i] & 0xffff0000u);
-      const float r_lo = __uint_as_float(rw[i] << 16), r_hi = __uint_as_float(rw[i] & 0xffff0000u);
-      s0 += c_lo * w0[2 * i] + c_hi * w0[2 * i + 1];
-      s1 += r_lo * w1[2 * i] + r_hi * w1[2 * i + 1];
-      s2 += r_lo * w2[2 * i] + r_hi * w2[2 * i + 1];
+    for (int u = 0; u < 2; ++u) {
+      const int64_t row = row0 + 4 * u + grp;
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          c4[u][j] = __ldcs(reinterpret_cast<const uint4*>(ac + row * 256) + 8 * j + sub);
+          r4[u][j] = __ldcs(reinterpret_cast<const uint4*>(ar + row * 256) + 8 * j + sub);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c4[u][j] = r4[u][j] = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
-    s0 = warp_sum(s0);
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) {
-      logits[row] = s0 + bias_c;
-      offsets[2 * row] = fmaxf(s1 + bias_r0, 0.0f);
-      offsets[2 * row + 1] = fmaxf(s2 + bias_r1, 0.0f);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t cw[4] = {c4[u][j].x, c4[u][j].y, c4[u][j].z, c4[u][j].w};
+        const uint32_t rw[4] = {r4[u][j].x, r4[u][j].y, r4[u][j].z, r4[u][j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float c_lo = __uint_as_float(cw[i] << 16), c_hi = __uint_as_float(cw[i] & 0xffff0000u);
+          const float r_lo = __uint_as_float(rw[i] << 16), r_hi = __uint_as_float(rw[i] & 0xffff0000u);
+          s0 += c_lo * w0[8 * j + 2 * i] + c_hi * w0[8 * j + 2 * i + 1];
+          s1 += r_lo * w1[8 * j + 2 * i] + r_hi * w1[8 * j + 2 * i + 1];
+          s2 += r_lo * w2[8 * j + 2 * i] + r_hi * w2[8 * j + 2 * i + 1];
+        }
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      const int64_t row = row0 + 4 * u + grp;
+      if (sub == 0 && row < M) {
+        logits[row] = s0 + bias_c;
+        *reinterpret_cast<float2*>(offsets + 2 * row) = make_float2(fmaxf(s1 + bias_r0, 0.0f), fmaxf(s2 + bias_r1, 0.0f));
+      }
     }
   }
 }
@@ -365,10 +416,11 @@ int launch_head_out(const void* a_cls_bf16, const void* a_reg_bf16, const float*
                     const float* b_cls, const float* w_reg, const float* b_reg, float* logits,
                     float* offsets, int64_t M, cudaStream_t stream) {
   RP_CHECK(M > 0, "head_out: empty");
-  head_out_kernel<<<grid_for(M, 8), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(a_cls_bf16),
-      reinterpret_cast<const __nv_bfloat16*>(a_reg_bf16), w_cls, b_cls, w_reg, b_reg, logits,
-      offsets, M);
+  RP_CHECK(reinterpret_cast<uintptr_t>(offsets) % 8 == 0, "head_out: offsets must be 8-byte aligned");
+  RP_CUDA_CHECK(launch_pdl(head_out_kernel, dim3(grid_for(M, 64)), dim3(256), 0, stream,
+                           reinterpret_cast<const __nv_bfloat16*>(a_cls_bf16),
+                           reinterpret_cast<const __nv_bfloat16*>(a_reg_bf16), w_cls, b_cls, w_reg, b_reg, logits,
+                           offsets, M));
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;

@@ -50,7 +50,7 @@ constexpr int LNB_WARPS = 8;
 __global__ void __launch_bounds__(LNB_WARPS * 32)
 layernorm512_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
                         int64_t M, float eps, float* __restrict__ dx, float* __restrict__ part_g,
-                        float* __restrict__ part_b) {
+                        float* __restrict__ part_b, int accumulate, __nv_bfloat16* __restrict__ dx_bf16) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float acc_g[16], acc_b[16], gm[16];
 #pragma unroll
@@ -108,7 +108,18 @@ layernorm512_bwd_kernel(const float* __restrict__ x, const float* __restrict__ d
       o4.y = rstd * (dv[4 * i + 1] - s1 - xv[4 * i + 1] * s2);
       o4.z = rstd * (dv[4 * i + 2] - s1 - xv[4 * i + 2] * s2);
       o4.w = rstd * (dv[4 * i + 3] - s1 - xv[4 * i + 3] * s2);
-      reinterpret_cast<float4*>(dx + row * 512)[i * 32 + lane] = o4;
+      float4* dst = reinterpret_cast<float4*>(dx + row * 512) + i * 32 + lane;
+      if (accumulate) {  // the residual stream's gradient: dh += d(LN branch)
+        const float4 old = *dst;
+        o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
+      }
+      *dst = o4;
+      if (dx_bf16 != nullptr) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o4.x, o4.y);
+        pk.y = pack_bf16x2(o4.z, o4.w);
+        reinterpret_cast<uint2*>(dx_bf16 + row * 512)[i * 32 + lane] = pk;
+      }
     }
   }
   __shared__ float sg[LNB_WARPS][512], sb[LNB_WARPS][512];
@@ -164,6 +175,124 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
   if (p_bf16 != nullptr) p_bf16[i] = __float2bfloat16_rn(out);
 }
 
+
+// ---- split-K partial sums -> gradient (fixed summation order: deterministic) ---------------------------------
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 acc = *reinterpret_cast<const float4*>(part + i);
+  for (int s = 1; s < splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(part + int64_t(s) * n + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + i) = acc;
+}
+
+// ---- column sums of a bf16 [M, N] matrix (bias gradients), two fixed-order stages ----------------------------
+// stage 1: block (bx, by) sums rows [by * rows_per, ...) of the 256 columns bx*256.. (thread = column pair... one column
+// per thread, coalesced 512-byte row segments); stage 2 adds the per-block partials in order.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t M, int N, int64_t rows_per, float* __restrict__ part) {
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col >= N) return;
+  const int64_t r0 = int64_t(blockIdx.y) * rows_per;
+  const int64_t r1 = r0 + rows_per < M ? r0 + rows_per : M;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int64_t r = r0;
+  for (; r + 3 < r1; r += 4) {
+    a0 += __bfloat162float(x[r * N + col]);
+    a1 += __bfloat162float(x[(r + 1) * N + col]);
+    a2 += __bfloat162float(x[(r + 2) * N + col]);
+    a3 += __bfloat162float(x[(r + 3) * N + col]);
+  }
+  for (; r < r1; ++r) a0 += __bfloat162float(x[r * N + col]);
+  part[int64_t(blockIdx.y) * N + col] = (a0 + a1) + (a2 + a3);
+}
+__global__ void colsum_reduce_kernel(const float* __restrict__ part, int parts, int N, float* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  float a = 0.f;
+  for (int p = 0; p < parts; ++p) a += part[int64_t(p) * N + col];
+  out[col] = a;
+}
+
+// ---- ReLU backward: dy = act > 0 ? dy : 0 (bf16 in place; fp32 gradient against an fp32 activation) ----------
+__global__ void relu_bwd_bf16_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ act, int64_t n8) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  uint4 d = reinterpret_cast<const uint4*>(dy)[i];
+  const uint4 a = __ldcs(reinterpret_cast<const uint4*>(act) + i);
+  // bf16 > 0: sign bit clear and not zero
+  auto mask2 = [](uint32_t dv, uint32_t av) {
+    const uint32_t lo = (av & 0x8000u) == 0u && (av & 0x7fffu) != 0u ? 0xffffu : 0u;
+    const uint32_t hi = (av & 0x80000000u) == 0u && (av & 0x7fff0000u) != 0u ? 0xffff0000u : 0u;
+    return dv & (lo | hi);
+  };
+  d.x = mask2(d.x, a.x); d.y = mask2(d.y, a.y); d.z = mask2(d.z, a.z); d.w = mask2(d.w, a.w);
+  reinterpret_cast<uint4*>(dy)[i] = d;
+}
+__global__ void relu_bwd_f32_kernel(float* __restrict__ dy, const float* __restrict__ act, int64_t n4) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 d = reinterpret_cast<const float4*>(dy)[i];
+  const float4 a = __ldcs(reinterpret_cast<const float4*>(act) + i);
+  d.x = a.x > 0.f ? d.x : 0.f; d.y = a.y > 0.f ? d.y : 0.f; d.z = a.z > 0.f ? d.z : 0.f; d.w = a.w > 0.f ? d.w : 0.f;
+  reinterpret_cast<float4*>(dy)[i] = d;
+}
+
+// ---- last head layer backward: logits[m] = a2[m,:] . w + b  (cls_head.7, models/MMCTransformer.py:71-80) ----------
+// da2[m, c] = dlogit[m] * w[c] where a2[m, c] > 0 (the ReLU in front of the layer), bf16; per-block partials of
+// dw[c] = sum_m dlogit[m] a2[m, c] and db = sum_m dlogit[m] (reduced in order by colsum_reduce_kernel).
+__global__ void __launch_bounds__(256)
+head_out_bwd_kernel(const float* __restrict__ dlogit, const __nv_bfloat16* __restrict__ a2, const float* __restrict__ w,
+                    int64_t M, int64_t rows_per, __nv_bfloat16* __restrict__ da2, float* __restrict__ part) {
+  const int c = threadIdx.x;  // 256 columns
+  const float wc = w[c];
+  const int64_t r0 = int64_t(blockIdx.x) * rows_per;
+  const int64_t r1 = r0 + rows_per < M ? r0 + rows_per : M;
+  float dw = 0.f, db = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float g = dlogit[r];
+    const float a = __bfloat162float(a2[r * 256 + c]);
+    da2[r * 256 + c] = __float2bfloat16_rn(a > 0.f ? g * wc : 0.f);
+    dw = fmaf(g, a, dw);
+    db += g;
+  }
+  part[int64_t(blockIdx.x) * 257 + c] = dw;
+  if (c == 0) part[int64_t(blockIdx.x) * 257 + 256] = db;
+}
+
+// ---- attention backward pre-process: Dsum[b, h, t] = sum_d dO[b,t,h,d] * O[b,t,h,d] (fp32) ----------------------
+// one warp per token row of 512 bf16 (lane owns 16 consecutive columns = a quarter of head lane / 4)
+__global__ void __launch_bounds__(256)
+attn_bwd_dsum_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int B, int T, int H,
+                     float* __restrict__ dsum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= int64_t(B) * T) return;
+  const int cols = H * 64;
+  for (int c0 = lane * 16; c0 < cols; c0 += 512) {
+    float acc = 0.f;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const uint4 a = *reinterpret_cast<const uint4*>(o + row * cols + c0 + 8 * v);
+      const uint4 g = *reinterpret_cast<const uint4*>(d_o + row * cols + c0 + 8 * v);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc = fmaf(__uint_as_float(aw[i] << 16), __uint_as_float(gw[i] << 16), acc);
+        acc = fmaf(__uint_as_float(aw[i] & 0xffff0000u), __uint_as_float(gw[i] & 0xffff0000u), acc);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if ((lane & 3) == 0) {
+      const int head = c0 >> 6;
+      const int64_t b = row / T, t = row - b * T;
+      dsum[(b * H + head) * T + t] = acc;
+    }
+  }
+}
 }  // namespace
 
 int launch_focal_loss_grad(const float* logits, const float* targets, const uint8_t* mask, int64_t n, float alpha,
@@ -179,14 +308,17 @@ int launch_focal_loss_grad(const float* logits, const float* targets, const uint
 int64_t layernorm512_bwd_scratch_floats() { return int64_t(2) * 4 * num_sms() * 512; }
 
 int launch_layernorm512_bwd(const float* x, const float* dy, const float* gamma, int64_t M, float eps, float* dx,
-                            float* dgamma, float* dbeta, float* scratch, cudaStream_t stream) {
+                            float* dgamma, float* dbeta, float* scratch, cudaStream_t stream, bool accumulate,
+                            void* dx_bf16) {
   RP_CHECK(M > 0, "layernorm512_bwd: empty");
   const int sms = num_sms();
   int grid = 4 * sms;
   if (int64_t(grid) * LNB_WARPS > M) grid = int((M + LNB_WARPS - 1) / LNB_WARPS);
   float* part_g = scratch;
   float* part_b = scratch + int64_t(4) * sms * 512;
-  layernorm512_bwd_kernel<<<grid, LNB_WARPS * 32, 0, stream>>>(x, dy, gamma, M, eps, dx, part_g, part_b);
+  layernorm512_bwd_kernel<<<grid, LNB_WARPS * 32, 0, stream>>>(x, dy, gamma, M, eps, dx, part_g, part_b,
+                                                               accumulate ? 1 : 0,
+                                                               reinterpret_cast<__nv_bfloat16*>(dx_bf16));
   layernorm512_bwd_reduce_kernel<<<4, 128, 0, stream>>>(part_g, part_b, grid, dgamma, dbeta);
   count_launch(2);
   RP_CUDA_CHECK(cudaGetLastError());
@@ -200,6 +332,75 @@ int launch_adam_step(float* p, const float* g, float* m, float* v, int64_t n, fl
   const float c2s = sqrtf(1.0f - powf(beta2, float(step)));
   adam_step_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, c1,
                                                                   c2s, reinterpret_cast<__nv_bfloat16*>(p_bf16));
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+
+int launch_splitk_reduce(const float* part, int splits, int64_t n, float* out, cudaStream_t stream) {
+  RP_CHECK(splits >= 1 && n > 0 && n % 4 == 0, "splitk_reduce: n must be a positive multiple of 4");
+  splitk_reduce_kernel<<<unsigned((n / 4 + 255) / 256), 256, 0, stream>>>(part, splits, n, out);
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+// one scratch size for every two-stage reduction of the backward pass (LayerNorm 2 x 4 SMs x 512, column sums
+// <= 4 SMs x 256 per column block, head_out_bwd 4 SMs x 257 + 257)
+int64_t train_scratch_floats() { return int64_t(4) * num_sms() * 1024 + 1024; }
+
+int launch_colsum_bf16(const void* x, int64_t M, int N, float* out, float* scratch, cudaStream_t stream) {
+  RP_CHECK(M > 0 && N > 0, "colsum: empty");
+  const int bx = (N + 255) / 256;
+  int by = 4 * num_sms() / bx;
+  if (by < 1) by = 1;
+  if (by > M) by = int(M);
+  const int64_t rows_per = (M + by - 1) / by;
+  by = int((M + rows_per - 1) / rows_per);
+  colsum_bf16_kernel<<<dim3(bx, by), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, N, rows_per, scratch);
+  colsum_reduce_kernel<<<(N + 127) / 128, 128, 0, stream>>>(scratch, by, N, out);
+  count_launch(2);
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+int launch_relu_bwd(void* dy, const void* act, int64_t n, bool f32, cudaStream_t stream) {
+  RP_CHECK(n > 0 && n % 8 == 0, "relu_bwd: n must be a positive multiple of 8");
+  if (f32)
+    relu_bwd_f32_kernel<<<unsigned((n / 4 + 255) / 256), 256, 0, stream>>>(static_cast<float*>(dy),
+                                                                           static_cast<const float*>(act), n / 4);
+  else
+    relu_bwd_bf16_kernel<<<unsigned((n / 8 + 255) / 256), 256, 0, stream>>>(
+        static_cast<__nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(act), n / 8);
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+int launch_head_out_bwd(const float* dlogit, const void* a2, const float* w, int64_t M, void* da2, float* dw, float* db,
+                        float* scratch, cudaStream_t stream) {
+  RP_CHECK(M > 0, "head_out_bwd: empty");
+  int blocks = 4 * num_sms();
+  if (blocks > M) blocks = int(M);
+  const int64_t rows_per = (M + blocks - 1) / blocks;
+  blocks = int((M + rows_per - 1) / rows_per);
+  head_out_bwd_kernel<<<blocks, 256, 0, stream>>>(dlogit, static_cast<const __nv_bfloat16*>(a2), w, M, rows_per,
+                                                  static_cast<__nv_bfloat16*>(da2), scratch);
+  // the 257 partial columns: dw[0..256) and db
+  colsum_reduce_kernel<<<3, 128, 0, stream>>>(scratch, blocks, 257, scratch + int64_t(blocks) * 257);
+  RP_CUDA_CHECK(cudaMemcpyAsync(dw, scratch + int64_t(blocks) * 257, 256 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  RP_CUDA_CHECK(cudaMemcpyAsync(db, scratch + int64_t(blocks) * 257 + 256, sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  count_launch(2);
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+int launch_attn_bwd_dsum(const void* o, const void* d_o, int B, int T, int H, float* dsum, cudaStream_t stream) {
+  RP_CHECK(B > 0 && T > 0 && H > 0 && H % 8 == 0, "attn_bwd_dsum: H must be a positive multiple of 8");
+  const int64_t rows = int64_t(B) * T;
+  attn_bwd_dsum_kernel<<<unsigned((rows + 7) / 8), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(o),
+                                                                     static_cast<const __nv_bfloat16*>(d_o), B, T, H, dsum);
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;

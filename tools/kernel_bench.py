@@ -2,7 +2,7 @@
 """Micro-benchmark of the individual kernels at the bench.py shapes (B=32, T=1801), timed with CUDA
 events.  Used while optimising and as the target command for `ncu -k regex:<kernel>`.
 
-    python tools/kernel_bench.py [fmha] [gemm] [ln] [--iters N] [--B 32] [--T 1801]
+    python tools/kernel_bench.py [fmha] [gemm] [gemmln] [rowwise] [ln] [--iters N] [--B 32] [--T 1801]
 """
 import argparse
 import json
@@ -82,6 +82,63 @@ def main():
             ms = timeit(run, args.iters, flush)
             byt = M * K * 2 + N * K * 2 + M * N * (4 if f32 else 2) * (2 if epi == 3 else 1)
             out[f"gemm_{name}"] = {"ms": ms, "tflops": 2.0 * M * N * K / ms / 1e9, "gbs": byt / ms / 1e6}
+    if "gemmln" in args.what:
+        # the LayerNorm-fused residual GEMMs of the forward (out-proj K=512, FF2 K=2048): h += A W^T + b; u = LN(h)
+        for name, K in (("out+ln", 512), ("ff2+ln", 2048)):
+            A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+            W = (torch.randn(512, K, device=dev) * 0.05).bfloat16()
+            bias = torch.randn(512, device=dev)
+            hres = torch.zeros(M, 512, device=dev)
+            u = torch.empty(M, 512, dtype=torch.bfloat16, device=dev)
+            g = torch.ones(512, device=dev)
+            b = torch.zeros(512, device=dev)
+
+            def run():
+                check(lib.rp_gemm_resid_ln(ptr(A), K, ptr(W), K, ptr(hres), 512, ptr(bias), ptr(g), ptr(b), 1e-5,
+                                           ptr(u), 512, M, K, cur_stream()), "gemm_resid_ln")
+            ms = timeit(run, args.iters, flush)
+            byt = M * (K * 2 + 512 * 4 * 2 + 512 * 2) + 512 * K * 2
+            out[f"gemm_{name}"] = {"ms": ms, "tflops": 2.0 * M * 512 * K / ms / 1e9, "gbs": byt / ms / 1e6}
+    if "rowwise" in args.what:
+        # memory-bound kernels of the step, against their algorithmic bytes
+        a_c = torch.randn(M, 256, device=dev).bfloat16()
+        a_r = torch.randn(M, 256, device=dev).bfloat16()
+        wc, bc = torch.randn(256, device=dev), torch.randn(1, device=dev)
+        wr, br = torch.randn(2, 256, device=dev), torch.randn(2, device=dev)
+        lg = torch.empty(M, device=dev)
+        off = torch.empty(M, 2, device=dev)
+
+        def run():
+            check(lib.rp_head_out(ptr(a_c), ptr(a_r), ptr(wc), ptr(bc), ptr(wr), ptr(br), ptr(lg), ptr(off), M,
+                                  cur_stream()), "head_out")
+        ms = timeit(run, args.iters, flush)
+        out["head_out"] = {"ms": ms, "gbs": M * (2 * 512 + 12) / ms / 1e6}
+        x = torch.randn(M, 512, device=dev)
+        g = torch.ones(512, device=dev)
+        b = torch.zeros(512, device=dev)
+        pe = torch.randn(T, 512, device=dev)
+        hf = torch.empty(M, 512, device=dev)
+        y = torch.empty(M, 512, dtype=torch.bfloat16, device=dev)
+        y2 = torch.empty(M, 512, dtype=torch.bfloat16, device=dev)
+
+        def run():
+            check(lib.rp_layernorm512(1, ptr(x), M, T, ptr(g), ptr(b), ptr(g), ptr(b), 0, 0, ptr(pe), ptr(hf), ptr(y), 0,
+                                      cur_stream()), "ln1")
+        ms = timeit(run, args.iters, flush)
+        out["ln_mode1"] = {"ms": ms, "gbs": M * 5120 / ms / 1e6}
+
+        def run():
+            check(lib.rp_layernorm512(2, ptr(x), M, T, ptr(g), ptr(b), ptr(g), ptr(b), ptr(g), ptr(b), 0, ptr(hf), ptr(y),
+                                      ptr(y2), cur_stream()), "ln2")
+        ms = timeit(run, args.iters, flush)
+        out["ln_mode2"] = {"ms": ms, "gbs": M * 6144 / ms / 1e6}
+        vis, aud, txt = (torch.randn(M, c, device=dev) for c in (512, 2048, 384))
+        xc = torch.empty(M, 2944, dtype=torch.bfloat16, device=dev)
+
+        def run():
+            check(lib.rp_concat_cast(ptr(vis), ptr(aud), ptr(txt), 512, 2048, 384, ptr(xc), M, cur_stream()), "concat")
+        ms = timeit(run, args.iters, flush)
+        out["concat_cast"] = {"ms": ms, "gbs": M * 2944 * 6 / ms / 1e6}
     if "ln" in args.what:
         x = torch.randn(M, 512, device=dev)
         g = torch.ones(512, device=dev)
