@@ -388,6 +388,14 @@ def run_ours(args, rank, world, local_rank):
                 extra["config3_10k"][tag] = {"videos_per_s": r["value"], "seconds": r["seconds"], "segments": r["segments"]}
         if world == 1:
             extra["stress_T8192"] = stress_t8192(model, dev, peaks)
+        # BASELINE.json configs[4]: the training step (forward + backward + flat gradient all-reduce + Adam), 16 videos
+        # at T = 1801 per GPU; at N > 1 the all-reduce over the 210 MB fp32 gradient buffer is inside the timed step
+        del model
+        torch.cuda.empty_cache()
+        from train_bench import run_train_bench
+        r = run_train_bench(16, SEQ, steps=3, warmup=2, rank=rank, world=world, dev=dev)
+        if rank == 0:
+            extra["train_step"] = r
 
     if rank == 0:
         flops_step = BATCH * algorithmic_flops_per_video(SEQ)

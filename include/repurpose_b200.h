@@ -187,6 +187,11 @@ int32_t rp_adam_step(float* param, const float* grad, float* exp_avg, float* exp
  * rp_fmha_train            rp_fmha (key-padding mode) that also writes the log2-domain log-sum-exp [B,H,T]
  * rp_fmha_bwd              autograd of the attention inside nn.MultiheadAttention (models/MMCTransformer.py:41-55,
  *                          132-138): dq (w.r.t. the unscaled q), dk, dv; dsum = scratch [B,H,T] fp32 */
+/* out = in with the first n_scaled elements multiplied by scale, as bf16 and / or fp32: the attention kernels take
+ * q pre-scaled by log2(e)/sqrt(64), so the training forward's in_proj operand is in_proj_weight / in_proj_bias with the
+ * q rows scaled (rp_load_weight does the same fold for inference) */
+int32_t rp_cast_scaled(const float* in, int64_t n, int64_t n_scaled, float scale, void* out_bf16, float* out_f32,
+                       void* stream);
 int64_t rp_train_scratch_bytes(void);
 int32_t rp_layernorm512_bwd_acc(const float* x, const float* dy, const float* gamma, int64_t M, float eps,
                                 float* dh_inout, void* dh_bf16, float* dgamma, float* dbeta, void* scratch,

@@ -537,6 +537,18 @@ int32_t rp_layernorm512_bwd(const float* x, const float* dy, const float* gamma,
                                  reinterpret_cast<cudaStream_t>(stream));
 }
 
+int32_t rp_cast_scaled(const float* in, int64_t n, int64_t n_scaled, float scale, void* out_bf16, float* out_f32,
+                       void* stream) {
+  RP_CHECK(in && (out_bf16 || out_f32) && n > 0, "rp_cast_scaled: null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = int(std::min<int64_t>((n + 255) / 256, 4096));
+  if (out_bf16) repack_bf16_kernel<<<grid, 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n, n_scaled, scale);
+  if (out_f32) repack_f32_kernel<<<grid, 256, 0, st>>>(in, out_f32, n, n_scaled, scale);
+  count_launch((out_bf16 ? 1 : 0) + (out_f32 ? 1 : 0));
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
 int64_t rp_train_scratch_bytes(void) { return train_scratch_floats() * int64_t(sizeof(float)); }
 
 int32_t rp_layernorm512_bwd_acc(const float* x, const float* dy, const float* gamma, int64_t M, float eps,

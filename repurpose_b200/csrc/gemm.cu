@@ -38,7 +38,6 @@ constexpr int BN = 256;                // accumulator columns per tile
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
 constexpr int SLAB_BYTES = 32 * 128;   // 32 rows x 128 B: one TMA box of the output / residual
-constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_SLABS = 8;  // barriers reserved per epilogue warp
 
@@ -46,7 +45,10 @@ constexpr int MAX_SLABS = 8;  // barriers reserved per epilogue warp
 // stages for a deeper slab ring (loads and stores both live there).
 // RS = slabs per epilogue warp of the residual epilogues (4, 6 or 8): RS - 2 residual chunks of 4 KB are in
 // flight per warp.  A memory-bound problem (K = 512: out-proj) wants the deeper ring more than operand stages.
-template <int EPI, int CG, int RS = 4>
+// EW = epilogue warps (4, or 8 for the LayerNorm-fused epilogue of memory-bound problems): with 8, two warps share a
+// TMEM lane quarter and each walks half of the tile's columns, so two dependent chunk chains per SM sub-partition
+// overlap instead of one (profiles/r02_notes.md: the 4-warp epilogue is latency-, not bandwidth-bound).
+template <int EPI, int CG, int RS = 4, int EW = 4>
 struct Cfg {
   static constexpr bool RESID = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_LN);
   static constexpr bool LNF = (EPI == EPI_BIAS_RESID_LN);   // LayerNorm of the updated rows fused in (cluster of 4)
@@ -55,14 +57,20 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SLABS = RESID ? RS : 2;          // per epilogue warp
   static constexpr int LOOKAHEAD = SLABS - 2;          // residual chunks in flight per warp
-  static constexpr int STAGES = (229376 - 4 * SLABS * SLAB_BYTES) / STAGE_BYTES;  // CG1: 4/3, CG2: 6/5
+  static constexpr int COL_SPLIT = EW / 4;             // warps per TMEM lane quarter = column parts of a tile
+  static constexpr int NUM_THREADS = 64 + 32 * EW;
+  static constexpr int BAR_BYTES = EW == 8 ? 1024 : 512;
+  // LNF row statistics: EW = 4: [2 buffers][128 rows] (mean, M2) from the partner pair; EW = 8: [2][4 column quarters][128]
+  static constexpr int STATS_BYTES = !LNF ? 0 : (EW == 8 ? 2 * 4 * 128 * 8 : 2 * 128 * 8);
+  static constexpr int SLACK_BYTES = LNF ? 512 : 1024;  // alignment slack (the dynamic segment is declared 1024-aligned; checked at run time)
+  static constexpr int STAGES = (232448 - BAR_BYTES - STATS_BYTES - SLACK_BYTES - EW * SLABS * SLAB_BYTES) / STAGE_BYTES;  // CG1: 4/3, CG2: 6/5
   static constexpr int SMEM_A_OFF = 0;
   static constexpr int SMEM_B_OFF = STAGES * A_BYTES;
   static constexpr int SMEM_D_OFF = SMEM_B_OFF + STAGES * B_BYTES;
-  static constexpr int SMEM_BAR_OFF = SMEM_D_OFF + 4 * SLABS * SLAB_BYTES;
-  static constexpr int SMEM_STATS_OFF = SMEM_BAR_OFF + 512;     // LNF: [2 buffers][128 rows] (sum, sumsq) from the partner pair
-  // barriers (+ LNF statistics) + alignment slack (the dynamic segment is declared 1024-aligned; checked at run time)
-  static constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 512 + (LNF ? 2048 + 512 : 1024);
+  static constexpr int SMEM_BAR_OFF = SMEM_D_OFF + EW * SLABS * SLAB_BYTES;
+  static constexpr int SMEM_STATS_OFF = SMEM_BAR_OFF + BAR_BYTES;
+  static constexpr int SMEM_TOTAL = SMEM_STATS_OFF + STATS_BYTES + SLACK_BYTES;
+  static_assert(EW == 4 || (EW == 8 && LNF && CG == 2), "8 epilogue warps: LayerNorm-fused epilogue only");
   static_assert(STAGES >= 3 && STAGES <= 8, "stage count");
   static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 };
@@ -82,12 +90,12 @@ struct GemmArgs {
 //      over the tokens; rows beyond K are zero-filled by TMA)
 // An MN-major operand tile is staged as 64-column blocks of BK rows x 128 B (one TMA box each); the UMMA descriptor
 // walks them with LBO = BK * 128 (stride between 64-wide MN blocks) and SBO = 1024 (8 K indices).
-template <int EPI, int CG, int RS, int TR>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int EPI, int CG, int RS, int TR, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                  const __grid_constant__ CUtensorMap tmU, const GemmArgs g) {
-  using C = Cfg<EPI, CG, RS>;
+  using C = Cfg<EPI, CG, RS, EW>;
   constexpr int STAGES = C::STAGES;
   constexpr int SLABS = C::SLABS;
   constexpr bool OUT_F32 = (EPI == EPI_BIAS_F32 || C::RESID);
@@ -111,7 +119,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tfull_bar = [&](int b) { return bar_base + 128u + 8u * b; };
   auto tempty_bar = [&](int b) { return bar_base + 144u + 8u * b; };
   auto resid_bar = [&](int ew, int s) { return bar_base + 192u + 8u * (ew * MAX_SLABS + s); };
-  auto stats_bar = [&](int b) { return bar_base + 448u + 8u * b; };  // LNF: partner pair's row statistics have landed
+  auto stats_bar = [&](int b) { return bar_base + (EW == 8 ? 704u : 448u) + 8u * b; };  // LNF: partner pair's row statistics have landed
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::SMEM_BAR_OFF + 160);
 
   const int warp = threadIdx.x >> 5;
@@ -149,10 +157,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4 * CG);
+      mbar_init(tempty_bar(b), EW * CG);
     }
-    for (int i = 0; i < 4 * MAX_SLABS; ++i) mbar_init(bar_base + 192u + 8u * i, 1);
-    for (int b = 0; b < 2; ++b) mbar_init(stats_bar(b), 128);
+    for (int i = 0; i < EW * MAX_SLABS; ++i) mbar_init(bar_base + 192u + 8u * i, 1);
+    // EW = 4: the partner pair's 128 threads arrive; EW = 8: this CTA's 256 epilogue threads and the partner's 256
+    for (int b = 0; b < 2; ++b) mbar_init(stats_bar(b), EW == 8 ? 512 : 128);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -258,18 +267,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;   // TMEM lane quarter this warp may access
     const int ew = warp - 2;  // slab ring / barrier set of this warp
+    const int ch = ew >> 2;   // column part of the tile this warp walks (EW = 8: two warps per lane quarter)
     const uint32_t slab0 = base + C::SMEM_D_OFF + ew * SLABS * SLAB_BYTES;
     const int my_tiles = group < total_tiles ? (total_tiles - group + num_groups - 1) / num_groups : 0;
-    // Slab uses per tile: CHUNKS residual/output chunks, then (LNF) 4 chunks of normalised bf16 rows.
-    constexpr int UPT = CHUNKS + (LNF ? BN / 64 : 0);
+    // Slab uses per tile and warp: its residual/output chunks, then (LNF) its chunks of normalised bf16 rows.
+    constexpr int WCH = CHUNKS / C::COL_SPLIT;           // fp32 chunks per warp and tile
+    constexpr int WLN = (BN / 64) / C::COL_SPLIT;        // LayerNorm output chunks per warp and tile
+    constexpr int UPT = WCH + (LNF ? WLN : 0);
     static_assert(!LNF || CHUNKS == 8, "LNF: 8 fp32 chunks of 32 columns per 256-column tile");
     const int total_chunks = my_tiles * UPT;
     auto tile_row0 = [&](int m_blk) { return (m_blk * CG + cta_rank) * BM + q * 32; };
 
     // slab use gc (per-warp counter) -> if it is a residual chunk, issue its TMA load into slab gc % SLABS
     auto issue_resid_load = [&](int gc) {
-      const int c = gc % UPT;
-      if (c >= CHUNKS) return;  // a LayerNorm output chunk: nothing to load
+      const int cl = gc % UPT;
+      if (cl >= WCH) return;  // a LayerNorm output chunk: nothing to load
+      const int c = ch * WCH + cl;
       const int tile = group + (gc / UPT) * num_groups;
       const int m_blk = tile / n_tiles;  // (residual epilogues never run split-K)
       const int n_blk = tile - m_blk * n_tiles;
@@ -301,7 +314,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
 
 #pragma unroll 1
-      for (int c = 0; c < CHUNKS; ++c, ++gc) {
+      for (int c = ch * WCH; c < (ch + 1) * WCH; ++c, ++gc) {
         const int s = gc % SLABS;
         const uint32_t slab = slab0 + s * SLAB_BYTES;
         // bias of this chunk: requested before the barrier waits below so that the global-load
@@ -377,7 +390,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if constexpr (LNF) {
               // keep the updated row in TMEM for the normalisation pass and accumulate its statistics
               tmem_st32(t_row + uint32_t(c * CPC + half * 32), v);
-              if (c == 0 && half == 0) st_shift = __uint_as_float(v[0]);
+              if (c == ch * WCH && half == 0) st_shift = __uint_as_float(v[0]);
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const float d = __uint_as_float(v[i]) - st_shift;
@@ -413,26 +426,54 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_st_wait();
         const int my_row = q * 32 + lane;
         const uint32_t partner = uint32_t(cluster_rank ^ 2);
-        // this half's mean and centred sum of squares; the halves are merged with the pairwise update of
-        // Chan et al. (symmetric in the two halves, so both CTAs compute bit-identical statistics)
-        const float my_mean = st_shift + st_sum * (1.0f / float(BN));
-        const float my_m2 = fmaxf(st_sq - st_sum * st_sum * (1.0f / float(BN)), 0.f);
-        st_cluster_f32x2(mapa_shared(base + C::SMEM_STATS_OFF + uint32_t(buf * 128 + my_row) * 8u, partner), my_mean, my_m2);
-        mbar_arrive_cluster(mapa_shared(stats_bar(buf), partner));
-        for (uint32_t polls = 0; !mbar_try_wait_cluster(stats_bar(buf), use_parity);)
-          if (++polls > (1u << 26)) __trap();  // a protocol bug must trap, not hang the GPU (ptx.cuh bounded-wait policy)
-        float2 other;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
-                     : "=f"(other.x), "=f"(other.y)
-                     : "r"(base + C::SMEM_STATS_OFF + uint32_t(buf * 128 + my_row) * 8u)
-                     : "memory");
-        const float inv_w = 1.0f / float(2 * BN);
-        const float mean = 0.5f * (my_mean + other.x);
-        const float dm = my_mean - other.x;
-        const float rstd = rsqrtf((my_m2 + other.y + dm * dm * (0.5f * float(BN))) * inv_w + g.ln.eps);
+        constexpr int WCOLS = BN / C::COL_SPLIT;  // columns behind this thread's statistics
+        // this part's mean and centred sum of squares; parts are merged with the pairwise update of Chan et al. in
+        // a fixed order over the column quarters, so every CTA and warp computes bit-identical statistics
+        const float my_mean = st_shift + st_sum * (1.0f / float(WCOLS));
+        const float my_m2 = fmaxf(st_sq - st_sum * st_sum * (1.0f / float(WCOLS)), 0.f);
+        float mean, m2;
+        if constexpr (EW == 8) {
+          // [buffer][global column quarter][row]: written here and in the partner pair's CTA of the same rows
+          const int gq_ = ((cluster_rank >> 1) & 1) * 2 + ch;
+          const uint32_t slot = base + C::SMEM_STATS_OFF + uint32_t((buf * 4 + gq_) * 128 + my_row) * 8u;
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(slot), "f"(my_mean), "f"(my_m2) : "memory");
+          mbar_arrive(stats_bar(buf));
+          st_cluster_f32x2(mapa_shared(slot, partner), my_mean, my_m2);
+          mbar_arrive_cluster(mapa_shared(stats_bar(buf), partner));
+          for (uint32_t polls = 0; !mbar_try_wait_cluster(stats_bar(buf), use_parity);)
+            if (++polls > (1u << 26)) __trap();  // a protocol bug must trap, not hang the GPU (ptx.cuh bounded-wait policy)
+          float2 pq[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                         : "=f"(pq[j].x), "=f"(pq[j].y)
+                         : "r"(base + C::SMEM_STATS_OFF + uint32_t((buf * 4 + j) * 128 + my_row) * 8u)
+                         : "memory");
+          const float d01 = pq[0].x - pq[1].x, d23 = pq[2].x - pq[3].x;
+          const float mA = 0.5f * (pq[0].x + pq[1].x), mB = 0.5f * (pq[2].x + pq[3].x);
+          const float sA = pq[0].y + pq[1].y + d01 * d01 * (0.5f * float(WCOLS));
+          const float sB = pq[2].y + pq[3].y + d23 * d23 * (0.5f * float(WCOLS));
+          const float dAB = mA - mB;
+          mean = 0.5f * (mA + mB);
+          m2 = sA + sB + dAB * dAB * (0.5f * float(2 * WCOLS));
+        } else {
+          st_cluster_f32x2(mapa_shared(base + C::SMEM_STATS_OFF + uint32_t(buf * 128 + my_row) * 8u, partner), my_mean, my_m2);
+          mbar_arrive_cluster(mapa_shared(stats_bar(buf), partner));
+          for (uint32_t polls = 0; !mbar_try_wait_cluster(stats_bar(buf), use_parity);)
+            if (++polls > (1u << 26)) __trap();  // a protocol bug must trap, not hang the GPU (ptx.cuh bounded-wait policy)
+          float2 other;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                       : "=f"(other.x), "=f"(other.y)
+                       : "r"(base + C::SMEM_STATS_OFF + uint32_t(buf * 128 + my_row) * 8u)
+                       : "memory");
+          mean = 0.5f * (my_mean + other.x);
+          const float dm = my_mean - other.x;
+          m2 = my_m2 + other.y + dm * dm * (0.5f * float(BN));
+        }
+        const float rstd = rsqrtf(m2 * (1.0f / float(2 * BN)) + g.ln.eps);
         const float nmr = -mean * rstd;
 #pragma unroll 1
-        for (int c2 = 0; c2 < BN / 64; ++c2, ++gc) {
+        for (int c2 = ch * WLN; c2 < (ch + 1) * WLN; ++c2, ++gc) {
           const int s = gc % SLABS;
           const uint32_t slab = slab0 + s * SLAB_BYTES;
           if (lane == 0) {
@@ -503,24 +544,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int EPI, int CG, int RS = 4, int TR = 0>
+template <int EPI, int CG, int RS = 4, int TR = 0, int EW = 4>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                const CUtensorMap& tmR, const CUtensorMap& tmU, const GemmArgs& g, int groups,
                cudaStream_t stream) {
-  using C = Cfg<EPI, CG, RS>;
+  using C = Cfg<EPI, CG, RS, EW>;
   constexpr int CLUSTER = C::LNF ? 4 : CG;  // LNF: two CTA pairs per cluster share full 512-column rows
   static bool configured_on[kMaxDevices];
   static int max_clusters_on[kMaxDevices];
   bool& configured = configured_on[current_device()];
   int& max_clusters = max_clusters_on[current_device()];
   if (!configured) {
-    RP_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, CG, RS, TR>,
+    RP_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI, CG, RS, TR, EW>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(unsigned(groups * CG));
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(C::NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -537,7 +578,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
     // co-resident (33 clusters = 132 SMs on B200).  Pairs 2c / 2c+1 walk tiles (m, 0) / (m, 1) in step.
     if (max_clusters == 0) {
       cfg.gridDim = dim3(unsigned(num_sms() / 4 * 4));
-      RP_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters, gemm_bf16_kernel<EPI, CG, RS, TR>, &cfg));
+      RP_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters, gemm_bf16_kernel<EPI, CG, RS, TR, EW>, &cfg));
       RP_CHECK(max_clusters > 0, "gemm: no cluster of 4 CTAs fits");
     }
     const int m_tiles = (g.M + BM * CG - 1) / (BM * CG);
@@ -545,7 +586,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
     cfg.gridDim = dim3(unsigned(clusters * 4));
   }
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  RP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, CG, RS, TR>, tmA, tmB, tmD, tmR, tmU, g));
+  RP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<EPI, CG, RS, TR, EW>, tmA, tmB, tmD, tmR, tmU, g));
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;
@@ -557,6 +598,13 @@ int resid_slabs_for(int K) {
   if (env == 4 || env == 6 || env == 8) return env;
   (void)K;
   return 4;  // measured (profiles/r02_notes.md): 6 / 8 slabs cost operand stages and buy nothing, even at K = 512
+}
+
+// Epilogue warps of the LayerNorm-fused GEMM.  RP_EPI_WARPS (4 / 8) overrides the choice for A/B runs.
+int epi_warps_for(int K) {
+  static const int env = getenv("RP_EPI_WARPS") ? atoi(getenv("RP_EPI_WARPS")) : 0;
+  if (env == 4 || env == 8) return env;
+  return K <= 512 ? 8 : 4;
 }
 
 template <int CG>
@@ -599,6 +647,8 @@ int launch_cg(int epilogue, const void* A, int64_t lda, const void* W, int64_t l
       return launch_one<EPI_BIAS_RESID_F32, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
     case EPI_BIAS_RESID_LN:
       if constexpr (CG == 2) {
+        // memory-bound instances (K <= 512: out-proj): eight epilogue warps, three slabs each, three operand stages
+        if (epi_warps_for(K) == 8) return launch_one<EPI_BIAS_RESID_LN, 2, 3, 0, 8>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
         switch (resid_slabs_for(K)) {
           case 8: return launch_one<EPI_BIAS_RESID_LN, 2, 8>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
           case 6: return launch_one<EPI_BIAS_RESID_LN, 2, 6>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
@@ -653,6 +703,12 @@ int launch_gemm_bwd(int kind, bool out_f32, const void* A, int64_t lda, const vo
            "gemm_bwd: N and the pitches must keep rows 16-byte aligned");
   RP_CHECK(kind == 3 || K % BK == 0, "gemm_bwd: dgrad needs K %% %d == 0", BK);
   RP_CHECK(splits >= 1 && splits <= (K + BK - 1) / BK, "gemm_bwd: bad split count %d", splits);
+  {
+    // every split must own at least one k-block (an empty one would never complete its accumulator barrier)
+    const int kb = (K + BK - 1) / BK, per = (kb + splits - 1) / splits;
+    RP_CHECK((splits - 1) * per < kb, "gemm_bwd: %d splits of %d k-blocks leave the last split empty (use %d)", splits,
+             per, (kb + per - 1) / per);
+  }
   RP_CHECK(splits == 1 || M % (2 * BM) == 0, "gemm_bwd: split-K needs M %% %d == 0", 2 * BM);
   RP_CHECK((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(D)) % 16 == 0,
            "gemm_bwd: pointers must be 16-byte aligned");

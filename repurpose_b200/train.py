@@ -1,5 +1,7 @@
-"""First pieces of the training step (BASELINE configs[4]; reference main.py:294-409): the
-memory-bound kernels around the (not yet written) GEMM / attention backward, behind small Python mirrors.
+"""The training step (BASELINE configs[4]; reference main.py:294-409) behind small Python mirrors:
+
+  TrainStep(model, lr, weight_decay).step(batch)      <- one iteration of main.py's loop: forward (train graph), masked
+                                                         focal loss / batch_size, backward, gradient all-reduce, Adam
 
   focal_loss_grad(masks, logits, labels, batch_size)  <- autograd of `model.losses(...)['cls_loss'] / batch_size`
   layernorm512_backward(x, dy, gamma)                 <- autograd of nn.LayerNorm(512)
@@ -7,8 +9,9 @@ memory-bound kernels around the (not yet written) GEMM / attention backward, beh
   allreduce_flat_(flat_grads, group)                  <- DDP's gradient averaging (utils/distributed.py:415-428):
                                                          ONE all-reduce over the flat gradient buffer
 
-All compute is in librepurpose_b200.so; there is no PyTorch fallback.  What a full step still needs is listed
-in DESIGN.md §7 (dgrad / wgrad GEMMs with MN-major operands, attention backward, dropout)."""
+All compute is in librepurpose_b200.so; there is no PyTorch fallback.  Deviation from the reference's training graph,
+listed in DESIGN.md §7: dropout (p = 0.1 in the encoder layers, the attention weights and the heads) is not applied —
+the step is the reference's with `dropout = 0`, which is also the graph the parity test differentiates with autograd."""
 from __future__ import annotations
 
 import torch
@@ -113,3 +116,290 @@ def allreduce_flat_(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
             dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
             flat_grad.div_(world)
     return flat_grad
+
+
+LOG2E_OVER_8 = 1.4426950408889634 / 8.0
+
+
+class TrainStep:
+    """One training iteration of the reference loop (main.py:318-368) on the device:
+
+        output = model(batch); loss = model.losses(*output)['cls_loss'] / batch_size
+        optimizer.zero_grad(); loss.backward(); optimizer.step()          (+ DDP's gradient averaging)
+
+    `model` is this package's MMCTransformer (reference state-dict schema).  Its parameters become views of one flat
+    fp32 master buffer (FlatAdam); a bf16 copy feeds the tensor-core GEMMs.  The forward keeps, per encoder layer, the
+    residual stream before each LayerNorm (fp32), the LayerNorm outputs, q|k|v, the attention output and its
+    log-sum-exp, and the ReLU output (bf16): 14.3 KB per token and layer.  The backward is autograd's chain written
+    out with rp_gemm_bwd / rp_fmha_bwd / rp_layernorm512_bwd_acc / rp_colsum_bf16 / rp_relu_bwd / rp_head_out_bwd.
+    reg_head receives no gradient in the reference (the loss is the focal classification term only,
+    models/MMCTransformer.py:159-179) — torch's Adam skips such parameters, and so does this step."""
+
+    def __init__(self, model, lr=1e-3, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, group=None):
+        self.model = model
+        self.cfg = c = model._cfg
+        if c["d_model"] != 512 or c["head_hidden"] != 256 or c["num_heads"] * 64 != c["d_model"]:
+            raise ValueError("TrainStep: kernels are specialised for d_model 512, heads of 64, head hidden 256")
+        named = [(n, p) for n, p in model.named_parameters()]
+        _cuda(named[0][1], "TrainStep")
+        self.dev = named[0][1].device
+        trainable = [(n, p) for n, p in named if not n.startswith("reg_head.")]
+        self.opt = FlatAdam([p for _, p in trainable], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                            bf16_copy=True)
+        self._index = {n: i for i, (n, _) in enumerate(trainable)}
+        self._frozen16 = {n: p.data.to(torch.bfloat16) for n, p in named if n.startswith("reg_head.") and p.dim() == 2}
+        self._frozen32 = {n: p.data for n, p in named if n.startswith("reg_head.")}
+        self.group = group
+        self.lib = _lib.load()
+        self._bufs = None
+        self._scratch = torch.empty(int(self.lib.rp_train_scratch_bytes()), dtype=torch.uint8, device=self.dev)
+        self._part = torch.empty(8 << 20, dtype=torch.float32, device=self.dev)  # split-K partials (32 MB)
+        L = c["num_layers"]
+        self._wqkv16 = [torch.empty(1536, 512, dtype=torch.bfloat16, device=self.dev) for _ in range(L)]
+        self._bqkv = [torch.empty(1536, dtype=torch.float32, device=self.dev) for _ in range(L)]
+        self.refresh_weights()
+
+    # ---- parameter views -------------------------------------------------------------------------------------
+    def w32(self, name):
+        return self._frozen32[name] if name in self._frozen32 else self.opt.params[self._index[name]].data
+
+    def w16(self, name):
+        if name in self._frozen16:
+            return self._frozen16[name]
+        pos, k = self.opt._slices[self._index[name]]
+        return self.opt.flat_bf16[pos:pos + k].view_as(self.opt.params[self._index[name]].data)
+
+    def grad(self, name):
+        return self.opt.grads_like(self._index[name])
+
+    def refresh_weights(self):
+        """bf16 operands after a parameter update: the flat copy, and in_proj with the q rows scaled by log2(e)/8."""
+        st, lib = cur_stream(), self.lib
+        with torch.cuda.device(self.dev):
+            check(lib.rp_cast_scaled(ptr(self.opt.flat), self.opt.flat.numel(), 0, 1.0, ptr(self.opt.flat_bf16), 0, st),
+                  "rp_cast_scaled")
+            for l in range(self.cfg["num_layers"]):
+                pre = f"multimodal_encoder.layers.{l}.self_attn."
+                check(lib.rp_cast_scaled(ptr(self.w32(pre + "in_proj_weight")), 1536 * 512, 512 * 512, LOG2E_OVER_8,
+                                         ptr(self._wqkv16[l]), 0, st), "rp_cast_scaled")
+                check(lib.rp_cast_scaled(ptr(self.w32(pre + "in_proj_bias")), 1536, 512, LOG2E_OVER_8, 0,
+                                         ptr(self._bqkv[l]), st), "rp_cast_scaled")
+
+    # ---- buffers -----------------------------------------------------------------------------------------------
+    def _buffers(self, B, T):
+        if self._bufs is not None and self._bufs["shape"] == (B, T):
+            return self._bufs
+        c, dev, M, L = self.cfg, self.dev, B * T, self.cfg["num_layers"]
+        f32 = dict(dtype=torch.float32, device=dev)
+        b16 = dict(dtype=torch.bfloat16, device=dev)
+        Cin = c["vis_dim"] + c["aud_dim"] + c["text_dim"]
+        d = dict(shape=(B, T))
+        d["xcat"] = torch.empty(M, Cin, **b16)
+        d["xproj"] = torch.empty(M, 512, **f32)
+        d["h"] = [torch.empty(M, 512, **f32) for _ in range(L + 1)]
+        d["hmid"] = [torch.empty(M, 512, **f32) for _ in range(L)]
+        d["u1"] = [torch.empty(M, 512, **b16) for _ in range(L + 1)]   # u1[L] = encoder_norm output
+        d["u2"] = [torch.empty(M, 512, **b16) for _ in range(L)]
+        d["qkv"] = [torch.empty(M, 1536, **b16) for _ in range(L)]
+        d["attn"] = [torch.empty(M, 512, **b16) for _ in range(L)]
+        d["ffn"] = [torch.empty(M, c["d_ff"], **b16) for _ in range(L)]
+        d["lse"] = [torch.empty(B, c["num_heads"], T, **f32) for _ in range(L)]
+        d["fm"] = torch.empty(M, 512, **f32)
+        d["feats"] = torch.empty(B, T, 512, **f32)
+        d["uc"], d["ur"] = torch.empty(M, 512, **b16), torch.empty(M, 512, **b16)
+        d["a1c"], d["a2c"] = torch.empty(M, 256, **b16), torch.empty(M, 256, **b16)
+        d["a1r"], d["a2r"] = torch.empty(M, 256, **b16), torch.empty(M, 256, **b16)
+        d["logits"] = torch.empty(B, T, 1, **f32)
+        d["offsets"] = torch.empty(B, T, 2, **f32)
+        # backward
+        d["dh"], d["dh16"] = torch.empty(M, 512, **f32), torch.empty(M, 512, **b16)
+        d["du"] = torch.empty(M, 512, **f32)                      # fp32 gradient entering a LayerNorm
+        d["dwide"] = torch.empty(M, c["d_ff"], **b16)             # dffn / dqkv / head activations' gradients
+        d["d512"] = torch.empty(M, 512, **b16)                    # dattn
+        d["dsum"] = torch.empty(B, c["num_heads"], T, **f32)
+        d["lens"] = torch.empty(B, dtype=torch.int32, device=dev)
+        self._bufs = d
+        return d
+
+    # ---- thin wrappers over the C ABI ------------------------------------------------------------------------------
+    def _gemm(self, epi, A, W, D, bias, resid=None):
+        M, K = A.shape
+        N = W.shape[0]
+        check(self.lib.rp_gemm_bf16(epi, ptr(A), K, ptr(W), K, ptr(D), N, ptr(bias), ptr(resid), N if resid is not None else 0,
+                                    M, N, K, cur_stream()), "rp_gemm_bf16")
+
+    def _ln(self, mode, x, M, T, g0, b0, g1=None, b1=None, g2=None, b2=None, pe=None, out_f32=None, y=None, y2=None):
+        check(self.lib.rp_layernorm512(mode, ptr(x), M, T, ptr(g0), ptr(b0), ptr(g1), ptr(b1), ptr(g2), ptr(b2), ptr(pe),
+                                       ptr(out_f32), ptr(y), ptr(y2), cur_stream()), "rp_layernorm512")
+
+    def _dgrad(self, dY, W, out):
+        """out[M, in] = dY[M, out] W[out, in]"""
+        M, Nout = dY.shape
+        Kin = W.shape[1]
+        check(self.lib.rp_gemm_bwd(1, 1 if out.dtype == torch.float32 else 0, ptr(dY), Nout, ptr(W), Kin, ptr(out), Kin,
+                                   M, Kin, Nout, 1, cur_stream()), "rp_gemm_bwd dgrad")
+
+    def _wgrad(self, dY, X, name):
+        """grad(name)[out, in] = dY[tok, out]^T X[tok, in];  grad(name bias)[out] = column sums of dY"""
+        tok, Nout = dY.shape
+        Kin = X.shape[1]
+        gw = self.grad(name + "weight") if name.endswith(".") else self.grad(name)
+        tiles = ((Nout + 255) // 256) * ((Kin + 255) // 256)
+        kblocks = (tok + 63) // 64
+        splits = max(1, min(kblocks, 74 // tiles, self._part.numel() // (Nout * Kin)))
+        per = (kblocks + splits - 1) // splits
+        splits = (kblocks + per - 1) // per          # no empty split
+        st = cur_stream()
+        if splits == 1:
+            check(self.lib.rp_gemm_bwd(3, 1, ptr(dY), Nout, ptr(X), Kin, ptr(gw), Kin, Nout, Kin, tok, 1, st), "rp_gemm_bwd wgrad")
+        else:
+            check(self.lib.rp_gemm_bwd(3, 1, ptr(dY), Nout, ptr(X), Kin, ptr(self._part), Kin, Nout, Kin, tok, splits, st),
+                  "rp_gemm_bwd wgrad")
+            check(self.lib.rp_splitk_reduce(ptr(self._part), splits, Nout * Kin, ptr(gw), st), "rp_splitk_reduce")
+
+    def _colsum(self, X, out):
+        M, N = X.shape
+        check(self.lib.rp_colsum_bf16(ptr(X), M, N, ptr(out), ptr(self._scratch), self._scratch.numel(), cur_stream()),
+              "rp_colsum_bf16")
+
+    def _ln_bwd(self, x, dy, prefix, dh, dh16, accumulate):
+        """dh (+)= LayerNorm backward of the branch `prefix` (…weight / …bias receive their gradients)"""
+        M = x.shape[0] if x.dim() == 2 else x.numel() // 512
+        if not accumulate:
+            dh.zero_()
+        check(self.lib.rp_layernorm512_bwd_acc(ptr(x), ptr(dy), ptr(self.w32(prefix + "weight")), M, 1e-5, ptr(dh), ptr(dh16),
+                                               ptr(self.grad(prefix + "weight")), ptr(self.grad(prefix + "bias")),
+                                               ptr(self._scratch), self._scratch.numel(), cur_stream()),
+              "rp_layernorm512_bwd_acc")
+
+    def _relu_bwd(self, dy, act):
+        check(self.lib.rp_relu_bwd(ptr(dy), ptr(act), dy.numel(), 1 if dy.dtype == torch.float32 else 0, cur_stream()),
+              "rp_relu_bwd")
+
+    # ---- forward (train graph, activations kept) -------------------------------------------------------------------
+    def forward(self, batch):
+        """-> the reference's 6-tuple (models/MMCTransformer.py:109-151), computed by the same kernels as inference but
+        with every tensor the backward needs kept (no in-place residual updates, no LayerNorm-in-GEMM fusion)."""
+        m, c, lib = self.model, self.cfg, self.lib
+        vis, aud, txt = (batch[k].to(self.dev, torch.float32).contiguous() for k in ("visual_feats", "audio_feats", "text_feats"))
+        B, T = vis.shape[0], vis.shape[1]
+        M, L, H = B * T, c["num_layers"], c["num_heads"]
+        d = self._buffers(B, T)
+        masks = batch["masks"].to(self.dev)
+        with torch.cuda.device(self.dev):
+            st = cur_stream()
+            lens = m._lens_from_masks(masks, B, T)
+            d["lens"].copy_(lens)
+            check(lib.rp_concat_cast(ptr(vis), ptr(aud), ptr(txt), c["vis_dim"], c["aud_dim"], c["text_dim"], ptr(d["xcat"]), M, st),
+                  "rp_concat_cast")
+            self._gemm(2, d["xcat"], self.w16("input_projection.weight"), d["xproj"], self.w32("input_projection.bias"))
+            pe = m.positional_encoding.pe[0]
+            lay = "multimodal_encoder.layers.{}."
+            self._ln(1, d["xproj"], M, T, self.w32("input_norm.weight"), self.w32("input_norm.bias"),
+                     self.w32(lay.format(0) + "norm1.weight"), self.w32(lay.format(0) + "norm1.bias"), pe=pe,
+                     out_f32=d["h"][0], y=d["u1"][0])
+            for l in range(L):
+                p = lay.format(l)
+                self._gemm(0, d["u1"][l], self._wqkv16[l], d["qkv"][l], self._bqkv[l])
+                q = d["qkv"][l]
+                check(lib.rp_fmha_train(ptr(q), ptr(q) + 1024, ptr(q) + 2048, ptr(d["attn"][l]), 1536, 512, B, H, T,
+                                        ptr(d["lens"]), ptr(d["lse"][l]), st), "rp_fmha_train")
+                self._gemm(3, d["attn"][l], self.w16(p + "self_attn.out_proj.weight"), d["hmid"][l],
+                           self.w32(p + "self_attn.out_proj.bias"), resid=d["h"][l])
+                self._ln(0, d["hmid"][l], M, T, self.w32(p + "norm2.weight"), self.w32(p + "norm2.bias"), y=d["u2"][l])
+                self._gemm(1, d["u2"][l], self.w16(p + "linear1.weight"), d["ffn"][l], self.w32(p + "linear1.bias"))
+                self._gemm(3, d["ffn"][l], self.w16(p + "linear2.weight"), d["h"][l + 1], self.w32(p + "linear2.bias"),
+                           resid=d["hmid"][l])
+                nxt = lay.format(l + 1) + "norm1." if l + 1 < L else "encoder_norm."
+                self._ln(0, d["h"][l + 1], M, T, self.w32(nxt + "weight"), self.w32(nxt + "bias"), y=d["u1"][l + 1])
+            self._gemm(2, d["u1"][L], self.w16("feature_map.0.weight"), d["fm"], self.w32("feature_map.0.bias"))
+            self._ln(2, d["fm"], M, T, self.w32("feature_map.1.weight"), self.w32("feature_map.1.bias"),
+                     self.w32("cls_head.0.weight"), self.w32("cls_head.0.bias"), self.w32("reg_head.0.weight"),
+                     self.w32("reg_head.0.bias"), out_f32=d["feats"], y=d["uc"], y2=d["ur"])
+            self._gemm(1, d["uc"], self.w16("cls_head.1.weight"), d["a1c"], self.w32("cls_head.1.bias"))
+            self._gemm(1, d["a1c"], self.w16("cls_head.4.weight"), d["a2c"], self.w32("cls_head.4.bias"))
+            self._gemm(1, d["ur"], self.w16("reg_head.1.weight"), d["a1r"], self.w32("reg_head.1.bias"))
+            self._gemm(1, d["a1r"], self.w16("reg_head.4.weight"), d["a2r"], self.w32("reg_head.4.bias"))
+            check(lib.rp_head_out(ptr(d["a2c"]), ptr(d["a2r"]), ptr(self.w32("cls_head.7.weight")), ptr(self.w32("cls_head.7.bias")),
+                                  ptr(self.w32("reg_head.7.weight")), ptr(self.w32("reg_head.7.bias")), ptr(d["logits"]),
+                                  ptr(d["offsets"]), M, st), "rp_head_out")
+        return masks, d["logits"], d["offsets"], batch.get("labels"), batch.get("segments"), d["feats"]
+
+    # ---- backward ----------------------------------------------------------------------------------------------------
+    def backward(self, dlogits):
+        """gradients of every trainable parameter into the flat gradient buffer, given d loss / d logits [B,T,1]"""
+        c, lib, d = self.cfg, self.lib, self._bufs
+        B, T = d["shape"]
+        M, L, H = B * T, c["num_layers"], c["num_heads"]
+        dh, dh16, du = d["dh"], d["dh16"], d["du"]
+        lay = "multimodal_encoder.layers.{}."
+        with torch.cuda.device(self.dev):
+            st = cur_stream()
+            # cls head: Linear(256,1) <- ReLU <- Linear(256,256) <- ReLU <- Linear(512,256) <- LayerNorm
+            da2 = d["dwide"].view(-1)[:M * 256].view(M, 256)
+            da1 = d["dwide"].view(-1)[M * 256:2 * M * 256].view(M, 256)
+            check(lib.rp_head_out_bwd(ptr(dlogits), ptr(d["a2c"]), ptr(self.w32("cls_head.7.weight")), M, ptr(da2),
+                                      ptr(self.grad("cls_head.7.weight")), ptr(self.grad("cls_head.7.bias")), ptr(self._scratch),
+                                      self._scratch.numel(), st), "rp_head_out_bwd")
+            self._wgrad(da2, d["a1c"], "cls_head.4.")
+            self._colsum(da2, self.grad("cls_head.4.bias"))
+            self._dgrad(da2, self.w16("cls_head.4.weight"), da1)
+            self._relu_bwd(da1, d["a1c"])
+            self._wgrad(da1, d["uc"], "cls_head.1.")
+            self._colsum(da1, self.grad("cls_head.1.bias"))
+            self._dgrad(da1, self.w16("cls_head.1.weight"), du)
+            feats = d["feats"].view(M, 512)
+            self._ln_bwd(feats, du, "cls_head.0.", dh, None, accumulate=False)       # dh = d loss / d feats
+            self._relu_bwd(dh, feats)                                                # feats = relu(LN(fm))
+            self._ln_bwd(d["fm"], dh, "feature_map.1.", du, dh16, accumulate=False)  # du = d fm, dh16 = its bf16 copy
+            self._wgrad(dh16, d["u1"][L], "feature_map.0.")
+            self._colsum(dh16, self.grad("feature_map.0.bias"))
+            self._dgrad(dh16, self.w16("feature_map.0.weight"), du)                  # du = d encoder_norm output
+            self._ln_bwd(d["h"][L], du, "encoder_norm.", dh, dh16, accumulate=False)
+            dffn, dattn = d["dwide"], d["d512"]
+            dqkv = d["dwide"].view(-1)[:M * 1536].view(M, 1536)
+            for l in range(L - 1, -1, -1):
+                p = lay.format(l)
+                # FFN: h_out = hmid + relu(u2 W1^T + b1) W2^T + b2
+                self._wgrad(dh16, d["ffn"][l], p + "linear2.")
+                self._colsum(dh16, self.grad(p + "linear2.bias"))
+                self._dgrad(dh16, self.w16(p + "linear2.weight"), dffn)
+                self._relu_bwd(dffn, d["ffn"][l])
+                self._wgrad(dffn, d["u2"][l], p + "linear1.")
+                self._colsum(dffn, self.grad(p + "linear1.bias"))
+                self._dgrad(dffn, self.w16(p + "linear1.weight"), du)
+                self._ln_bwd(d["hmid"][l], du, p + "norm2.", dh, dh16, accumulate=True)
+                # attention: hmid = h + attn Wo^T + bo
+                self._wgrad(dh16, d["attn"][l], p + "self_attn.out_proj.")
+                self._colsum(dh16, self.grad(p + "self_attn.out_proj.bias"))
+                self._dgrad(dh16, self.w16(p + "self_attn.out_proj.weight"), dattn)
+                q = d["qkv"][l]
+                check(lib.rp_fmha_bwd(ptr(q), ptr(q) + 1024, ptr(q) + 2048, ptr(d["attn"][l]), ptr(dattn), ptr(d["lse"][l]),
+                                      ptr(d["dsum"]), ptr(dqkv), ptr(dqkv) + 1024, ptr(dqkv) + 2048, 1536, 512, 1536, B, H, T,
+                                      ptr(d["lens"]), st), "rp_fmha_bwd")
+                self._wgrad(dqkv, d["u1"][l], p + "self_attn.in_proj_weight")
+                self._colsum(dqkv, self.grad(p + "self_attn.in_proj_bias"))
+                self._dgrad(dqkv, self.w16(p + "self_attn.in_proj_weight"), du)
+                self._ln_bwd(d["h"][l], du, p + "norm1.", dh, dh16, accumulate=True)
+            # h0 = LayerNorm(x W_in^T + b_in) + PE
+            self._ln_bwd(d["xproj"], dh, "input_norm.", du, dh16, accumulate=False)
+            self._wgrad(dh16, d["xcat"], "input_projection.")
+            self._colsum(dh16, self.grad("input_projection.bias"))
+
+    # ---- one iteration ------------------------------------------------------------------------------------------------
+    def loss_and_grads(self, batch, batch_size=None):
+        """forward + loss + backward (no parameter update): -> cls_loss / batch_size as a device scalar"""
+        out = self.forward(batch)
+        masks, logits, _, labels, _, _ = out
+        bs = int(batch_size if batch_size is not None else logits.shape[0])
+        loss = self.model.losses(*out)["cls_loss"] / bs
+        dlogits = focal_loss_grad(masks, logits, labels, batch_size=bs)
+        self.backward(dlogits)
+        return loss
+
+    def step(self, batch, batch_size=None):
+        loss = self.loss_and_grads(batch, batch_size)
+        allreduce_flat_(self.opt.grad, self.group)
+        self.opt.step()
+        self.refresh_weights()
+        return loss

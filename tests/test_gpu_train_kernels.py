@@ -164,3 +164,15 @@ def test_fmha_backward_matches_autograd(B, T, lens):
         assert err < 3e-2, (name, err)
     for b, n in enumerate(lens):   # padded keys receive exactly zero gradient
         assert (dqkv[b, n:, D:].float() == 0).all()
+
+
+def test_gemm_wgrad_refuses_an_empty_split():
+    """10 k-blocks in 6 splits of 2 would leave the sixth split without work (its accumulator barrier would never
+    complete): the launcher refuses instead of hanging."""
+    L, lib = _lib()
+    dy = torch.zeros(640, 512, dtype=torch.bfloat16, device=DEV)
+    x = torch.zeros(640, 512, dtype=torch.bfloat16, device=DEV)
+    part = torch.zeros(6 * 512, 512, device=DEV)
+    rc = lib.rp_gemm_bwd(3, 1, L.ptr(dy), 512, L.ptr(x), 512, L.ptr(part), 512, 512, 512, 640, 6, L.cur_stream())
+    assert rc != 0 and b"empty" in lib.rp_last_error()
+    L.check(lib.rp_gemm_bwd(3, 1, L.ptr(dy), 512, L.ptr(x), 512, L.ptr(part), 512, 512, 512, 640, 5, L.cur_stream()), "wgrad")

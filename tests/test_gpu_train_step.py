@@ -1,0 +1,119 @@
+"""The training step end to end (BASELINE configs[4]): loss and EVERY parameter gradient of
+`TrainStep` against torch.autograd over the fp32 restatement of the reference graph (oracle/mmct.py — and over the
+reference's own module from oracle/_ref where it is staged), the reference's `losses()` / `/ batch_size` scaling
+(main.py:326), then whole iterations: Adam moves the parameters and the loss on a fixed batch goes down."""
+import pytest
+import torch
+
+from oracle import build_ref, mmct, synth
+from oracle import losses as ol
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _setup(layers, lens, seed):
+    from repurpose_b200.models.MMCTransformer import MMCTransformer
+    torch.manual_seed(seed)
+    cfg = dict(synth.MODEL_CFG, self_num_layers=layers)
+    model = MMCTransformer(**cfg).to(DEV)
+    batch = synth.make_batch(lens, seed=seed + 1)
+    g = torch.Generator().manual_seed(seed + 2)
+    batch["labels"] = (torch.rand(len(lens), max(lens), generator=g) < 0.3).float()
+    batch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    return cfg, model, batch
+
+
+def _autograd_reference(sd, batch, B, autocast=False):
+    """loss and gradients of the reference graph by torch.autograd: fp32 (the bar), or under torch's own bf16 autocast
+    (the yardstick: what ANY bf16 tensor-core forward/backward of this graph loses against fp32)."""
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and not k.endswith(".pe")) for k, v in sd.items()}
+    with torch.enable_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        logits, _, _ = mmct.forward.__wrapped__(sd, batch)
+        loss = ol.losses(batch["masks"], logits.float(), batch["labels"]) / B
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in sd.items()}
+
+
+def _check_grads(ts, ref_grads, amp_grads=None, floor=2e-2):
+    """every trainable parameter: cosine to the fp32 gradient >= 0.99 and relative L2 error <= `floor`, or — where the
+    bf16 noise of this graph is larger than that (the input projection after 16 layers) — <= 1.3 x the error torch's
+    own bf16 autocast makes on the same parameter.  Measured (profiles/r02_train_grad_parity_*.txt): ours ~= autocast."""
+    rows = []
+    for name, p in ts.model.named_parameters():
+        ref = ref_grads[name]
+        if name.startswith("reg_head."):
+            assert ref is None or float(ref.abs().max()) == 0.0, name   # the focal loss never reaches reg_head
+            continue
+        got = ts.grad(name)
+        assert got.shape == ref.shape, name
+        l2 = float((got - ref).norm() / ref.norm())
+        cos = float((got * ref).sum() / (got.norm() * ref.norm()))
+        amp = float((amp_grads[name].float() - ref).norm() / ref.norm()) if amp_grads is not None else 0.0
+        rows.append((l2, cos, amp, name))
+    rows.sort(reverse=True)
+    print("largest relative L2 gradient errors (ours, cosine, torch bf16 autocast):",
+          [(round(a, 4), round(c, 5), round(m, 4), n) for a, c, m, n in rows[:5]])
+    for l2, cos, amp, name in rows:
+        assert cos >= 0.99, (name, cos)
+        assert l2 <= max(floor, 1.3 * amp), (name, l2, amp)
+
+
+@pytest.mark.parametrize("layers,lens", [(2, [300, 170]), (16, [700, 413])])
+def test_gradients_match_autograd_of_the_reference_graph(layers, lens):
+    from repurpose_b200.train import TrainStep
+    cfg, model, batch = _setup(layers, lens, seed=5 + layers)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    B = len(lens)
+    ts = TrainStep(model, lr=1e-3)
+    loss = ts.loss_and_grads(batch, batch_size=B)
+    ref_loss, ref_grads = _autograd_reference(sd, batch, B)
+    _, amp_grads = _autograd_reference(sd, batch, B, autocast=True)
+    assert abs(float(loss) - float(ref_loss)) <= 2e-2 * abs(float(ref_loss)), (float(loss), float(ref_loss))
+    _check_grads(ts, ref_grads, amp_grads)
+    # deterministic: a second pass over the same batch gives bit-identical gradients
+    g1 = ts.opt.grad.clone()
+    ts.loss_and_grads(batch, batch_size=B)
+    assert torch.equal(g1, ts.opt.grad)
+
+
+def test_gradients_match_the_staged_reference_module():
+    """the reference's own MMCTransformer (oracle/_ref, unmodified): eval() switches its dropout off, autograd on
+    — loss = model.losses(*model(batch))['cls_loss'] / batch_size; backward() exactly as main.py:318-333"""
+    ref = build_ref.import_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref not staged")
+    from repurpose_b200.train import TrainStep
+    cfg, model, batch = _setup(2, [260, 133], seed=21)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    rmodel = ref.MMCTransformer(**cfg).to(DEV)
+    rmodel.load_state_dict(sd)
+    rmodel.eval()
+    B = 2
+    out = rmodel(batch)
+    rloss = rmodel.losses(*out)["cls_loss"] / B
+    rloss.backward()
+    ts = TrainStep(model, lr=1e-3)
+    loss = ts.loss_and_grads(batch, batch_size=B)
+    assert abs(float(loss) - float(rloss)) <= 2e-2 * abs(float(rloss))
+    _, amp_grads = _autograd_reference(sd, batch, B, autocast=True)
+    _check_grads(ts, {n: p.grad for n, p in rmodel.named_parameters()}, amp_grads)
+
+
+def test_training_iterations_reduce_the_loss_and_update_inference():
+    from repurpose_b200.train import TrainStep
+    cfg, model, batch = _setup(2, [256, 200], seed=33)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    ts = TrainStep(model, lr=3e-4)
+    losses = [float(ts.step(batch)) for _ in range(8)]
+    print("loss per iteration:", [round(x, 4) for x in losses])
+    assert losses[-1] < 0.8 * losses[0], losses
+    moved = [n for n, p in model.named_parameters() if not torch.equal(p.detach(), before[n])]
+    assert all(n.startswith("reg_head.") == False for n in moved) and len(moved) == len(before) - 8
+    # the module's inference path sees the trained weights (same tensors, re-packed on the next forward)
+    model.eval()
+    model._invalidate()
+    _, logits, _, _, _, _ = model(batch)
+    _, tl, _, _, _, _ = ts.forward(batch)
+    valid = batch["masks"][:, 0, :]
+    assert (logits[valid] - tl[valid]).abs().max().item() < 3e-2 * tl[valid].abs().max().item()
