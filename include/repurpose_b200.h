@@ -174,8 +174,10 @@ int32_t rp_adam_step(float* param, const float* grad, float* exp_avg, float* exp
  *      i.e. torch.autograd over models/MMCTransformer.py:109-151).  bf16 tensor-core GEMMs with fp32 accumulation,
  *      fp32 gradients, every reduction in a fixed order (no atomics).
  * rp_train_scratch_bytes   size of the scratch buffer the two-stage reductions below need
- * rp_layernorm512_bwd_acc  autograd of nn.LayerNorm(512) on a pre-LN branch: dh_inout += dx; dh_bf16 (optional) =
- *                          bf16 copy of the updated dh (the operand of the next dgrad / wgrad GEMMs)
+ * rp_layernorm512_bwd_acc  autograd of nn.LayerNorm(512) on a pre-LN branch: dh_inout (+)= dx (accumulate != 0: +=);
+ *                          dh_bf16 (optional) = bf16 copy of the resulting dh (the operand of the next dgrad / wgrad
+ *                          GEMMs); dh_colsum (optional) = its column sums [512] = the bias gradient of the Linear
+ *                          whose output gradient dh is
  * rp_gemm_bwd              autograd of nn.Linear: kind 1 (dgrad) D[M,N] = A[M,K] B[K,N] with B the weight [out=K, in=N]
  *                          as stored; kind 3 (wgrad) D[M,N] = A[K,M]^T B[K,N] with A = dY [tokens, out], B = X [tokens, in]
  *                          (K = tokens, any count); out_f32 != 0: fp32 D, else bf16; splits > 1: split-K partials
@@ -194,14 +196,17 @@ int32_t rp_cast_scaled(const float* in, int64_t n, int64_t n_scaled, float scale
                        void* stream);
 int64_t rp_train_scratch_bytes(void);
 int32_t rp_layernorm512_bwd_acc(const float* x, const float* dy, const float* gamma, int64_t M, float eps,
-                                float* dh_inout, void* dh_bf16, float* dgamma, float* dbeta, void* scratch,
-                                int64_t scratch_bytes, void* stream);
+                                int32_t accumulate, float* dh_inout, void* dh_bf16, float* dh_colsum, float* dgamma,
+                                float* dbeta, void* scratch, int64_t scratch_bytes, void* stream);
 int32_t rp_gemm_bwd(int32_t kind, int32_t out_f32, const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
                     int64_t ldd, int32_t M, int32_t N, int32_t K, int32_t splits, void* stream);
 int32_t rp_splitk_reduce(const float* partials, int32_t splits, int64_t n, float* out, void* stream);
 int32_t rp_colsum_bf16(const void* x, int64_t M, int32_t N, float* out, void* scratch, int64_t scratch_bytes,
                        void* stream);
 int32_t rp_relu_bwd(void* dy, const void* act, int64_t n, int32_t is_f32, void* stream);
+/* rp_relu_bwd followed by rp_colsum_bf16 in one pass: the ReLU mask and the bias gradient of the Linear in front of it */
+int32_t rp_relu_bwd_colsum(void* dy_bf16, const void* act_bf16, int64_t M, int32_t N, float* colsum, void* scratch,
+                           int64_t scratch_bytes, void* stream);
 int32_t rp_head_out_bwd(const float* dlogits, const void* a2_bf16, const float* w, int64_t M, void* da2_bf16,
                         float* dw, float* db, void* scratch, int64_t scratch_bytes, void* stream);
 int32_t rp_fmha_train(const void* q, const void* k, const void* v, void* o, int64_t ld_qkv, int64_t ld_o, int32_t B,

@@ -48,11 +48,13 @@ SIGNATURES = {
     "rp_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_vp]),
     "rp_train_scratch_bytes": (c_i64, []),
     "rp_cast_scaled": (c_i32, [c_vp, c_i64, c_i64, c_f32, c_vp, c_vp, c_vp]),
-    "rp_layernorm512_bwd_acc": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "rp_layernorm512_bwd_acc": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
+                                        c_vp]),
     "rp_gemm_bwd": (c_i32, [c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "rp_splitk_reduce": (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp]),
     "rp_colsum_bf16": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "rp_relu_bwd": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp]),
+    "rp_relu_bwd_colsum": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "rp_head_out_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "rp_fmha_train": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "rp_fmha_bwd": (c_i32, [c_vp] * 10 + [c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]),

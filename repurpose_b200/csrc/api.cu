@@ -552,12 +552,12 @@ int32_t rp_cast_scaled(const float* in, int64_t n, int64_t n_scaled, float scale
 int64_t rp_train_scratch_bytes(void) { return train_scratch_floats() * int64_t(sizeof(float)); }
 
 int32_t rp_layernorm512_bwd_acc(const float* x, const float* dy, const float* gamma, int64_t M, float eps,
-                                float* dh_inout, void* dh_bf16, float* dgamma, float* dbeta, void* scratch,
-                                int64_t scratch_bytes, void* stream) {
+                                int32_t accumulate, float* dh_inout, void* dh_bf16, float* dh_colsum, float* dgamma,
+                                float* dbeta, void* scratch, int64_t scratch_bytes, void* stream) {
   RP_CHECK(x && dy && gamma && dh_inout && dgamma && dbeta && scratch, "rp_layernorm512_bwd_acc: null argument");
   RP_CHECK(scratch_bytes >= rp_train_scratch_bytes(), "rp_layernorm512_bwd_acc: scratch too small");
   return launch_layernorm512_bwd(x, dy, gamma, M, eps, dh_inout, dgamma, dbeta, reinterpret_cast<float*>(scratch),
-                                 reinterpret_cast<cudaStream_t>(stream), true, dh_bf16);
+                                 reinterpret_cast<cudaStream_t>(stream), accumulate != 0, dh_bf16, dh_colsum);
 }
 
 int32_t rp_gemm_bwd(int32_t kind, int32_t out_f32, const void* A, int64_t lda, const void* B, int64_t ldb, void* D,
@@ -582,6 +582,14 @@ int32_t rp_colsum_bf16(const void* x, int64_t M, int32_t N, float* out, void* sc
 int32_t rp_relu_bwd(void* dy, const void* act, int64_t n, int32_t is_f32, void* stream) {
   RP_CHECK(dy && act, "rp_relu_bwd: null argument");
   return launch_relu_bwd(dy, act, n, is_f32 != 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_relu_bwd_colsum(void* dy_bf16, const void* act_bf16, int64_t M, int32_t N, float* colsum, void* scratch,
+                           int64_t scratch_bytes, void* stream) {
+  RP_CHECK(dy_bf16 && act_bf16 && colsum && scratch, "rp_relu_bwd_colsum: null argument");
+  RP_CHECK(scratch_bytes >= rp_train_scratch_bytes(), "rp_relu_bwd_colsum: scratch too small");
+  return launch_relu_bwd_colsum(dy_bf16, act_bf16, M, N, colsum, reinterpret_cast<float*>(scratch),
+                                reinterpret_cast<cudaStream_t>(stream));
 }
 
 int32_t rp_head_out_bwd(const float* dlogits, const void* a2_bf16, const float* w, int64_t M, void* da2_bf16,

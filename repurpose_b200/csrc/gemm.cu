@@ -43,8 +43,8 @@ constexpr int MAX_SLABS = 8;  // barriers reserved per epilogue warp
 
 // Shared-memory budget per (epilogue kind, CTA-group size): the residual epilogue trades operand
 // stages for a deeper slab ring (loads and stores both live there).
-// RS = slabs per epilogue warp of the residual epilogues (4, 6 or 8): RS - 2 residual chunks of 4 KB are in
-// flight per warp.  A memory-bound problem (K = 512: out-proj) wants the deeper ring more than operand stages.
+// RS = slabs per epilogue warp of the residual epilogues: RS - 2 residual chunks of 4 KB are in flight per warp
+// (4 with four epilogue warps, 3 with eight; 6 and 8 were measured and lost operand stages for nothing).
 // EW = epilogue warps (4, or 8 for the LayerNorm-fused epilogue of memory-bound problems): with 8, two warps share a
 // TMEM lane quarter and each walks half of the tile's columns, so two dependent chunk chains per SM sub-partition
 // overlap instead of one (profiles/r02_notes.md: the 4-warp epilogue is latency-, not bandwidth-bound).
@@ -592,21 +592,6 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   return RP_OK;
 }
 
-// Slabs per epilogue warp of the residual epilogues.  RP_RESID_SLABS (4 / 6 / 8) overrides the choice for A/B runs.
-int resid_slabs_for(int K) {
-  static const int env = getenv("RP_RESID_SLABS") ? atoi(getenv("RP_RESID_SLABS")) : 0;
-  if (env == 4 || env == 6 || env == 8) return env;
-  (void)K;
-  return 4;  // measured (profiles/r02_notes.md): 6 / 8 slabs cost operand stages and buy nothing, even at K = 512
-}
-
-// Epilogue warps of the LayerNorm-fused GEMM.  RP_EPI_WARPS (4 / 8) overrides the choice for A/B runs.
-int epi_warps_for(int K) {
-  static const int env = getenv("RP_EPI_WARPS") ? atoi(getenv("RP_EPI_WARPS")) : 0;
-  if (env == 4 || env == 8) return env;
-  return K <= 512 ? 8 : 4;
-}
-
 template <int CG>
 int launch_cg(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd,
               const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
@@ -640,20 +625,13 @@ int launch_cg(int epilogue, const void* A, int64_t lda, const void* W, int64_t l
     case EPI_BIAS_BF16: return launch_one<EPI_BIAS_BF16, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
     case EPI_BIAS_RELU_BF16: return launch_one<EPI_BIAS_RELU_BF16, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
     case EPI_BIAS_F32: return launch_one<EPI_BIAS_F32, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
-    case EPI_BIAS_RESID_F32:
-      if constexpr (CG == 2) {
-        if (resid_slabs_for(K) >= 6) return launch_one<EPI_BIAS_RESID_F32, 2, 6>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
-      }
-      return launch_one<EPI_BIAS_RESID_F32, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
+    case EPI_BIAS_RESID_F32: return launch_one<EPI_BIAS_RESID_F32, CG>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
     case EPI_BIAS_RESID_LN:
       if constexpr (CG == 2) {
-        // memory-bound instances (K <= 512: out-proj): eight epilogue warps, three slabs each, three operand stages
-        if (epi_warps_for(K) == 8) return launch_one<EPI_BIAS_RESID_LN, 2, 3, 0, 8>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
-        switch (resid_slabs_for(K)) {
-          case 8: return launch_one<EPI_BIAS_RESID_LN, 2, 8>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
-          case 6: return launch_one<EPI_BIAS_RESID_LN, 2, 6>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
-          default: return launch_one<EPI_BIAS_RESID_LN, 2, 4>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
-        }
+        // memory-bound instances (K <= 512: out-proj): eight epilogue warps with three slabs each and three operand
+        // stages (92 -> 84 us); compute-bound ones (FF2) keep four warps, four slabs and five stages
+        if (K <= 512) return launch_one<EPI_BIAS_RESID_LN, 2, 3, 0, 8>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
+        return launch_one<EPI_BIAS_RESID_LN, 2, 4>(tmA, tmB, tmD, tmR, tmU, g, groups, stream);
       }
       set_last_error("gemm: the LayerNorm-fused epilogue needs CTA pairs");
       return RP_ERR_INVALID;

@@ -135,10 +135,11 @@ int launch_focal_loss_grad(const float* logits, const float* targets, const uint
 // LayerNorm over rows of 512: dx [M,512], dgamma [512], dbeta [512] from x, dy, gamma; scratch: fp32,
 // layernorm512_bwd_scratch_floats() values
 int64_t layernorm512_bwd_scratch_floats();
-// accumulate: dx += (the residual stream's gradient); dx_bf16 (optional): bf16 copy of the final dx
+// accumulate: dx += (the residual stream's gradient); dx_bf16 (optional): bf16 copy of the final dx; dx_colsum
+// (optional): column sums [512] of the final dx = the bias gradient of the Linear whose output gradient dx is
 int launch_layernorm512_bwd(const float* x, const float* dy, const float* gamma, int64_t M, float eps, float* dx,
                             float* dgamma, float* dbeta, float* scratch, cudaStream_t stream, bool accumulate = false,
-                            void* dx_bf16 = nullptr);
+                            void* dx_bf16 = nullptr, float* dx_colsum = nullptr);
 // one torch.optim.Adam step (L2 weight decay added to the gradient) on a flat fp32 buffer; p_bf16 (optional): bf16 copy
 int launch_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                      float eps, float weight_decay, int step, void* p_bf16, cudaStream_t stream);
@@ -152,6 +153,8 @@ int64_t train_scratch_floats();
 int launch_colsum_bf16(const void* x, int64_t M, int N, float* out, float* scratch, cudaStream_t stream);
 // dy = act > 0 ? dy : 0, in place; f32: both fp32, else both bf16; n % 8 == 0
 int launch_relu_bwd(void* dy, const void* act, int64_t n, bool f32, cudaStream_t stream);
+// the same for bf16 [M, N] fused with the bias gradient: colsum[N] = column sums of the masked dy
+int launch_relu_bwd_colsum(void* dy, const void* act, int64_t M, int N, float* colsum, float* scratch, cudaStream_t stream);
 // last cls_head layer: da2[M,256] bf16 = dlogit[m] w[c] where a2 > 0, dw[256], db[1]
 int launch_head_out_bwd(const float* dlogit, const void* a2, const float* w, int64_t M, void* da2, float* dw, float* db,
                         float* scratch, cudaStream_t stream);

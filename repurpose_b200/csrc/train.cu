@@ -47,27 +47,33 @@ __global__ void focal_loss_grad_kernel(const float* __restrict__ logits, const f
 // block; a second kernel adds the partials in a fixed order (deterministic, no atomics).
 constexpr int LNB_WARPS = 8;
 
-__global__ void __launch_bounds__(LNB_WARPS * 32)
+__global__ void __launch_bounds__(LNB_WARPS * 32, 2)
 layernorm512_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
                         int64_t M, float eps, float* __restrict__ dx, float* __restrict__ part_g,
-                        float* __restrict__ part_b, int accumulate, __nv_bfloat16* __restrict__ dx_bf16) {
+                        float* __restrict__ part_b, int accumulate, __nv_bfloat16* __restrict__ dx_bf16,
+                        float* __restrict__ part_c) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float acc_g[16], acc_b[16], gm[16];
+  float acc_g[16], acc_b[16], acc_c[16];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
-    gm[4 * i] = g4.x; gm[4 * i + 1] = g4.y; gm[4 * i + 2] = g4.z; gm[4 * i + 3] = g4.w;
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) acc_g[i] = acc_b[i] = 0.0f;
+  for (int i = 0; i < 16; ++i) acc_g[i] = acc_b[i] = acc_c[i] = 0.0f;
   for (int64_t row = int64_t(blockIdx.x) * LNB_WARPS + warp; row < M; row += int64_t(gridDim.x) * LNB_WARPS) {
-    float xv[16], dv[16];
+    float xv[16], dv[16], old[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {  // lane owns columns 4 (32 i + lane) .. + 3: coalesced 512-byte requests
-      const float4 a = __ldg(reinterpret_cast<const float4*>(x + row * 512) + i * 32 + lane);
-      const float4 d = __ldg(reinterpret_cast<const float4*>(dy + row * 512) + i * 32 + lane);
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(x + row * 512) + i * 32 + lane);
+      const float4 d = __ldcs(reinterpret_cast<const float4*>(dy + row * 512) + i * 32 + lane);
       xv[4 * i] = a.x; xv[4 * i + 1] = a.y; xv[4 * i + 2] = a.z; xv[4 * i + 3] = a.w;
       dv[4 * i] = d.x; dv[4 * i + 1] = d.y; dv[4 * i + 2] = d.z; dv[4 * i + 3] = d.w;
+    }
+    if (accumulate) {  // the residual stream's gradient so far, requested together with x and dy
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 o = *(reinterpret_cast<const float4*>(dx + row * 512) + i * 32 + lane);
+        old[4 * i] = o.x; old[4 * i + 1] = o.y; old[4 * i + 2] = o.z; old[4 * i + 3] = o.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) old[i] = 0.0f;
     }
     float s = 0.0f;
 #pragma unroll
@@ -86,13 +92,19 @@ layernorm512_bwd_kernel(const float* __restrict__ x, const float* __restrict__ d
     const float rstd = rsqrtf(v * (1.0f / 512.0f) + eps);
     float s1 = 0.0f, s2 = 0.0f;  // sum(dy gamma), sum(dy gamma xhat)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      xv[i] *= rstd;  // xhat
-      acc_b[i] += dv[i];
-      acc_g[i] = fmaf(dv[i], xv[i], acc_g[i]);
-      dv[i] *= gm[i];
-      s1 += dv[i];
-      s2 = fmaf(dv[i], xv[i], s2);
+    for (int i = 0; i < 4; ++i) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+      const float gm[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = 4 * i + e;
+        xv[k] *= rstd;  // xhat
+        acc_b[k] += dv[k];
+        acc_g[k] = fmaf(dv[k], xv[k], acc_g[k]);
+        dv[k] *= gm[e];
+        s1 += dv[k];
+        s2 = fmaf(dv[k], xv[k], s2);
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -104,16 +116,12 @@ layernorm512_bwd_kernel(const float* __restrict__ x, const float* __restrict__ d
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float4 o4;
-      o4.x = rstd * (dv[4 * i] - s1 - xv[4 * i] * s2);
-      o4.y = rstd * (dv[4 * i + 1] - s1 - xv[4 * i + 1] * s2);
-      o4.z = rstd * (dv[4 * i + 2] - s1 - xv[4 * i + 2] * s2);
-      o4.w = rstd * (dv[4 * i + 3] - s1 - xv[4 * i + 3] * s2);
-      float4* dst = reinterpret_cast<float4*>(dx + row * 512) + i * 32 + lane;
-      if (accumulate) {  // the residual stream's gradient: dh += d(LN branch)
-        const float4 old = *dst;
-        o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
-      }
-      *dst = o4;
+      o4.x = old[4 * i] + rstd * (dv[4 * i] - s1 - xv[4 * i] * s2);
+      o4.y = old[4 * i + 1] + rstd * (dv[4 * i + 1] - s1 - xv[4 * i + 1] * s2);
+      o4.z = old[4 * i + 2] + rstd * (dv[4 * i + 2] - s1 - xv[4 * i + 2] * s2);
+      o4.w = old[4 * i + 3] + rstd * (dv[4 * i + 3] - s1 - xv[4 * i + 3] * s2);
+      *(reinterpret_cast<float4*>(dx + row * 512) + i * 32 + lane) = o4;
+      acc_c[4 * i] += o4.x; acc_c[4 * i + 1] += o4.y; acc_c[4 * i + 2] += o4.z; acc_c[4 * i + 3] += o4.w;
       if (dx_bf16 != nullptr) {
         uint2 pk;
         pk.x = pack_bf16x2(o4.x, o4.y);
@@ -122,37 +130,40 @@ layernorm512_bwd_kernel(const float* __restrict__ x, const float* __restrict__ d
       }
     }
   }
-  __shared__ float sg[LNB_WARPS][512], sb[LNB_WARPS][512];
+  // per-block partials of dgamma, dbeta and (optional) the column sums of the final dx: one pass through shared
+  // memory per quantity (16 KB), summed over the 8 warps in a fixed order
+  __shared__ float sred[LNB_WARPS][512];
+  auto block_reduce = [&](const float (&acc)[16], float* part) {
+    __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int col = 4 * (32 * (i >> 2) + lane) + (i & 3);
-    sg[warp][col] = acc_g[i];
-    sb[warp][col] = acc_b[i];
-  }
-  __syncthreads();
-  for (int col = threadIdx.x; col < 512; col += blockDim.x) {
-    float g = 0.0f, b = 0.0f;
+    for (int i = 0; i < 16; ++i) sred[warp][4 * (32 * (i >> 2) + lane) + (i & 3)] = acc[i];
+    __syncthreads();
+    for (int col = threadIdx.x; col < 512; col += blockDim.x) {
+      float t = 0.0f;
 #pragma unroll
-    for (int w = 0; w < LNB_WARPS; ++w) {
-      g += sg[w][col];
-      b += sb[w][col];
+      for (int w = 0; w < LNB_WARPS; ++w) t += sred[w][col];
+      part[int64_t(blockIdx.x) * 512 + col] = t;
     }
-    part_g[int64_t(blockIdx.x) * 512 + col] = g;
-    part_b[int64_t(blockIdx.x) * 512 + col] = b;
-  }
+  };
+  block_reduce(acc_g, part_g);
+  block_reduce(acc_b, part_b);
+  if (part_c != nullptr) block_reduce(acc_c, part_c);
 }
 
 __global__ void layernorm512_bwd_reduce_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b,
-                                               int parts, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                               const float* __restrict__ part_c, int parts, float* __restrict__ dgamma,
+                                               float* __restrict__ dbeta, float* __restrict__ dcol) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= 512) return;
-  float g = 0.0f, b = 0.0f;
+  float g = 0.0f, b = 0.0f, c = 0.0f;
   for (int p = 0; p < parts; ++p) {
     g += part_g[int64_t(p) * 512 + col];
     b += part_b[int64_t(p) * 512 + col];
+    if (part_c != nullptr) c += part_c[int64_t(p) * 512 + col];
   }
   dgamma[col] = g;
   dbeta[col] = b;
+  if (dcol != nullptr) dcol[col] = c;
 }
 
 // ---- Adam (torch.optim.Adam, weight_decay as L2 added to the gradient, no amsgrad) ---------------------------
@@ -231,6 +242,44 @@ __global__ void relu_bwd_bf16_kernel(__nv_bfloat16* __restrict__ dy, const __nv_
   d.x = mask2(d.x, a.x); d.y = mask2(d.y, a.y); d.z = mask2(d.z, a.z); d.w = mask2(d.w, a.w);
   reinterpret_cast<uint4*>(dy)[i] = d;
 }
+// ReLU backward fused with the bias gradient of the Linear in front of the ReLU: dy = act > 0 ? dy : 0 in place and
+// per-block partial column sums of the masked dy (block = a strip of rows, thread = groups of 8 consecutive columns)
+__global__ void __launch_bounds__(256)
+relu_bwd_colsum_bf16_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ act, int64_t M, int N,
+                            int64_t rows_per, float* __restrict__ part) {
+  const int64_t r0 = int64_t(blockIdx.x) * rows_per;
+  const int64_t r1 = r0 + rows_per < M ? r0 + rows_per : M;
+  const int groups = N >> 3;
+  for (int cg = threadIdx.x; cg < groups; cg += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    auto one = [&](int64_t r) {
+      uint4* dp = reinterpret_cast<uint4*>(dy + r * N) + cg;
+      uint4 d = *dp;
+      const uint4 a = __ldcs(reinterpret_cast<const uint4*>(act + r * N) + cg);
+      uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t lo = (aw[i] & 0x8000u) == 0u && (aw[i] & 0x7fffu) != 0u ? 0xffffu : 0u;
+        const uint32_t hi = (aw[i] & 0x80000000u) == 0u && (aw[i] & 0x7fff0000u) != 0u ? 0xffff0000u : 0u;
+        dw[i] &= (lo | hi);
+        acc[2 * i] += __uint_as_float(dw[i] << 16);
+        acc[2 * i + 1] += __uint_as_float(dw[i] & 0xffff0000u);
+      }
+      *dp = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+    };
+    int64_t r = r0;
+    for (; r + 3 < r1; r += 4) {
+      one(r); one(r + 1); one(r + 2); one(r + 3);
+    }
+    for (; r < r1; ++r) one(r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[int64_t(blockIdx.x) * N + 8 * cg + i] = acc[i];
+  }
+}
+
 __global__ void relu_bwd_f32_kernel(float* __restrict__ dy, const float* __restrict__ act, int64_t n4) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
@@ -305,21 +354,22 @@ int launch_focal_loss_grad(const float* logits, const float* targets, const uint
   return RP_OK;
 }
 
-int64_t layernorm512_bwd_scratch_floats() { return int64_t(2) * 4 * num_sms() * 512; }
+int64_t layernorm512_bwd_scratch_floats() { return int64_t(3) * 2 * num_sms() * 512; }
 
 int launch_layernorm512_bwd(const float* x, const float* dy, const float* gamma, int64_t M, float eps, float* dx,
                             float* dgamma, float* dbeta, float* scratch, cudaStream_t stream, bool accumulate,
-                            void* dx_bf16) {
+                            void* dx_bf16, float* dx_colsum) {
   RP_CHECK(M > 0, "layernorm512_bwd: empty");
   const int sms = num_sms();
-  int grid = 4 * sms;
+  int grid = 2 * sms;  // two resident blocks per SM walk the rows
   if (int64_t(grid) * LNB_WARPS > M) grid = int((M + LNB_WARPS - 1) / LNB_WARPS);
   float* part_g = scratch;
-  float* part_b = scratch + int64_t(4) * sms * 512;
+  float* part_b = scratch + int64_t(2) * sms * 512;
+  float* part_c = dx_colsum != nullptr ? scratch + int64_t(4) * sms * 512 : nullptr;
   layernorm512_bwd_kernel<<<grid, LNB_WARPS * 32, 0, stream>>>(x, dy, gamma, M, eps, dx, part_g, part_b,
                                                                accumulate ? 1 : 0,
-                                                               reinterpret_cast<__nv_bfloat16*>(dx_bf16));
-  layernorm512_bwd_reduce_kernel<<<4, 128, 0, stream>>>(part_g, part_b, grid, dgamma, dbeta);
+                                                               reinterpret_cast<__nv_bfloat16*>(dx_bf16), part_c);
+  layernorm512_bwd_reduce_kernel<<<4, 128, 0, stream>>>(part_g, part_b, part_c, grid, dgamma, dbeta, dx_colsum);
   count_launch(2);
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;
@@ -348,7 +398,7 @@ int launch_splitk_reduce(const float* part, int splits, int64_t n, float* out, c
 
 // one scratch size for every two-stage reduction of the backward pass (LayerNorm 2 x 4 SMs x 512, column sums
 // <= 4 SMs x 256 per column block, head_out_bwd 4 SMs x 257 + 257)
-int64_t train_scratch_floats() { return int64_t(4) * num_sms() * 1024 + 1024; }
+int64_t train_scratch_floats() { return int64_t(4) * num_sms() * 1024 + 1024; }  // >= 3 x 2 SMs x 512 of the LayerNorm backward
 
 int launch_colsum_bf16(const void* x, int64_t M, int N, float* out, float* scratch, cudaStream_t stream) {
   RP_CHECK(M > 0 && N > 0, "colsum: empty");
@@ -374,6 +424,24 @@ int launch_relu_bwd(void* dy, const void* act, int64_t n, bool f32, cudaStream_t
     relu_bwd_bf16_kernel<<<unsigned((n / 8 + 255) / 256), 256, 0, stream>>>(
         static_cast<__nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(act), n / 8);
   count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+int launch_relu_bwd_colsum(void* dy, const void* act, int64_t M, int N, float* colsum, float* scratch, cudaStream_t stream) {
+  RP_CHECK(M > 0 && N > 0 && N % 8 == 0, "relu_bwd_colsum: N must be a positive multiple of 8");
+  // scratch holds blocks x N partials: train_scratch_floats() >= 4 SMs x 1024 -> blocks <= that / N
+  int64_t blocks = train_scratch_floats() / N;
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  if (blocks > M) blocks = M;
+  RP_CHECK(blocks >= 1, "relu_bwd_colsum: N too large for the scratch buffer");
+  const int64_t rows_per = (M + blocks - 1) / blocks;
+  blocks = (M + rows_per - 1) / rows_per;
+  relu_bwd_colsum_bf16_kernel<<<unsigned(blocks), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(dy),
+                                                                    static_cast<const __nv_bfloat16*>(act), M, N, rows_per,
+                                                                    scratch);
+  colsum_reduce_kernel<<<(N + 127) / 128, 128, 0, stream>>>(scratch, int(blocks), N, colsum);
+  count_launch(2);
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;
 }

@@ -221,6 +221,49 @@ class TrainStep:
         self._bufs = d
         return d
 
+    # ---- per-kernel-class device timing (CUDA events on the launch stream) ----------------------------------------
+    _PROFILED = {"_gemm": "fwd_gemm", "_ln": "fwd_layernorm", "_dgrad": "bwd_dgrad", "_wgrad": "bwd_wgrad",
+                 "_colsum": "bwd_bias_colsum", "_ln_bwd": "bwd_layernorm", "_relu_bwd": "bwd_relu",
+                 "_relu_bwd_bias": "bwd_relu"}
+
+    def profile_begin(self):
+        """from now on every wrapped launch is bracketed by CUDA events; `profile_end()` -> {tag: (ms, launches)}"""
+        self._prof = []
+        for meth, tag in self._PROFILED.items():
+            inner = getattr(type(self), meth)
+
+            def wrapped(*a, _inner=inner, _tag=tag, **k):
+                with self._timed(_tag):
+                    return _inner(self, *a, **k)
+            setattr(self, meth, wrapped)
+
+    def _timed(self, tag):
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            if getattr(self, "_prof", None) is None:
+                yield
+                return
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            yield
+            e1.record()
+            self._prof.append((tag, e0, e1))
+        return cm()
+
+    def profile_end(self):
+        torch.cuda.synchronize(self.dev)
+        out = {}
+        for tag, e0, e1 in self._prof or []:
+            ms, n = out.get(tag, (0.0, 0))
+            out[tag] = (ms + e0.elapsed_time(e1), n + 1)
+        self._prof = None
+        for meth in self._PROFILED:
+            if meth in self.__dict__:
+                delattr(self, meth)
+        return out
+
     # ---- thin wrappers over the C ABI ------------------------------------------------------------------------------
     def _gemm(self, epi, A, W, D, bias, resid=None):
         M, K = A.shape
@@ -262,15 +305,23 @@ class TrainStep:
         check(self.lib.rp_colsum_bf16(ptr(X), M, N, ptr(out), ptr(self._scratch), self._scratch.numel(), cur_stream()),
               "rp_colsum_bf16")
 
-    def _ln_bwd(self, x, dy, prefix, dh, dh16, accumulate):
-        """dh (+)= LayerNorm backward of the branch `prefix` (…weight / …bias receive their gradients)"""
+    def _ln_bwd(self, x, dy, prefix, dh, dh16, accumulate, bias_grad=None):
+        """dh (+)= LayerNorm backward of the branch `prefix` (…weight / …bias receive their gradients); dh16 = bf16 copy
+        of the resulting dh; bias_grad (a parameter name) receives its column sums — the bias gradient of the Linear
+        whose output gradient dh is"""
         M = x.shape[0] if x.dim() == 2 else x.numel() // 512
-        if not accumulate:
-            dh.zero_()
-        check(self.lib.rp_layernorm512_bwd_acc(ptr(x), ptr(dy), ptr(self.w32(prefix + "weight")), M, 1e-5, ptr(dh), ptr(dh16),
+        check(self.lib.rp_layernorm512_bwd_acc(ptr(x), ptr(dy), ptr(self.w32(prefix + "weight")), M, 1e-5,
+                                               1 if accumulate else 0, ptr(dh), ptr(dh16),
+                                               ptr(self.grad(bias_grad)) if bias_grad else 0,
                                                ptr(self.grad(prefix + "weight")), ptr(self.grad(prefix + "bias")),
                                                ptr(self._scratch), self._scratch.numel(), cur_stream()),
               "rp_layernorm512_bwd_acc")
+
+    def _relu_bwd_bias(self, dy, act, bias_name):
+        """dy = act > 0 ? dy : 0 in place, and grad(bias_name) = column sums of the masked dy"""
+        M, N = dy.shape
+        check(self.lib.rp_relu_bwd_colsum(ptr(dy), ptr(act), M, N, ptr(self.grad(bias_name)), ptr(self._scratch),
+                                          self._scratch.numel(), cur_stream()), "rp_relu_bwd_colsum")
 
     def _relu_bwd(self, dy, act):
         check(self.lib.rp_relu_bwd(ptr(dy), ptr(act), dy.numel(), 1 if dy.dtype == torch.float32 else 0, cur_stream()),
@@ -302,8 +353,9 @@ class TrainStep:
                 p = lay.format(l)
                 self._gemm(0, d["u1"][l], self._wqkv16[l], d["qkv"][l], self._bqkv[l])
                 q = d["qkv"][l]
-                check(lib.rp_fmha_train(ptr(q), ptr(q) + 1024, ptr(q) + 2048, ptr(d["attn"][l]), 1536, 512, B, H, T,
-                                        ptr(d["lens"]), ptr(d["lse"][l]), st), "rp_fmha_train")
+                with self._timed("fwd_fmha"):
+                    check(lib.rp_fmha_train(ptr(q), ptr(q) + 1024, ptr(q) + 2048, ptr(d["attn"][l]), 1536, 512, B, H, T,
+                                            ptr(d["lens"]), ptr(d["lse"][l]), st), "rp_fmha_train")
                 self._gemm(3, d["attn"][l], self.w16(p + "self_attn.out_proj.weight"), d["hmid"][l],
                            self.w32(p + "self_attn.out_proj.bias"), resid=d["h"][l])
                 self._ln(0, d["hmid"][l], M, T, self.w32(p + "norm2.weight"), self.w32(p + "norm2.bias"), y=d["u2"][l])
@@ -344,47 +396,46 @@ class TrainStep:
             self._wgrad(da2, d["a1c"], "cls_head.4.")
             self._colsum(da2, self.grad("cls_head.4.bias"))
             self._dgrad(da2, self.w16("cls_head.4.weight"), da1)
-            self._relu_bwd(da1, d["a1c"])
+            self._relu_bwd_bias(da1, d["a1c"], "cls_head.1.bias")
             self._wgrad(da1, d["uc"], "cls_head.1.")
-            self._colsum(da1, self.grad("cls_head.1.bias"))
             self._dgrad(da1, self.w16("cls_head.1.weight"), du)
             feats = d["feats"].view(M, 512)
             self._ln_bwd(feats, du, "cls_head.0.", dh, None, accumulate=False)       # dh = d loss / d feats
             self._relu_bwd(dh, feats)                                                # feats = relu(LN(fm))
-            self._ln_bwd(d["fm"], dh, "feature_map.1.", du, dh16, accumulate=False)  # du = d fm, dh16 = its bf16 copy
+            self._ln_bwd(d["fm"], dh, "feature_map.1.", du, dh16, accumulate=False,  # du = d fm, dh16 = its bf16 copy
+                         bias_grad="feature_map.0.bias")
             self._wgrad(dh16, d["u1"][L], "feature_map.0.")
-            self._colsum(dh16, self.grad("feature_map.0.bias"))
             self._dgrad(dh16, self.w16("feature_map.0.weight"), du)                  # du = d encoder_norm output
-            self._ln_bwd(d["h"][L], du, "encoder_norm.", dh, dh16, accumulate=False)
+            self._ln_bwd(d["h"][L], du, "encoder_norm.", dh, dh16, accumulate=False,
+                         bias_grad=lay.format(L - 1) + "linear2.bias")               # dh = d h[L] = dY of the last linear2
             dffn, dattn = d["dwide"], d["d512"]
             dqkv = d["dwide"].view(-1)[:M * 1536].view(M, 1536)
             for l in range(L - 1, -1, -1):
                 p = lay.format(l)
                 # FFN: h_out = hmid + relu(u2 W1^T + b1) W2^T + b2
                 self._wgrad(dh16, d["ffn"][l], p + "linear2.")
-                self._colsum(dh16, self.grad(p + "linear2.bias"))
                 self._dgrad(dh16, self.w16(p + "linear2.weight"), dffn)
-                self._relu_bwd(dffn, d["ffn"][l])
+                self._relu_bwd_bias(dffn, d["ffn"][l], p + "linear1.bias")
                 self._wgrad(dffn, d["u2"][l], p + "linear1.")
-                self._colsum(dffn, self.grad(p + "linear1.bias"))
                 self._dgrad(dffn, self.w16(p + "linear1.weight"), du)
-                self._ln_bwd(d["hmid"][l], du, p + "norm2.", dh, dh16, accumulate=True)
+                self._ln_bwd(d["hmid"][l], du, p + "norm2.", dh, dh16, accumulate=True,
+                             bias_grad=p + "self_attn.out_proj.bias")                # dh = d hmid = dY of out_proj
                 # attention: hmid = h + attn Wo^T + bo
                 self._wgrad(dh16, d["attn"][l], p + "self_attn.out_proj.")
-                self._colsum(dh16, self.grad(p + "self_attn.out_proj.bias"))
                 self._dgrad(dh16, self.w16(p + "self_attn.out_proj.weight"), dattn)
                 q = d["qkv"][l]
-                check(lib.rp_fmha_bwd(ptr(q), ptr(q) + 1024, ptr(q) + 2048, ptr(d["attn"][l]), ptr(dattn), ptr(d["lse"][l]),
-                                      ptr(d["dsum"]), ptr(dqkv), ptr(dqkv) + 1024, ptr(dqkv) + 2048, 1536, 512, 1536, B, H, T,
-                                      ptr(d["lens"]), st), "rp_fmha_bwd")
+                with self._timed("bwd_fmha"):
+                    check(lib.rp_fmha_bwd(ptr(q), ptr(q) + 1024, ptr(q) + 2048, ptr(d["attn"][l]), ptr(dattn), ptr(d["lse"][l]),
+                                          ptr(d["dsum"]), ptr(dqkv), ptr(dqkv) + 1024, ptr(dqkv) + 2048, 1536, 512, 1536, B, H,
+                                          T, ptr(d["lens"]), st), "rp_fmha_bwd")
                 self._wgrad(dqkv, d["u1"][l], p + "self_attn.in_proj_weight")
                 self._colsum(dqkv, self.grad(p + "self_attn.in_proj_bias"))
                 self._dgrad(dqkv, self.w16(p + "self_attn.in_proj_weight"), du)
-                self._ln_bwd(d["h"][l], du, p + "norm1.", dh, dh16, accumulate=True)
+                self._ln_bwd(d["h"][l], du, p + "norm1.", dh, dh16, accumulate=True,  # dh = d h[l] = dY of layer l-1's linear2
+                             bias_grad=(lay.format(l - 1) + "linear2.bias") if l > 0 else None)
             # h0 = LayerNorm(x W_in^T + b_in) + PE
-            self._ln_bwd(d["xproj"], dh, "input_norm.", du, dh16, accumulate=False)
+            self._ln_bwd(d["xproj"], dh, "input_norm.", du, dh16, accumulate=False, bias_grad="input_projection.bias")
             self._wgrad(dh16, d["xcat"], "input_projection.")
-            self._colsum(dh16, self.grad("input_projection.bias"))
 
     # ---- one iteration ------------------------------------------------------------------------------------------------
     def loss_and_grads(self, batch, batch_size=None):
@@ -399,7 +450,9 @@ class TrainStep:
 
     def step(self, batch, batch_size=None):
         loss = self.loss_and_grads(batch, batch_size)
-        allreduce_flat_(self.opt.grad, self.group)
-        self.opt.step()
-        self.refresh_weights()
+        with self._timed("allreduce"):
+            allreduce_flat_(self.opt.grad, self.group)
+        with self._timed("adam_and_recast"):
+            self.opt.step()
+            self.refresh_weights()
         return loss

@@ -77,6 +77,10 @@ def test_colsum_and_relu_bwd(M, N):
     dy = x.clone()
     L.check(lib.rp_relu_bwd(L.ptr(dy), L.ptr(act), M * N, 0, L.cur_stream()), "relu_bwd")
     assert torch.equal(dy, torch.where(act > 0, x, torch.zeros_like(x)))
+    dy2, cs = x.clone(), torch.empty(N, device=DEV)                              # the fused mask + bias gradient
+    L.check(lib.rp_relu_bwd_colsum(L.ptr(dy2), L.ptr(act), M, N, L.ptr(cs), L.ptr(sc), sc.numel(), L.cur_stream()), "relu_colsum")
+    assert torch.equal(dy2, dy)
+    assert torch.allclose(cs, dy.float().sum(0), atol=2e-3 * max(1.0, M ** 0.5), rtol=1e-4)
     dy32, act32 = x.float().contiguous(), act.float().contiguous()
     exp32 = torch.where(act32 > 0, dy32, torch.zeros_like(dy32))
     L.check(lib.rp_relu_bwd(L.ptr(dy32), L.ptr(act32), M * N, 1, L.cur_stream()), "relu_bwd f32")
@@ -97,12 +101,18 @@ def test_layernorm_bwd_accumulates_and_head_out_bwd(M):
     dh16 = torch.empty(M, 512, dtype=torch.bfloat16, device=DEV)
     dgm, dbt = torch.empty(512, device=DEV), torch.empty(512, device=DEV)
     sc = _scratch(lib)
-    L.check(lib.rp_layernorm512_bwd_acc(L.ptr(x.detach()), L.ptr(dy), L.ptr(gamma.detach()), M, 1e-5, L.ptr(dh), L.ptr(dh16),
-                                        L.ptr(dgm), L.ptr(dbt), L.ptr(sc), sc.numel(), L.cur_stream()), "ln_bwd_acc")
+    csum = torch.empty(512, device=DEV)
+    L.check(lib.rp_layernorm512_bwd_acc(L.ptr(x.detach()), L.ptr(dy), L.ptr(gamma.detach()), M, 1e-5, 1, L.ptr(dh), L.ptr(dh16),
+                                        L.ptr(csum), L.ptr(dgm), L.ptr(dbt), L.ptr(sc), sc.numel(), L.cur_stream()), "ln_bwd_acc")
     assert torch.allclose(dh, dh0 + x.grad, atol=3e-5, rtol=1e-4)
     assert torch.equal(dh16, dh.bfloat16())
     tol = 2e-4 * max(1.0, M ** 0.5)
     assert torch.allclose(dgm, gamma.grad, atol=tol, rtol=1e-4) and torch.allclose(dbt, beta.grad, atol=tol, rtol=1e-4)
+    assert torch.allclose(csum, dh.sum(0), atol=5 * tol, rtol=1e-4)          # bias gradient of the Linear in front
+    dh2 = torch.full_like(dh0, float("nan"))                                   # accumulate = 0 overwrites
+    L.check(lib.rp_layernorm512_bwd_acc(L.ptr(x.detach()), L.ptr(dy), L.ptr(gamma.detach()), M, 1e-5, 0, L.ptr(dh2), 0, 0,
+                                        L.ptr(dgm), L.ptr(dbt), L.ptr(sc), sc.numel(), L.cur_stream()), "ln_bwd")
+    assert torch.allclose(dh2, x.grad, atol=3e-5, rtol=1e-4)
     # last cls-head layer (Linear 256 -> 1) and the ReLU in front of it
     a2 = torch.relu(torch.randn(M, 256, device=DEV, generator=g)).bfloat16()
     w = torch.randn(256, device=DEV, generator=g)

@@ -65,6 +65,31 @@ def main():
         ms = timeit(run, args.iters, flush)
         fl = 4.0 * B * H * T * T * 64
         out["fmha"] = {"ms": ms, "tflops": fl / ms / 1e9}
+    if "fmhabwd" in args.what:
+        qkv = torch.randn(B, T, 3 * D, device=dev)
+        qkv[..., :D] *= LOG2E / 8
+        qkv = qkv.bfloat16()
+        o = torch.empty(B, T, D, dtype=torch.bfloat16, device=dev)
+        d_o = torch.randn(B, T, D, device=dev).bfloat16()
+        dqkv = torch.empty(B, T, 3 * D, dtype=torch.bfloat16, device=dev)
+        lse = torch.empty(B, H, T, device=dev)
+        dsum = torch.empty(B, H, T, device=dev)
+        lens = torch.full((B,), T, dtype=torch.int32, device=dev)
+
+        def fwd():
+            check(lib.rp_fmha_train(ptr(qkv), ptr(qkv) + D * 2, ptr(qkv) + 2 * D * 2, ptr(o), 3 * D, D, B, H, T, ptr(lens),
+                                    ptr(lse), cur_stream()), "fmha_train")
+
+        def bwd():
+            check(lib.rp_fmha_bwd(ptr(qkv), ptr(qkv) + D * 2, ptr(qkv) + 2 * D * 2, ptr(o), ptr(d_o), ptr(lse), ptr(dsum),
+                                  ptr(dqkv), ptr(dqkv) + D * 2, ptr(dqkv) + 2 * D * 2, 3 * D, D, 3 * D, B, H, T, ptr(lens),
+                                  cur_stream()), "fmha_bwd")
+        ms = timeit(fwd, args.iters, flush)
+        out["fmha_train_fwd"] = {"ms": ms, "tflops": 4.0 * B * H * T * T * 64 / ms / 1e9}
+        ms = timeit(bwd, args.iters, flush)
+        # algorithmic: 5 T x T x 64 contractions (dV, dP, dQ, dK + the S recompute); the two-kernel split executes 7
+        out["fmha_bwd"] = {"ms": ms, "tflops_algorithmic": 10.0 * B * H * T * T * 64 / ms / 1e9,
+                           "tflops_executed": 14.0 * B * H * T * T * 64 / ms / 1e9}
     if "gemm" in args.what:
         shapes = {"qkv(epi0)": (0, 1536, 512), "ff1(epi1)": (1, 2048, 512), "out(epi3)": (3, 512, 512),
                   "ff2(epi3)": (3, 512, 2048), "in(epi2)": (2, 512, 2944)}

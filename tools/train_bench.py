@@ -48,6 +48,9 @@ def run_train_bench(B, T, steps, warmup=2, rank=0, world=1, dev=None):
     e2.record()
     torch.cuda.synchronize()
     fwd_ms = e0.elapsed_time(e2) / steps
+    ts.profile_begin()
+    ts.step(batch, batch_size=B)
+    prof = {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in sorted(ts.profile_end().items(), key=lambda kv: -kv[1][0])}
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms], device=dev)
@@ -56,7 +59,7 @@ def run_train_bench(B, T, steps, warmup=2, rank=0, world=1, dev=None):
     flops = 3.0 * B * (104_989_696.0 * T + 32_768.0 * T * T)   # forward + 2x for the backward (SURVEY 8d forward count)
     return {"batch_per_gpu": B, "seq_len": T, "n_gpus": world, "ms_per_step": ms, "forward_ms": fwd_ms,
             "videos_per_s": world * B / (ms * 1e-3), "model_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
-            "loss_first_last": [losses[0], losses[-1]],
+            "loss_first_last": [losses[0], losses[-1]], "kernel_classes_ms": prof,
             "activation_gb": 16 * B * T * 14.3e3 / 1e9,
             "what": "forward (activations kept) + masked focal loss + backward + one flat gradient all-reduce + Adam; "
                     "dropout off (documented deviation)"}
