@@ -116,6 +116,13 @@ enum {
   RP_TAG_GEMM_OUT = 5, RP_TAG_GEMM_FF1 = 6, RP_TAG_GEMM_FF2 = 7, RP_TAG_GEMM_FMAP = 8,
   RP_TAG_GEMM_HEAD = 9, RP_TAG_HEAD_OUT = 10, RP_NUM_TAGS = 11
 };
+/* rp_forward* skip work that only touches padding (default on; RP_SKIP_PADDING=0 in the environment turns it off at
+ * rp_create): 256-row blocks of the padded [B, T] token matrix without a step t < round_up(lens[b], 128) are left out of
+ * every GEMM, attention query tiles beyond that limit exit at once, and the padded steps (t >= lens[b]) of logits /
+ * offsets / feats are returned as zeros.  The reference computes padded steps too and returns finite values nobody
+ * reads (models/MMCTransformer.py:132-138 masks them as keys; callers mask them as outputs); valid steps are
+ * bit-identical either way. */
+int32_t rp_set_skip_padding(rp_handle* h, int32_t on);
 int32_t rp_profile_begin(rp_handle* h);
 int32_t rp_profile_end(rp_handle* h, float* ms_by_tag, int32_t* launches_by_tag);
 
@@ -229,6 +236,12 @@ int32_t rp_gemm_bf16(int32_t epilogue, const void* A, int64_t lda, const void* W
 int32_t rp_gemm_resid_ln(const void* A, int64_t lda, const void* W, int64_t ldw, float* h, int64_t ldh,
                          const float* bias, const float* gamma, const float* beta, float eps, void* u_bf16,
                          int64_t ldu, int32_t M, int32_t K, void* stream);
+/* The tail of cls_head / reg_head (models/MMCTransformer.py:71-93: Linear(256,256), ReLU, [Dropout], Linear(256, nj), and
+ * reg_head's final ReLU) in one kernel: out[m, j] = act(sum_c relu(A[m,:] . W[c,:] + bias[c]) * w_last[j, c] + b_last[j]);
+ * A bf16 [M,K] (pitch lda), W bf16 [256,K], bias [256], w_last fp32 [nj,256], nj = 1 or 2, out fp32 [M,nj]. */
+int32_t rp_gemm_head_dot(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* w_last,
+                         const float* b_last, int32_t nj, int32_t final_relu, float* out, int32_t M, int32_t K,
+                         void* stream);
 /* softmax(q k^T + mask) v per head of 64; q must be pre-scaled by log2(e)/8.  bf16 in/out; ld* row
  * pitch and bs* batch pitch in elements.  mask_mode 0: keys >= kv_lens[b] are -inf (kv_lens may be
  * NULL); mask_mode 1: uint8 mask, 0 => masked_fill(-1e9), mask_q_stride 0 broadcasts over queries. */

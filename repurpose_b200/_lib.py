@@ -58,8 +58,10 @@ SIGNATURES = {
     "rp_head_out_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "rp_fmha_train": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "rp_fmha_bwd": (c_i32, [c_vp] * 10 + [c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "rp_gemm_head_dot": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp]),
     "rp_gemm_resid_ln": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64,
                                  c_i32, c_i32, c_vp]),
+    "rp_set_skip_padding": (c_i32, [c_vp, c_i32]),
     "rp_profile_begin": (c_i32, [c_vp]),
     "rp_profile_end": (c_i32, [c_vp, c_vp, c_vp]),
     "rp_decode_nms": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, C.POINTER(RpDecodeCfg), c_i32,

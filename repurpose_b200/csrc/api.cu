@@ -48,6 +48,8 @@ struct rp_handle {
   float *r0_g, *r0_b, *b_r1, *b_r4, *w_r7, *b_r7;
   float* pe;
   int64_t pe_rows_loaded = 0;
+  // skip 256-row blocks / query tiles that hold nothing but padding (rp_set_skip_padding; default RP_SKIP_PADDING or 1)
+  bool skip_padding = !(getenv("RP_SKIP_PADDING") && atoi(getenv("RP_SKIP_PADDING")) == 0);
   // optional per-kernel-class CUDA-event profiler (rp_profile_begin / rp_profile_end)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_pool;
@@ -160,6 +162,8 @@ struct Workspace {
   __nv_bfloat16* attn;  // [M,512]
   __nv_bfloat16* qkv;   // [M,1536]   } contiguous: also holds xcat [M,Cin] during the input stage
   __nv_bfloat16* ffn;   // [M,d_ff]   }
+  int32_t* row_blocks;  // RowMap: [ceil(M/256)] valid 256-row blocks + their count (padding-only blocks are skipped)
+  int32_t* row_count;
   int64_t bytes;
 };
 
@@ -179,12 +183,15 @@ Workspace carve(const rp_model_cfg& c, int64_t M, void* base) {
   int64_t wide = M * (3 * D + c.d_ff) * 2;
   if (wide < M * Cin * 2) wide = M * Cin * 2;
   const int64_t o_q = take(wide);
+  const int64_t o_m = take(((M + 255) / 256 + 1) * 4);
   uint8_t* b = reinterpret_cast<uint8_t*>(base);
   w.h = reinterpret_cast<float*>(b + o_h);
   w.u = reinterpret_cast<__nv_bfloat16*>(b + o_u);
   w.attn = reinterpret_cast<__nv_bfloat16*>(b + o_a);
   w.qkv = reinterpret_cast<__nv_bfloat16*>(b + o_q);
   w.ffn = w.qkv + M * 3 * D;
+  w.row_count = reinterpret_cast<int32_t*>(b + o_m);
+  w.row_blocks = w.row_count + 1;
   w.bytes = off;
   return w;
 }
@@ -340,6 +347,17 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
     }                                                          \
   } while (0)
 
+  // Padding-only blocks are skipped (rp_set_skip_padding / RP_SKIP_PADDING, default on): the GEMMs walk the RowMap's 256-row blocks, attention
+  // CTAs of padding-only query tiles exit at once, and the padded steps of the three outputs are zeroed at the end.
+  // The reference computes padded rows too (finite values nobody reads); valid rows are bit-identical
+  // with and without skipping because no tile's arithmetic depends on which other tiles run.
+  const bool skip = h->skip_padding && M > 128;
+  RowMap rmap{w.row_blocks, w.row_count};
+  const RowMap* rows = skip ? &rmap : nullptr;
+  if (skip) {
+    rc = launch_row_map(lens, B, T, w.row_blocks, w.row_count, st);
+    if (rc) return rc;
+  }
   // (1) concat + cast, input projection (fp32 out), input_norm + PE -> h, layers[0].norm1 -> u
   __nv_bfloat16* xcat = w.qkv;
   if (rg.row_off != nullptr)
@@ -347,7 +365,7 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
                                                rg.txt_off, rg.txt_lens, lens, B, T, xcat, st));
   else
     RUN(RP_TAG_CAST, launch_concat_cast(vis, aud, txt, c.vis_dim, c.aud_dim, c.text_dim, xcat, M, st));
-  RUN(RP_TAG_GEMM_IN, launch_gemm(EPI_BIAS_F32, xcat, Cin, h->w_in, Cin, w.h, D, h->b_in, nullptr, 0, M, D, Cin, st));
+  RUN(RP_TAG_GEMM_IN, launch_gemm(EPI_BIAS_F32, xcat, Cin, h->w_in, Cin, w.h, D, h->b_in, nullptr, 0, M, D, Cin, st, rows));
   {
     LnArgs a{};
     a.x = w.h; a.M = M; a.T = T; a.eps = eps;
@@ -364,12 +382,12 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
   const bool ln_in_gemm = ln_in_gemm_env && D == 512 && M > 128;
   for (int l = 0; l < c.num_layers; ++l) {
     const LayerW& L = h->layers[l];
-    RUN(RP_TAG_GEMM_QKV, launch_gemm(EPI_BIAS_BF16, w.u, D, L.w_qkv, D, w.qkv, 3 * D, L.b_qkv, nullptr, 0, M, 3 * D, D, st));
+    RUN(RP_TAG_GEMM_QKV, launch_gemm(EPI_BIAS_BF16, w.u, D, L.w_qkv, D, w.qkv, 3 * D, L.b_qkv, nullptr, 0, M, 3 * D, D, st, rows));
     FmhaArgs fa{};
     fa.q = w.qkv; fa.k = w.qkv + D; fa.v = w.qkv + 2 * D; fa.o = w.attn;
     fa.ldq = fa.ldk = fa.ldv = 3 * D; fa.ldo = D;
     fa.bsq = fa.bsk = fa.bsv = int64_t(T) * 3 * D; fa.bso = int64_t(T) * D;
-    fa.B = B; fa.H = H; fa.Tq = T; fa.Tk = T; fa.kv_lens = lens; fa.mask_mode = 0;
+    fa.B = B; fa.H = H; fa.Tq = T; fa.Tk = T; fa.kv_lens = lens; fa.mask_mode = 0; fa.skip_padded_queries = skip;
     RUN(RP_TAG_FMHA, launch_fmha(fa, st));
     if (ln_in_gemm) {
       // The LayerNorm that follows each residual update runs inside the GEMM epilogue (clusters of
@@ -377,20 +395,20 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
       GemmLnFusion f{};
       f.eps = eps; f.u_out = w.u; f.ld_u = D;
       f.ln_gamma = L.n2_g; f.ln_beta = L.n2_b;
-      RUN(RP_TAG_GEMM_OUT, launch_gemm_ln(EPI_BIAS_RESID_LN, w.attn, D, L.w_out, D, w.h, D, L.b_out, w.h, D, M, D, D, f, st));
-      RUN(RP_TAG_GEMM_FF1, launch_gemm(EPI_BIAS_RELU_BF16, w.u, D, L.w_ff1, D, w.ffn, F, L.b_ff1, nullptr, 0, M, F, D, st));
+      RUN(RP_TAG_GEMM_OUT, launch_gemm_ln(EPI_BIAS_RESID_LN, w.attn, D, L.w_out, D, w.h, D, L.b_out, w.h, D, M, D, D, f, st, rows));
+      RUN(RP_TAG_GEMM_FF1, launch_gemm(EPI_BIAS_RELU_BF16, w.u, D, L.w_ff1, D, w.ffn, F, L.b_ff1, nullptr, 0, M, F, D, st, rows));
       if (l + 1 < c.num_layers) { f.ln_gamma = h->layers[l + 1].n1_g; f.ln_beta = h->layers[l + 1].n1_b; }
       else { f.ln_gamma = h->enc_g; f.ln_beta = h->enc_b; }  // encoder_norm feeds feature_map
-      RUN(RP_TAG_GEMM_FF2, launch_gemm_ln(EPI_BIAS_RESID_LN, w.ffn, F, L.w_ff2, F, w.h, D, L.b_ff2, w.h, D, M, D, F, f, st));
+      RUN(RP_TAG_GEMM_FF2, launch_gemm_ln(EPI_BIAS_RESID_LN, w.ffn, F, L.w_ff2, F, w.h, D, L.b_ff2, w.h, D, M, D, F, f, st, rows));
     } else {
-      RUN(RP_TAG_GEMM_OUT, launch_gemm(EPI_BIAS_RESID_F32, w.attn, D, L.w_out, D, w.h, D, L.b_out, w.h, D, M, D, D, st));
+      RUN(RP_TAG_GEMM_OUT, launch_gemm(EPI_BIAS_RESID_F32, w.attn, D, L.w_out, D, w.h, D, L.b_out, w.h, D, M, D, D, st, rows));
       {
         LnArgs a{};
         a.x = w.h; a.M = M; a.T = T; a.eps = eps; a.g0 = L.n2_g; a.b0 = L.n2_b; a.y_bf16 = w.u;
         RUN(RP_TAG_LAYERNORM, launch_layernorm512(0, a, st));
       }
-      RUN(RP_TAG_GEMM_FF1, launch_gemm(EPI_BIAS_RELU_BF16, w.u, D, L.w_ff1, D, w.ffn, F, L.b_ff1, nullptr, 0, M, F, D, st));
-      RUN(RP_TAG_GEMM_FF2, launch_gemm(EPI_BIAS_RESID_F32, w.ffn, F, L.w_ff2, F, w.h, D, L.b_ff2, w.h, D, M, D, F, st));
+      RUN(RP_TAG_GEMM_FF1, launch_gemm(EPI_BIAS_RELU_BF16, w.u, D, L.w_ff1, D, w.ffn, F, L.b_ff1, nullptr, 0, M, F, D, st, rows));
+      RUN(RP_TAG_GEMM_FF2, launch_gemm(EPI_BIAS_RESID_F32, w.ffn, F, L.w_ff2, F, w.h, D, L.b_ff2, w.h, D, M, D, F, st, rows));
       {
         LnArgs a{};
         a.x = w.h; a.M = M; a.T = T; a.eps = eps; a.y_bf16 = w.u;
@@ -401,7 +419,7 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
     }
   }
   // (3) feature_map: Linear -> LN -> ReLU = feats (returned); head LayerNorms
-  RUN(RP_TAG_GEMM_FMAP, launch_gemm(EPI_BIAS_F32, w.u, D, h->w_fm, D, w.h, D, h->b_fm, nullptr, 0, M, D, D, st));
+  RUN(RP_TAG_GEMM_FMAP, launch_gemm(EPI_BIAS_F32, w.u, D, h->w_fm, D, w.h, D, h->b_fm, nullptr, 0, M, D, D, st, rows));
   {
     LnArgs a{};
     a.x = w.h; a.M = M; a.T = T; a.eps = eps;
@@ -414,11 +432,22 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
   __nv_bfloat16* a2c = a1c + int64_t(M) * Hh;
   __nv_bfloat16* a1r = a2c + int64_t(M) * Hh;
   __nv_bfloat16* a2r = a1r + int64_t(M) * Hh;
-  RUN(RP_TAG_GEMM_HEAD, launch_gemm(EPI_BIAS_RELU_BF16, w.u, D, h->w_c1, D, a1c, Hh, h->b_c1, nullptr, 0, M, Hh, D, st));
-  RUN(RP_TAG_GEMM_HEAD, launch_gemm(EPI_BIAS_RELU_BF16, a1c, Hh, h->w_c4, Hh, a2c, Hh, h->b_c4, nullptr, 0, M, Hh, Hh, st));
-  RUN(RP_TAG_GEMM_HEAD, launch_gemm(EPI_BIAS_RELU_BF16, w.attn, D, h->w_r1, D, a1r, Hh, h->b_r1, nullptr, 0, M, Hh, D, st));
-  RUN(RP_TAG_GEMM_HEAD, launch_gemm(EPI_BIAS_RELU_BF16, a1r, Hh, h->w_r4, Hh, a2r, Hh, h->b_r4, nullptr, 0, M, Hh, Hh, st));
-  RUN(RP_TAG_HEAD_OUT, launch_head_out(a2c, a2r, h->w_c7, h->b_c7, h->w_r7, h->b_r7, out_logits, out_offsets, M, st));
+  RUN(RP_TAG_GEMM_HEAD, launch_gemm(EPI_BIAS_RELU_BF16, w.u, D, h->w_c1, D, a1c, Hh, h->b_c1, nullptr, 0, M, Hh, D, st, rows));
+  RUN(RP_TAG_GEMM_HEAD, launch_gemm(EPI_BIAS_RELU_BF16, w.attn, D, h->w_r1, D, a1r, Hh, h->b_r1, nullptr, 0, M, Hh, D, st, rows));
+  if (Hh == 256) {
+    // Linear(256,256) + ReLU + Linear(256, 1 | 2) (+ ReLU) in one kernel per head: the second hidden activation never
+    // leaves the epilogue registers; no [M,256] write, no head_out pass
+    RUN(RP_TAG_GEMM_HEAD, launch_gemm_head_dot(a1c, Hh, h->w_c4, Hh, h->b_c4, h->w_c7, h->b_c7, 1, false, out_logits, M, Hh, st, rows));
+    RUN(RP_TAG_GEMM_HEAD, launch_gemm_head_dot(a1r, Hh, h->w_r4, Hh, h->b_r4, h->w_r7, h->b_r7, 2, true, out_offsets, M, Hh, st, rows));
+  } else {
+    RUN(RP_TAG_GEMM_HEAD, launch_gemm(EPI_BIAS_RELU_BF16, a1c, Hh, h->w_c4, Hh, a2c, Hh, h->b_c4, nullptr, 0, M, Hh, Hh, st, rows));
+    RUN(RP_TAG_GEMM_HEAD, launch_gemm(EPI_BIAS_RELU_BF16, a1r, Hh, h->w_r4, Hh, a2r, Hh, h->b_r4, nullptr, 0, M, Hh, Hh, st, rows));
+    RUN(RP_TAG_HEAD_OUT, launch_head_out(a2c, a2r, h->w_c7, h->b_c7, h->w_r7, h->b_r7, out_logits, out_offsets, M, st));
+  }
+  if (skip) {
+    rc = launch_zero_padded_rows(out_logits, out_offsets, out_feats, lens, B, T, D, st);
+    if (rc) return rc;
+  }
 #undef RUN
   return RP_OK;
 }
@@ -452,6 +481,12 @@ int32_t rp_forward_ragged_bf16(rp_handle* h, const void* vis, const void* aud, c
   rg.row_off = row_off; rg.txt_off = txt_off; rg.txt_lens = txt_lens; rg.bf16 = true;
   return forward_core(h, vis, aud, txt, rg, lens, B, T, out_logits, out_offsets, out_feats, workspace,
                       workspace_bytes, stream);
+}
+
+int32_t rp_set_skip_padding(rp_handle* h, int32_t on) {
+  RP_CHECK(h != nullptr, "rp_set_skip_padding: null handle");
+  h->skip_padding = on != 0;
+  return RP_OK;
 }
 
 int32_t rp_profile_begin(rp_handle* h) {
@@ -647,6 +682,13 @@ int32_t rp_fmha(const void* q, const void* k, const void* v, void* o, int64_t ld
   a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.kv_lens = kv_lens; a.mask_mode = mask_mode;
   a.mask = mask; a.mask_b_stride = mask_b_stride; a.mask_q_stride = mask_q_stride;
   return launch_fmha(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_gemm_head_dot(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* w_last,
+                         const float* b_last, int32_t nj, int32_t final_relu, float* out, int32_t M, int32_t K,
+                         void* stream) {
+  return launch_gemm_head_dot(A, lda, W, ldw, bias, w_last, b_last, nj, final_relu != 0, out, M, K,
+                              reinterpret_cast<cudaStream_t>(stream));
 }
 
 int32_t rp_gemm_resid_ln(const void* A, int64_t lda, const void* W, int64_t ldw, float* h, int64_t ldh,

@@ -108,6 +108,7 @@ struct FmhaParams {
   const uint8_t* mask;
   int64_t mask_b_stride, mask_q_stride;
   float* lse;  // optional [B, H, Tq]: log2-domain log-sum-exp of every score row (what the backward pass recomputes P from)
+  int skip_padded_queries;  // query tiles at or beyond round_up(kv_len, 128) are padding: exit at once
 };
 
 // ---- packed f32x2 helpers (sm_100 FFMA2/FADD2) ---------------------------------------------------
@@ -214,6 +215,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     kv_len = kv_len < 0 ? 0 : (kv_len > p.Tk ? p.Tk : kv_len);
   }
   const int n_kv = (kv_len + KT - 1) / KT;
+  // self-attention over a padded batch: a query tile that starts beyond the video's last (rounded-up) key tile holds
+  // padding rows only — nobody reads its output (FmhaArgs::skip_padded_queries; block-uniform, before any barrier)
+  if (MASK_MODE == 0 && p.skip_padded_queries && q_start0 >= n_kv * KT) return;
   const int nv_last = kv_len - (n_kv - 1) * KT;  // valid keys of the last tile (1 .. KT)
   const int nch_last = (nv_last + 15) >> 4;      // its 16-key chunks: the only ones multiplied and exponentiated
   // softmax warps of query tile q with at least one row below Tq (the others exit at once)
@@ -724,7 +728,8 @@ int launch_fmha(const FmhaArgs& a, cudaStream_t stream) {
   if ((rc = make_tmap_3d(&tmV, bf, a.v, cols, a.Tk, a.B, a.ldv * 2, a.bsv * 2, HD, KT))) return rc;
   if ((rc = make_tmap_3d(&tmO, bf, a.o, cols, a.Tq, a.B, a.ldo * 2, a.bso * 2, HD, QT))) return rc;
 
-  FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride, a.lse};
+  FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride, a.lse,
+               (a.skip_padded_queries && a.kv_lens != nullptr && a.Tq == a.Tk) ? 1 : 0};
   // One build of the kernel ships (NQ = 1: two independent CTAs per SM; one exp2 pair in four on the FMA pipe).
   // The alternatives that were built, verified and measured — NQ = 2, 0 or 2 emulated pairs, a 64-key-tile
   // three-CTA variant and a two-warpgroup ping-pong kernel — live under tools/experiments/ with their numbers.

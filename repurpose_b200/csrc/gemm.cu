@@ -79,6 +79,14 @@ struct GemmArgs {
   int M, N, K;
   const float* bias;
   GemmLnFusion ln;
+  // EPI_HEAD_DOT: the head's last Linear folded into the epilogue
+  const float* head_w = nullptr;  // [nj, 256]
+  const float* head_b = nullptr;  // [nj]
+  float* head_out = nullptr;      // [M, nj]
+  int head_nj = 0, head_relu = 0;
+  // RowMap (kernels.h): when set, only the listed 256-row blocks are computed (tile index -> row_blocks[tile / n_tiles])
+  const int32_t* row_blocks = nullptr;
+  const int32_t* row_count = nullptr;
   int splits = 1;        // split-K: split s reduces k-blocks [s * kb_per_split, ...) and writes rows [s*M, (s+1)*M) of D
   int kb_per_split = 0;  // (0 = all)
 };
@@ -130,10 +138,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int group = blockIdx.x / CG;                           // tile-scheduler slot (pair index)
   const int num_groups = gridDim.x / CG;
 
-  const int m_tiles = (g.M + BM * CG - 1) / (BM * CG);
+  int m_tiles = (g.M + BM * CG - 1) / (BM * CG);  // (replaced by the RowMap's block count once it may be read)
   const int n_tiles = (g.N + BN - 1) / BN;
-  const int tiles_per_split = m_tiles * n_tiles;
-  const int total_tiles = tiles_per_split * g.splits;
+  int tiles_per_split = m_tiles * n_tiles;
+  int total_tiles = tiles_per_split * g.splits;
   const int k_blocks = (g.K + BK - 1) / BK;
   const int kbps = g.kb_per_split > 0 ? g.kb_per_split : k_blocks;
   // tile index -> (split, m block, n block, k-block range)
@@ -142,6 +150,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int t2 = tile - sp * tiles_per_split;
     m_blk = t2 / n_tiles;
     n_blk = t2 - m_blk * n_tiles;
+    if (g.row_blocks != nullptr) m_blk = __ldg(g.row_blocks + m_blk);
     kb0 = sp * kbps;
     kb1 = kb0 + kbps < k_blocks ? kb0 + kbps : k_blocks;
   };
@@ -174,6 +183,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the previous kernel's tail; its results are needed from here on
+  if (g.row_blocks != nullptr) {
+    m_tiles = __ldg(g.row_count);
+    tiles_per_split = m_tiles * n_tiles;
+    total_tiles = tiles_per_split * g.splits;
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -284,8 +298,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (cl >= WCH) return;  // a LayerNorm output chunk: nothing to load
       const int c = ch * WCH + cl;
       const int tile = group + (gc / UPT) * num_groups;
-      const int m_blk = tile / n_tiles;  // (residual epilogues never run split-K)
-      const int n_blk = tile - m_blk * n_tiles;
+      int sp, m_blk, n_blk, kb0, kb1;
+      decode(tile, sp, m_blk, n_blk, kb0, kb1);  // (residual epilogues never run split-K: sp = 0)
       const int s = gc % SLABS;
       mbar_expect_tx(resid_bar(ew, s), SLAB_BYTES);
       tma_load_2d(slab0 + s * SLAB_BYTES, &tmR, resid_bar(ew, s), n_blk * BN + c * CPC, tile_row0(m_blk));
@@ -310,6 +324,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // LNF: row statistics of the updated h over this tile's 256 columns, accumulated about a shift (the row's
       // first value) so that a large common offset of the residual stream does not cancel in E[x^2] - mean^2
       float st_sum = 0.f, st_sq = 0.f, st_shift = 0.f;
+      float hd0 = 0.f, hd1 = 0.f;  // EPI_HEAD_DOT: this row's dot products with the last layer's weight rows
       mbar_wait(tfull_bar(buf), use_parity);
       tc_fence_after();
 
@@ -336,7 +351,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           mbar_wait(resid_bar(ew, s), (resid_phase >> s) & 1u);
           resid_phase ^= 1u << s;
-        } else {
+        } else if constexpr (EPI != EPI_HEAD_DOT) {
           // the TMA store that last read this slab (SLABS chunks ago) must have drained it
           if (lane == 0) tma_store_wait_read<SLABS - 1>();
           __syncwarp();
@@ -358,7 +373,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + b4.w);
             }
           }
-          if constexpr (EPI == EPI_BIAS_RELU_BF16) {
+          if constexpr (EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_HEAD_DOT) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               v[i] = __float_as_uint(fmaxf(__uint_as_float(v[i]), 0.0f));
@@ -398,6 +413,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 st_sq = fmaf(d, d, st_sq);
               }
             }
+          } else if constexpr (EPI == EPI_HEAD_DOT) {
+            // the row's 32 activations of this half against the matching slice of the last layer's weight rows
+            // (every lane reads the same addresses: one broadcast request per float4)
+            const float4* w0 = reinterpret_cast<const float4*>(g.head_w + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 w = __ldg(w0 + i);
+              hd0 = fmaf(__uint_as_float(v[4 * i]), w.x, hd0);
+              hd0 = fmaf(__uint_as_float(v[4 * i + 1]), w.y, hd0);
+              hd0 = fmaf(__uint_as_float(v[4 * i + 2]), w.z, hd0);
+              hd0 = fmaf(__uint_as_float(v[4 * i + 3]), w.w, hd0);
+            }
+            if (g.head_nj == 2) {
+              const float4* w1 = reinterpret_cast<const float4*>(g.head_w + BN + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 w = __ldg(w1 + i);
+                hd1 = fmaf(__uint_as_float(v[4 * i]), w.x, hd1);
+                hd1 = fmaf(__uint_as_float(v[4 * i + 1]), w.y, hd1);
+                hd1 = fmaf(__uint_as_float(v[4 * i + 2]), w.z, hd1);
+                hd1 = fmaf(__uint_as_float(v[4 * i + 3]), w.w, hd1);
+              }
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -413,11 +451,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmD, slab, n_blk * BN + c * CPC, row0);
-          tma_store_commit();
+        if constexpr (EPI != EPI_HEAD_DOT) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmD, slab, n_blk * BN + c * CPC, row0);
+            tma_store_commit();
+          }
+        }
+      }
+      if constexpr (EPI == EPI_HEAD_DOT) {
+        const int row = row0 + lane;
+        if (row < g.M) {
+          float o0 = hd0 + g.head_b[0];
+          if (g.head_relu) o0 = fmaxf(o0, 0.0f);
+          if (g.head_nj == 2) {
+            float o1 = hd1 + g.head_b[1];
+            if (g.head_relu) o1 = fmaxf(o1, 0.0f);
+            *reinterpret_cast<float2*>(g.head_out + int64_t(row) * 2) = make_float2(o0, o1);
+          } else {
+            g.head_out[row] = o0;
+          }
         }
       }
       if constexpr (LNF) {
@@ -595,7 +649,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
 template <int CG>
 int launch_cg(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd,
               const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
-              const GemmLnFusion& ln, cudaStream_t stream) {
+              const GemmLnFusion& ln, cudaStream_t stream, const RowMap* rows) {
   const bool resid_epi = (epilogue == EPI_BIAS_RESID_F32 || epilogue == EPI_BIAS_RESID_LN);
   const bool out_f32 = (epilogue == EPI_BIAS_F32 || resid_epi);
   CUtensorMap tmA, tmB, tmD, tmR, tmU;
@@ -616,6 +670,10 @@ int launch_cg(int epilogue, const void* A, int64_t lda, const void* W, int64_t l
     return rc;
 
   GemmArgs g{M, N, K, bias, ln};
+  if (CG == 2 && rows != nullptr) {  // (256-row blocks are the CTA pair's tile height)
+    g.row_blocks = rows->blocks;
+    g.row_count = rows->count;
+  }
   const int total_tiles = ((M + BM * CG - 1) / (BM * CG)) * (N / BN);
   const int sms = num_sms();
   if (sms <= 0) return RP_ERR_NO_DEVICE;
@@ -693,9 +751,39 @@ int launch_gemm_bwd(int kind, bool out_f32, const void* A, int64_t lda, const vo
   return launch_tr(kind, out_f32, A, lda, B, ldb, D, ldd, M, N, K, splits, stream);
 }
 
+int launch_gemm_head_dot(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* w7,
+                         const float* b7, int nj, bool final_relu, float* out, int M, int K, cudaStream_t stream,
+                         const RowMap* rows) {
+  RP_CHECK(A && W && bias && w7 && b7 && out, "gemm_head_dot: null argument");
+  RP_CHECK(M > 0 && K > 0 && K % BK == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_head_dot: K %% 64 and pitches %% 8 required");
+  RP_CHECK(nj == 1 || nj == 2, "gemm_head_dot: nj must be 1 or 2");
+  RP_CHECK((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(bias) |
+            reinterpret_cast<uintptr_t>(w7)) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 8 == 0,
+           "gemm_head_dot: pointers must be 16-byte aligned (out: 8)");
+  const int N = BN;  // the head's hidden width: one 256-column tile, so an epilogue thread sees its whole row
+  CUtensorMap tmA, tmB;
+  int rc;
+  const bool pair = M > BM;
+  if ((rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, A, K, M, lda * 2, BK, BM))) return rc;
+  if ((rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, W, K, N, ldw * 2, BK, pair ? BN / 2 : BN))) return rc;
+  GemmArgs g{M, N, K, bias, GemmLnFusion{}};
+  g.head_w = w7; g.head_b = b7; g.head_out = out; g.head_nj = nj; g.head_relu = final_relu ? 1 : 0;
+  const int sms = num_sms();
+  if (sms <= 0) return RP_ERR_NO_DEVICE;
+  if (pair) {
+    if (rows != nullptr) {
+      g.row_blocks = rows->blocks;
+      g.row_count = rows->count;
+    }
+    const int tiles = (M + 2 * BM - 1) / (2 * BM);
+    return launch_one<EPI_HEAD_DOT, 2>(tmA, tmB, tmA, tmA, tmA, g, tiles < sms / 2 ? tiles : sms / 2, stream);
+  }
+  return launch_one<EPI_HEAD_DOT, 1>(tmA, tmB, tmA, tmA, tmA, g, 1, stream);
+}
+
 int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
                    int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
-                   const GemmLnFusion& ln, cudaStream_t stream) {
+                   const GemmLnFusion& ln, cudaStream_t stream, const RowMap* rows) {
   RP_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   RP_CHECK(N % BN == 0, "gemm: N=%d must be a multiple of %d", N, BN);
   RP_CHECK(K % BK == 0, "gemm: K=%d must be a multiple of %d", K, BK);
@@ -714,15 +802,15 @@ int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int6
            "gemm: pointers must be 16-byte aligned");
   // CTA pairs (cta_group::2) need two 128-row blocks; a problem of at most 128 rows runs the single-CTA kernel
   if (M <= BM && epilogue != EPI_BIAS_RESID_LN)
-    return launch_cg<1>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, ln, stream);
-  return launch_cg<2>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, ln, stream);
+    return launch_cg<1>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, ln, stream, nullptr);
+  return launch_cg<2>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, ln, stream, rows);
 }
 
 int launch_gemm(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
                 int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
-                cudaStream_t stream) {
+                cudaStream_t stream, const RowMap* rows) {
   return launch_gemm_ln(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, GemmLnFusion{},
-                        stream);
+                        stream, rows);
 }
 
 }  // namespace rp

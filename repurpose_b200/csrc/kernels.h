@@ -12,10 +12,24 @@ enum GemmEpilogue : int {
   EPI_BIAS_F32 = 2,        // D(f32)  = acc + bias
   EPI_BIAS_RESID_F32 = 3,  // D(f32)  = acc + bias + R   (R may alias D)
   EPI_BIAS_RESID_LN = 4,   // same, plus U(bf16) = LayerNorm(D row; gamma, beta) — N must be 512 (GemmLnFusion::u_out)
+  EPI_HEAD_DOT = 5,        // out[M, nj] = (relu)(relu(acc + bias) . w7[j] + b7[j]): the last two layers of a head in one
+                           // kernel, N must be 256 (launch_gemm_head_dot); nothing of size [M, 256] is written
+};
+// Valid 256-row blocks of a padded [B, T] token matrix (launch_row_map): GEMMs given a RowMap only compute those blocks,
+// i.e. skip blocks that hold nothing but padding rows of short videos.
+struct RowMap {
+  const int32_t* blocks = nullptr;  // [count] ascending block indices (device)
+  const int32_t* count = nullptr;   // device scalar
 };
 int launch_gemm(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
                 int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
-                cudaStream_t stream);
+                cudaStream_t stream, const RowMap* rows = nullptr);
+
+// cls_head / reg_head tail (models/MMCTransformer.py:71-93): Linear(256,256) + ReLU + Linear(256, nj) (+ final ReLU for
+// reg_head) fused: out[m, j] = act(sum_c relu(A[m,:] . W[c,:] + bias[c]) * w7[j, c] + b7[j]), nj = 1 or 2, fp32 out.
+int launch_gemm_head_dot(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* w7,
+                         const float* b7, int nj, bool final_relu, float* out, int M, int K, cudaStream_t stream,
+                         const RowMap* rows = nullptr);
 
 // Arguments of the LayerNorm-fused residual epilogue:
 struct GemmLnFusion {
@@ -30,7 +44,7 @@ struct GemmLnFusion {
 };
 int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
                    int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
-                   const GemmLnFusion& ln, cudaStream_t stream);
+                   const GemmLnFusion& ln, cudaStream_t stream, const RowMap* rows = nullptr);
 
 // Backward GEMMs of the training step, bf16 operands, fp32 accumulation, no bias:
 //   kind 1 (dgrad)  D[M,N] = A[M,K] * B[K,N]      A row-major [M,K] (dY), B row-major [K,N] (an nn.Linear weight
@@ -57,6 +71,9 @@ struct FmhaArgs {
   int mask_mode;
   const uint8_t* mask; int64_t mask_b_stride, mask_q_stride;
   float* lse = nullptr;  // optional output [B, H, Tq] fp32: log2-domain log-sum-exp per score row (training forward)
+  // mask_mode 0 only: query tiles that start at or beyond round_up(kv_lens[b], 128) are padding (self-attention over a
+  // padded batch): their CTAs exit at once and their output rows are left untouched
+  bool skip_padded_queries = false;
 };
 int launch_fmha(const FmhaArgs& a, cudaStream_t stream);
 
@@ -73,6 +90,14 @@ int launch_ragged_concat_cast(const void* vis, const void* aud, const void* txt,
 // lens[b] = number of non-zero bytes of mask[b, 0..T); *not_aligned = 1 if some mask is not of the form
 // t < lens[b] (both device pointers)
 int launch_mask_lens(const uint8_t* mask, int B, int T, int32_t* lens, int32_t* not_aligned, cudaStream_t stream);
+// blocks / count of the RowMap of a padded [B, T] batch: block m (rows 256 m .. 256 m + 255 of the flattened [B*T]
+// matrix) is valid iff it holds a row (b, t) with t < min(T, round_up(lens[b], 128)) — every row an attention key tile
+// of a valid query can touch is computed, whole-padding blocks are not
+int launch_row_map(const int32_t* lens, int B, int T, int32_t* blocks, int32_t* count, cudaStream_t stream);
+// zero the rows t >= lens[b] of the three forward outputs (padded steps carry no information; with block skipping
+// they would otherwise hold whatever the buffers held before)
+int launch_zero_padded_rows(float* logits, float* offsets, float* feats, const int32_t* lens, int B, int T, int D,
+                            cudaStream_t stream);
 // generic fp32 -> bf16 cast of a contiguous buffer (n % 8 == 0)
 int launch_cast_bf16(const float* in, void* out_bf16, int64_t n, cudaStream_t stream);
 

@@ -301,6 +301,63 @@ head_out_kernel(const __nv_bfloat16* __restrict__ ac, const __nv_bfloat16* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// RowMap of a padded batch (kernels.h): one block; flags per 256-row block, then an ordered compaction by warp 0
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+row_map_kernel(const int32_t* __restrict__ lens, int B, int T, int32_t* __restrict__ blocks, int32_t* __restrict__ count) {
+  const int64_t M = int64_t(B) * T;
+  const int nblk = int((M + 255) / 256);
+  // pass 1: flag[m] kept in `blocks` itself (0 / 1)
+  for (int m = threadIdx.x; m < nblk; m += blockDim.x) {
+    const int64_t r0 = int64_t(m) * 256, r1 = r0 + 256 < M ? r0 + 256 : M;
+    int valid = 0;
+    for (int64_t b = r0 / T; b <= (r1 - 1) / T && !valid; ++b) {
+      int len = lens[b];
+      len = len < 0 ? 0 : (len > T ? T : len);
+      int lim = (len + 127) & ~127;
+      if (lim > T) lim = T;
+      const int64_t t0 = r0 > b * T ? r0 - b * T : 0;  // first step of video b inside this block
+      valid = t0 < lim;
+    }
+    blocks[m] = valid;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int out = 0;
+    for (int m0 = 0; m0 < nblk; m0 += 32) {
+      const int m = m0 + threadIdx.x;
+      const int f = m < nblk ? blocks[m] : 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, f != 0);
+      __syncwarp();
+      // in-place ordered compaction is safe: the write index never exceeds the read index
+      if (f) blocks[out + __popc(bal & ((1u << threadIdx.x) - 1u))] = m;
+      out += __popc(bal);
+      __syncwarp();
+    }
+    if (threadIdx.x == 0) *count = out;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+zero_padded_rows_kernel(float* __restrict__ logits, float* __restrict__ offsets, float* __restrict__ feats,
+                        const int32_t* __restrict__ lens, int B, int T, int D) {
+  // one warp per padded row, rows enumerated per video from its length on
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t warps = int64_t(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t row = warp; row < int64_t(B) * T; row += warps) {
+    const int b = int(row / T), t = int(row - int64_t(b) * T);
+    if (t < lens[b]) continue;
+    if (lane == 0) {
+      logits[row] = 0.f;
+      offsets[2 * row] = 0.f;
+      offsets[2 * row + 1] = 0.f;
+    }
+    for (int c = 4 * lane; c < D; c += 128) *reinterpret_cast<float4*>(feats + row * D + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 inline int grid_for(int64_t work_items, int per_block) {
   int64_t blocks = (work_items + per_block - 1) / per_block;
   const int64_t cap = int64_t(num_sms()) * 16;
@@ -383,6 +440,23 @@ int launch_mask_lens(const uint8_t* mask, int B, int T, int32_t* lens, int32_t* 
   RP_CHECK(B > 0 && T > 0, "mask_lens: empty");
   RP_CUDA_CHECK(cudaMemsetAsync(not_aligned, 0, sizeof(int32_t), stream));
   mask_lens_kernel<<<B, 256, 0, stream>>>(mask, T, lens, not_aligned);
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+int launch_row_map(const int32_t* lens, int B, int T, int32_t* blocks, int32_t* count, cudaStream_t stream) {
+  RP_CHECK(B > 0 && T > 0 && lens && blocks && count, "row_map: bad arguments");
+  row_map_kernel<<<1, 256, 0, stream>>>(lens, B, T, blocks, count);
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+
+int launch_zero_padded_rows(float* logits, float* offsets, float* feats, const int32_t* lens, int B, int T, int D,
+                            cudaStream_t stream) {
+  RP_CHECK(B > 0 && T > 0 && D % 4 == 0, "zero_padded_rows: bad arguments");
+  zero_padded_rows_kernel<<<grid_for(int64_t(B) * T, 8), 256, 0, stream>>>(logits, offsets, feats, lens, B, T, D);
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;

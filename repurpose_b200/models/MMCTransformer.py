@@ -249,6 +249,13 @@ class MMCTransformer(nn.Module):
         if self._handle is None or self._weights_sig != self._signature():
             self.refresh_weights()
 
+    def set_skip_padding(self, on: bool):
+        """Extension: whether forward skips the blocks / attention tiles that hold nothing but padding and returns zeros
+        at padded steps (default on; include/repurpose_b200.h rp_set_skip_padding).  Valid steps are bit-identical."""
+        self._ensure_ready()
+        check(_lib.load().rp_set_skip_padding(self._handle, 1 if on else 0), "rp_set_skip_padding")
+        self._graphs = None   # captured graphs hold the old setting
+
     def _get_workspace(self, B, T):
         need = _lib.load().rp_workspace_bytes(self._handle, B, T)
         if need < 0:

@@ -168,6 +168,25 @@ def test_head_out():
     assert torch.allclose(offs, (ar.float() @ wr.T + br).relu(), atol=1e-3, rtol=1e-4)
 
 
+@pytest.mark.parametrize("M", [7, 128, 129, 1000, 57632])
+@pytest.mark.parametrize("nj,final_relu", [(1, False), (2, True)])
+def test_gemm_head_dot_fuses_the_last_two_head_layers(M, nj, final_relu):
+    """Linear(256,256) + ReLU + Linear(256, nj) (+ ReLU): the tail of cls_head / reg_head (models/MMCTransformer.py:71-93)"""
+    gen = torch.Generator(device=DEV).manual_seed(M + nj)
+    a1 = torch.relu(torch.randn(M, 256, device=DEV, generator=gen)).bfloat16()
+    w4 = (torch.randn(256, 256, device=DEV, generator=gen) * 0.08).bfloat16()
+    b4 = torch.randn(256, device=DEV, generator=gen) * 0.1
+    w7 = torch.randn(nj, 256, device=DEV, generator=gen) * 0.1
+    b7 = torch.randn(nj, device=DEV, generator=gen)
+    out = torch.full((M, nj), float("nan"), device=DEV)
+    check(_lib_().rp_gemm_head_dot(ptr(a1), 256, ptr(w4), 256, ptr(b4), ptr(w7), ptr(b7), nj, int(final_relu), ptr(out), M, 256,
+                                   cur_stream()), "gemm_head_dot")
+    ref = torch.relu(a1.float() @ w4.float().T + b4) @ w7.T + b7
+    if final_relu:
+        ref = ref.relu()
+    assert torch.allclose(out, ref, atol=2e-3, rtol=1e-3), (out - ref).abs().max().item()
+
+
 # ------------------------------------------------------------------------------------------ FMHA
 def _fmha(q, k, v, kv_lens=None, mask=None):
     """q [B,Tq,H*64] bf16 (already scaled), k/v [B,Tk,H*64] bf16 (possibly column views)."""

@@ -812,3 +812,25 @@ def test_runtime_switches_keep_parity(env):
                         "forward_matches_oracle_ragged_small or masks_that_are_not"],
                        env={**os.environ, **env}, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_padding_only_blocks_are_skipped_without_touching_valid_steps(full_model):
+    """A caller-built batch of very different lengths (main.py:571-626 builds such batches): the forward skips the
+    256-row blocks / attention query tiles that hold nothing but padding; the valid steps are bit-identical to the
+    run that computes every padded row, and padded steps come back as zeros."""
+    lens = [1801, 300, 64, 900, 1, 1290]
+    batch = synth.make_batch(lens, seed=99)
+    dev = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    full_model.set_skip_padding(False)
+    _, l0, o0, _, _, f0 = full_model(dev)
+    l0, o0, f0 = l0.clone(), o0.clone(), f0.clone()
+    r0 = full_model.inference_(dev, synth.TEST_CFG, to_host=True)
+    full_model.set_skip_padding(True)
+    _, l1, o1, _, _, f1 = full_model(dev)
+    r1 = full_model.inference_(dev, synth.TEST_CFG, to_host=True)
+    valid = batch["masks"][:, 0, :].to(DEV)
+    assert torch.equal(l0[valid], l1[valid]) and torch.equal(o0[valid], o1[valid]) and torch.equal(f0[valid], f1[valid])
+    assert (l1[~valid] == 0).all() and (o1[~valid] == 0).all() and (f1[~valid] == 0).all()
+    assert torch.isfinite(l1).all() and torch.isfinite(f1).all()
+    for a, b in zip(r0, r1):
+        assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["segments"], b["segments"]) and torch.equal(a["scores"], b["scores"])
