@@ -106,7 +106,9 @@ class _GraphedInference:
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # (an explicit capture stream: torch's default one is a process-wide singleton created on the first
+            # capturing device, which a second device of the same process cannot capture on)
+            with torch.cuda.graph(self.graph, stream=side):
                 launch()
         self.workspace = ws                    # the graph holds its address
 
