@@ -420,9 +420,12 @@ def run_ours(args, rank, world, local_rank):
         del model
         torch.cuda.empty_cache()
         from train_bench import run_train_bench
-        r = run_train_bench(16, SEQ, steps=3, warmup=2, rank=rank, world=world, dev=dev)
+        r = run_train_bench(16, SEQ, steps=3, warmup=2, rank=rank, world=world, dev=dev, dropout=0.1)
+        r0 = run_train_bench(16, SEQ, steps=3, warmup=2, rank=rank, world=world, dev=dev, dropout=0.0)
         if rank == 0:
-            extra["train_step"] = r
+            extra["train_step"] = r                      # the reference's train mode: dropout 0.1 at every site
+            extra["train_step_dropout_off"] = {k: r0[k] for k in ("ms_per_step", "forward_ms", "videos_per_s",
+                                                                  "model_tflops_per_gpu", "what")}
 
     if rank == 0:
         flops_step = BATCH * algorithmic_flops_per_video(SEQ)

@@ -222,6 +222,58 @@ int32_t rp_fmha_bwd(const void* q, const void* k, const void* v, const void* o, 
                     float* dsum, void* dq, void* dk, void* dv, int64_t ld_qkv, int64_t ld_o, int64_t ld_dqkv,
                     int32_t B, int32_t H, int32_t T, const int32_t* kv_lens, void* stream);
 
+/* ---- train-mode dropout (the nn.Dropout(0.1) sites of the reference graph under model.train(), main.py:285:
+ * nn.TransformerEncoderLayer's dropout1 / dropout / dropout2 and the attention-weight dropout of its
+ * nn.MultiheadAttention, models/MMCTransformer.py:41-49; feature_map[3], cls_head[3]/[6], reg_head[3]/[6], :63-93).
+ * A site's mask is a pure function of (key_a, key_b, element index): pair k = element >> 1,
+ * h = fmix32(k * 0x9E3779B1 + key_a) ^ key_b, element 2k kept iff (h & 0xffff) >= round(p * 65536), element 2k+1 iff
+ * (h >> 16) >= the same threshold; kept values are scaled by 1 / (1 - p).  The forward epilogues and the backward
+ * kernels evaluate the same function, so nothing is stored for the element-wise sites; the attention-weight mask is
+ * materialised as one keep bit per (query, key).  torch's Philox stream is not reproduced (same distribution,
+ * different draws).
+ *   rp_dropout_mask_u8            keep[i] in {0,1} for the first n elements of a site (tests feed it to autograd)
+ *   rp_attn_dropout_bits          keep bits of an attention site: word w = elements 32 w .. 32 w + 31 (bit = element & 31);
+ *                                 rows of bits_ld words (bits_ld % 4 == 0, 32 * bits_ld >= round_up(T, 128)) per (b, h, query)
+ *   rp_gemm_bf16_dropout          rp_gemm_bf16 epilogue 1 (Dropout after the ReLU) or 3 (Dropout before the residual add);
+ *                                 element index = row * N + column
+ *   rp_layernorm512_dropout       rp_layernorm512 mode 2 with feature_map's Dropout on f (the head LayerNorms see the
+ *                                 dropped row); element index = row * 512 + column
+ *   rp_layernorm512_bwd_acc_dropout  rp_layernorm512_bwd_acc where dh is the output gradient of a residual branch ending in
+ *                                 Dropout: dh_bf16 / dh_colsum hold kept ? dh / (1 - p) : 0, dh_inout stays the stream's gradient
+ *   rp_relu_bwd_scaled, rp_relu_bwd_colsum_scaled, rp_head_out_bwd_scaled
+ *                                 ReLU backward through a stored dropout(relu(.)) activation: act > 0 ? dy * scale : 0
+ *   rp_fmha_train_dropout / rp_fmha_bwd_dropout
+ *                                 out = (keep o softmax(S)) V / (1 - p) and its autograd */
+typedef struct rp_dropout {
+  uint32_t key_a, key_b;
+  float p; /* 0 = off */
+} rp_dropout;
+int32_t rp_dropout_mask_u8(const rp_dropout* drop, int64_t n, uint8_t* keep, void* stream);
+int32_t rp_attn_dropout_bits(const rp_dropout* drop, int64_t n_words, uint32_t* keep_bits, void* stream);
+int32_t rp_gemm_bf16_dropout(int32_t epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
+                             int64_t ldd, const float* bias, const float* resid, int64_t ldr, int32_t M, int32_t N,
+                             int32_t K, const rp_dropout* drop, void* stream);
+int32_t rp_layernorm512_dropout(int32_t mode, const float* x, int64_t M, int32_t T, const float* g0,
+                                const float* b0, const float* g1, const float* b1, const float* g2,
+                                const float* b2, const float* pe, float* out_f32, void* y_bf16, void* y2_bf16,
+                                const rp_dropout* drop, void* stream);
+int32_t rp_layernorm512_bwd_acc_dropout(const float* x, const float* dy, const float* gamma, int64_t M, float eps,
+                                        int32_t accumulate, float* dh_inout, void* dh_bf16, float* dh_colsum,
+                                        float* dgamma, float* dbeta, void* scratch, int64_t scratch_bytes,
+                                        const rp_dropout* drop, void* stream);
+int32_t rp_relu_bwd_scaled(void* dy, const void* act, int64_t n, int32_t is_f32, float scale, void* stream);
+int32_t rp_relu_bwd_colsum_scaled(void* dy_bf16, const void* act_bf16, int64_t M, int32_t N, float scale, float* colsum,
+                                  void* scratch, int64_t scratch_bytes, void* stream);
+int32_t rp_head_out_bwd_scaled(const float* dlogits, const void* a2_bf16, const float* w, int64_t M, float scale,
+                               void* da2_bf16, float* dw, float* db, void* scratch, int64_t scratch_bytes, void* stream);
+int32_t rp_fmha_train_dropout(const void* q, const void* k, const void* v, void* o, int64_t ld_qkv, int64_t ld_o,
+                              int32_t B, int32_t H, int32_t T, const int32_t* kv_lens, float* lse,
+                              const uint32_t* keep_bits, int64_t bits_ld, float p, void* stream);
+int32_t rp_fmha_bwd_dropout(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                            float* dsum, void* dq, void* dk, void* dv, int64_t ld_qkv, int64_t ld_o, int64_t ld_dqkv,
+                            int32_t B, int32_t H, int32_t T, const int32_t* kv_lens, const uint32_t* keep_bits,
+                            int64_t bits_ld, float p, void* stream);
+
 /* ---- building blocks (also what the unit tests drive) ---------------------------------------- */
 /* D[M,N] = A[M,K] * W[N,K]^T + bias (+ReLU | +residual); A, W bf16 row-major with pitches lda/ldw
  * (elements); epilogue: 0 bf16 out, 1 bf16 out + ReLU, 2 f32 out, 3 f32 out + residual (may alias D).

@@ -35,9 +35,16 @@ def _lin(x, sd, prefix):
     return F.linear(x, sd[prefix + ".weight"], sd[prefix + ".bias"])
 
 
-def encoder_layer(h, kpm, sd, p, num_heads):
-    """nn.TransformerEncoderLayer, norm_first=True, ReLU, eval mode (dropout off), as configured at
-    models/MMCTransformer.py:41-49.  kpm [B,T] bool, True = padded key -> -inf before softmax."""
+def _no_drop(site, x):
+    return x
+
+
+def encoder_layer(h, kpm, sd, p, num_heads, drop=_no_drop, layer=0):
+    """nn.TransformerEncoderLayer, norm_first=True, ReLU, as configured at models/MMCTransformer.py:41-49.
+    kpm [B,T] bool, True = padded key -> -inf before softmax.  Eval mode by default; `drop(site, x)` stands for the
+    module's nn.Dropout(0.1) instances under train(): ('attn', l) on the softmax output inside
+    nn.MultiheadAttention, ('drop1', l) = dropout1 after out_proj, ('ffn', l) = dropout after the activation,
+    ('drop2', l) = dropout2 after linear2 (torch/nn/modules/transformer.py _sa_block / _ff_block)."""
     B, T, D = h.shape
     dk = D // num_heads
     u = _ln(h, sd, p + "norm1")
@@ -48,18 +55,20 @@ def encoder_layer(h, kpm, sd, p, num_heads):
     v = v.view(B, T, num_heads, dk).transpose(1, 2)
     s = (q @ k.transpose(-2, -1)) / math.sqrt(dk)
     s = s.masked_fill(kpm[:, None, None, :], float("-inf"))
-    o = torch.softmax(s, dim=-1) @ v
+    o = drop(("attn", layer), torch.softmax(s, dim=-1)) @ v
     o = o.transpose(1, 2).reshape(B, T, D)
-    h = h + _lin(o, sd, p + "self_attn.out_proj")
+    h = h + drop(("drop1", layer), _lin(o, sd, p + "self_attn.out_proj"))
     u = _ln(h, sd, p + "norm2")
-    h = h + _lin(torch.relu(_lin(u, sd, p + "linear1")), sd, p + "linear2")
+    h = h + drop(("drop2", layer), _lin(drop(("ffn", layer), torch.relu(_lin(u, sd, p + "linear1"))), sd, p + "linear2"))
     return h
 
 
 @torch.no_grad()
-def forward(sd, batch, num_heads=8, query_chunk=None):
+def forward(sd, batch, num_heads=8, query_chunk=None, drop=_no_drop):
     """MMCTransformer.forward, models/MMCTransformer.py:109-151.
-    Returns (cls_logits [B,T,1], offsets [B,T,2], feats [B,T,D])."""
+    Returns (cls_logits [B,T,1], offsets [B,T,2], feats [B,T,D]).  `drop(site, x)`: the train-mode nn.Dropout at
+    `site` (see encoder_layer; heads: ('feats', 0) = feature_map[3], ('cls1' | 'cls2' | 'reg1' | 'reg2', 0) =
+    cls_head[3] / [6], reg_head[3] / [6], :63-93); the default is eval mode."""
     x = torch.cat([batch["visual_feats"], batch["audio_feats"], batch["text_feats"]], dim=-1).float()
     B, T, _ = x.shape
     h = _ln(_lin(x, sd, "input_projection"), sd, "input_norm")               # :121, :124
@@ -70,18 +79,18 @@ def forward(sd, batch, num_heads=8, query_chunk=None):
     kpm = (batch["masks"] == 0).squeeze(1)                                      # :132
     n_layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("multimodal_encoder.layers."))
     for l in range(n_layers):                                                   # :135-138
-        h = encoder_layer(h, kpm, sd, f"multimodal_encoder.layers.{l}.", num_heads)
+        h = encoder_layer(h, kpm, sd, f"multimodal_encoder.layers.{l}.", num_heads, drop, l)
     z = _ln(h, sd, "encoder_norm")                                              # :141
-    feats = torch.relu(_ln(_lin(z, sd, "feature_map.0"), sd, "feature_map.1"))  # :63-68, :144
+    feats = drop(("feats", 0), torch.relu(_ln(_lin(z, sd, "feature_map.0"), sd, "feature_map.1")))  # :63-68, :144
 
-    def head(name, final_relu):
+    def head(name, tag, final_relu):
         a = _ln(feats, sd, name + ".0")
-        a = torch.relu(_lin(a, sd, name + ".1"))
-        a = torch.relu(_lin(a, sd, name + ".4"))
+        a = drop((tag + "1", 0), torch.relu(_lin(a, sd, name + ".1")))
+        a = drop((tag + "2", 0), torch.relu(_lin(a, sd, name + ".4")))
         a = _lin(a, sd, name + ".7")
         return torch.relu(a) if final_relu else a
 
-    return head("cls_head", False), head("reg_head", True), feats              # :71-93, :147-149
+    return head("cls_head", "cls", False), head("reg_head", "reg", True), feats  # :71-93, :147-149
 
 
 @torch.no_grad()

@@ -22,6 +22,10 @@ class RpModelCfg(C.Structure):
                                      "num_heads", "d_ff", "head_hidden", "max_len")]
 
 
+class RpDropout(C.Structure):
+    _fields_ = [("key_a", C.c_uint32), ("key_b", C.c_uint32), ("p", c_f32)]
+
+
 class RpDecodeCfg(C.Structure):
     _fields_ = [("pre_nms_topk", c_i32), ("pre_nms_thresh", c_f32), ("duration_thresh", c_f32),
                 ("duration_thresh_max", c_f32), ("nms_sigma", c_f32), ("min_score", c_f32)]
@@ -58,6 +62,20 @@ SIGNATURES = {
     "rp_head_out_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "rp_fmha_train": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "rp_fmha_bwd": (c_i32, [c_vp] * 10 + [c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "rp_dropout_mask_u8": (c_i32, [C.POINTER(RpDropout), c_i64, c_vp, c_vp]),
+    "rp_attn_dropout_bits": (c_i32, [C.POINTER(RpDropout), c_i64, c_vp, c_vp]),
+    "rp_gemm_bf16_dropout": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i32,
+                                     c_i32, c_i32, C.POINTER(RpDropout), c_vp]),
+    "rp_layernorm512_dropout": (c_i32, [c_i32, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                        c_vp, c_vp, c_vp, C.POINTER(RpDropout), c_vp]),
+    "rp_layernorm512_bwd_acc_dropout": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                                c_i64, C.POINTER(RpDropout), c_vp]),
+    "rp_relu_bwd_scaled": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp]),
+    "rp_relu_bwd_colsum_scaled": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_i64, c_vp]),
+    "rp_head_out_bwd_scaled": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "rp_fmha_train_dropout": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64,
+                                      c_f32, c_vp]),
+    "rp_fmha_bwd_dropout": (c_i32, [c_vp] * 10 + [c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_f32, c_vp]),
     "rp_gemm_head_dot": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp]),
     "rp_gemm_resid_ln": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64,
                                  c_i32, c_i32, c_vp]),

@@ -616,14 +616,27 @@ int32_t rp_colsum_bf16(const void* x, int64_t M, int32_t N, float* out, void* sc
 
 int32_t rp_relu_bwd(void* dy, const void* act, int64_t n, int32_t is_f32, void* stream) {
   RP_CHECK(dy && act, "rp_relu_bwd: null argument");
-  return launch_relu_bwd(dy, act, n, is_f32 != 0, reinterpret_cast<cudaStream_t>(stream));
+  return launch_relu_bwd(dy, act, n, is_f32 != 0, 1.0f, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_relu_bwd_scaled(void* dy, const void* act, int64_t n, int32_t is_f32, float scale, void* stream) {
+  RP_CHECK(dy && act, "rp_relu_bwd_scaled: null argument");
+  return launch_relu_bwd(dy, act, n, is_f32 != 0, scale, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int32_t rp_relu_bwd_colsum(void* dy_bf16, const void* act_bf16, int64_t M, int32_t N, float* colsum, void* scratch,
                            int64_t scratch_bytes, void* stream) {
   RP_CHECK(dy_bf16 && act_bf16 && colsum && scratch, "rp_relu_bwd_colsum: null argument");
   RP_CHECK(scratch_bytes >= rp_train_scratch_bytes(), "rp_relu_bwd_colsum: scratch too small");
-  return launch_relu_bwd_colsum(dy_bf16, act_bf16, M, N, colsum, reinterpret_cast<float*>(scratch),
+  return launch_relu_bwd_colsum(dy_bf16, act_bf16, M, N, 1.0f, colsum, reinterpret_cast<float*>(scratch),
+                                reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_relu_bwd_colsum_scaled(void* dy_bf16, const void* act_bf16, int64_t M, int32_t N, float scale, float* colsum,
+                                  void* scratch, int64_t scratch_bytes, void* stream) {
+  RP_CHECK(dy_bf16 && act_bf16 && colsum && scratch, "rp_relu_bwd_colsum_scaled: null argument");
+  RP_CHECK(scratch_bytes >= rp_train_scratch_bytes(), "rp_relu_bwd_colsum_scaled: scratch too small");
+  return launch_relu_bwd_colsum(dy_bf16, act_bf16, M, N, scale, colsum, reinterpret_cast<float*>(scratch),
                                 reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -631,7 +644,15 @@ int32_t rp_head_out_bwd(const float* dlogits, const void* a2_bf16, const float* 
                         float* dw, float* db, void* scratch, int64_t scratch_bytes, void* stream) {
   RP_CHECK(dlogits && a2_bf16 && w && da2_bf16 && dw && db && scratch, "rp_head_out_bwd: null argument");
   RP_CHECK(scratch_bytes >= rp_train_scratch_bytes(), "rp_head_out_bwd: scratch too small");
-  return launch_head_out_bwd(dlogits, a2_bf16, w, M, da2_bf16, dw, db, reinterpret_cast<float*>(scratch),
+  return launch_head_out_bwd(dlogits, a2_bf16, w, M, 1.0f, da2_bf16, dw, db, reinterpret_cast<float*>(scratch),
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_head_out_bwd_scaled(const float* dlogits, const void* a2_bf16, const float* w, int64_t M, float scale,
+                               void* da2_bf16, float* dw, float* db, void* scratch, int64_t scratch_bytes, void* stream) {
+  RP_CHECK(dlogits && a2_bf16 && w && da2_bf16 && dw && db && scratch, "rp_head_out_bwd_scaled: null argument");
+  RP_CHECK(scratch_bytes >= rp_train_scratch_bytes(), "rp_head_out_bwd_scaled: scratch too small");
+  return launch_head_out_bwd(dlogits, a2_bf16, w, M, scale, da2_bf16, dw, db, reinterpret_cast<float*>(scratch),
                              reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -647,11 +668,75 @@ int32_t rp_fmha_train(const void* q, const void* k, const void* v, void* o, int6
   return launch_fmha(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int32_t rp_fmha_train_dropout(const void* q, const void* k, const void* v, void* o, int64_t ld_qkv, int64_t ld_o,
+                              int32_t B, int32_t H, int32_t T, const int32_t* kv_lens, float* lse,
+                              const uint32_t* keep_bits, int64_t bits_ld, float p, void* stream) {
+  RP_CHECK(q && k && v && o && lse && keep_bits, "rp_fmha_train_dropout: null argument");
+  RP_CHECK(p > 0.0f && p < 1.0f, "rp_fmha_train_dropout: 0 < p < 1");
+  FmhaArgs a{};
+  a.q = q; a.k = k; a.v = v; a.o = o;
+  a.ldq = a.ldk = a.ldv = ld_qkv; a.ldo = ld_o;
+  a.bsq = a.bsk = a.bsv = int64_t(T) * ld_qkv; a.bso = int64_t(T) * ld_o;
+  a.B = B; a.H = H; a.Tq = T; a.Tk = T; a.kv_lens = kv_lens; a.mask_mode = 0;
+  a.lse = lse;
+  a.drop_bits = keep_bits; a.drop_ld = bits_ld; a.drop_scale = 1.0f / (1.0f - p);
+  return launch_fmha(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int32_t rp_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                     float* dsum, void* dq, void* dk, void* dv, int64_t ld_qkv, int64_t ld_o, int64_t ld_dqkv,
                     int32_t B, int32_t H, int32_t T, const int32_t* kv_lens, void* stream) {
   FmhaBwdArgs a{q, k, v, o, d_o, lse, dsum, dq, dk, dv, ld_qkv, ld_o, ld_dqkv, B, H, T, kv_lens};
   return launch_fmha_bwd(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_fmha_bwd_dropout(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                            float* dsum, void* dq, void* dk, void* dv, int64_t ld_qkv, int64_t ld_o, int64_t ld_dqkv,
+                            int32_t B, int32_t H, int32_t T, const int32_t* kv_lens, const uint32_t* keep_bits,
+                            int64_t bits_ld, float p, void* stream) {
+  RP_CHECK(keep_bits != nullptr && p > 0.0f && p < 1.0f, "rp_fmha_bwd_dropout: keep bits and 0 < p < 1 required");
+  FmhaBwdArgs a{q, k, v, o, d_o, lse, dsum, dq, dk, dv, ld_qkv, ld_o, ld_dqkv, B, H, T, kv_lens};
+  a.drop_bits = keep_bits; a.drop_ld = bits_ld; a.drop_scale = 1.0f / (1.0f - p);
+  return launch_fmha_bwd(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+static DropKey drop_key_of(const rp_dropout* d) {
+  return (d == nullptr || !(d->p > 0.0f)) ? DropKey{} : make_drop_key(d->key_a, d->key_b, d->p);
+}
+#define RP_CHECK_DROP(d, what) RP_CHECK((d) == nullptr || ((d)->p >= 0.0f && (d)->p < 1.0f), what ": 0 <= p < 1")
+
+int32_t rp_dropout_mask_u8(const rp_dropout* drop, int64_t n, uint8_t* keep, void* stream) {
+  RP_CHECK(drop && keep, "rp_dropout_mask_u8: null argument");
+  RP_CHECK_DROP(drop, "rp_dropout_mask_u8");
+  return launch_dropout_mask_u8(keep, n, drop_key_of(drop), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_attn_dropout_bits(const rp_dropout* drop, int64_t n_words, uint32_t* keep_bits, void* stream) {
+  RP_CHECK(drop && keep_bits, "rp_attn_dropout_bits: null argument");
+  RP_CHECK_DROP(drop, "rp_attn_dropout_bits");
+  return launch_attn_dropout_bits(keep_bits, n_words, drop_key_of(drop), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_layernorm512_bwd_acc_dropout(const float* x, const float* dy, const float* gamma, int64_t M, float eps,
+                                        int32_t accumulate, float* dh_inout, void* dh_bf16, float* dh_colsum,
+                                        float* dgamma, float* dbeta, void* scratch, int64_t scratch_bytes,
+                                        const rp_dropout* drop, void* stream) {
+  RP_CHECK(x && dy && gamma && dh_inout && dgamma && dbeta && scratch, "rp_layernorm512_bwd_acc_dropout: null argument");
+  RP_CHECK(scratch_bytes >= rp_train_scratch_bytes(), "rp_layernorm512_bwd_acc_dropout: scratch too small");
+  RP_CHECK_DROP(drop, "rp_layernorm512_bwd_acc_dropout");
+  const DropKey key = drop_key_of(drop);
+  return launch_layernorm512_bwd(x, dy, gamma, M, eps, dh_inout, dgamma, dbeta, reinterpret_cast<float*>(scratch),
+                                 reinterpret_cast<cudaStream_t>(stream), accumulate != 0, dh_bf16, dh_colsum,
+                                 key.thr != 0u ? &key : nullptr);
+}
+
+int32_t rp_gemm_bf16_dropout(int32_t epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
+                             int64_t ldd, const float* bias, const float* resid, int64_t ldr, int32_t M, int32_t N,
+                             int32_t K, const rp_dropout* drop, void* stream) {
+  RP_CHECK(A && W && D, "rp_gemm_bf16_dropout: null argument");
+  RP_CHECK_DROP(drop, "rp_gemm_bf16_dropout");
+  return launch_gemm_dropout(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, drop_key_of(drop),
+                             reinterpret_cast<cudaStream_t>(stream));
 }
 
 int32_t rp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
@@ -726,6 +811,21 @@ int32_t rp_layernorm512(int32_t mode, const float* x, int64_t M, int32_t T, cons
   LnArgs a{};
   a.x = x; a.M = M; a.T = T; a.g0 = g0; a.b0 = b0; a.g1 = g1; a.b1 = b1; a.g2 = g2; a.b2 = b2;
   a.pe = pe; a.out_f32 = out_f32; a.y_bf16 = y_bf16; a.y2_bf16 = y2_bf16; a.eps = 1e-5f;
+  return launch_layernorm512(mode, a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int32_t rp_layernorm512_dropout(int32_t mode, const float* x, int64_t M, int32_t T, const float* g0,
+                                const float* b0, const float* g1, const float* b1, const float* g2,
+                                const float* b2, const float* pe, float* out_f32, void* y_bf16, void* y2_bf16,
+                                const rp_dropout* drop, void* stream) {
+  RP_CHECK(x && g0 && b0, "rp_layernorm512_dropout: null argument");
+  RP_CHECK(mode == 2, "rp_layernorm512_dropout: only mode 2 (feature_map) is followed by a Dropout");
+  RP_CHECK_DROP(drop, "rp_layernorm512_dropout");
+  RP_CHECK(M * 512 < (int64_t(1) << 32), "rp_layernorm512_dropout: dropout sites hold fewer than 2^32 elements");
+  LnArgs a{};
+  a.x = x; a.M = M; a.T = T; a.g0 = g0; a.b0 = b0; a.g1 = g1; a.b1 = b1; a.g2 = g2; a.b2 = b2;
+  a.pe = pe; a.out_f32 = out_f32; a.y_bf16 = y_bf16; a.y2_bf16 = y2_bf16; a.eps = 1e-5f;
+  a.drop = drop_key_of(drop);
   return launch_layernorm512(mode, a, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -109,6 +109,10 @@ struct FmhaParams {
   int64_t mask_b_stride, mask_q_stride;
   float* lse;  // optional [B, H, Tq]: log2-domain log-sum-exp of every score row (what the backward pass recomputes P from)
   int skip_padded_queries;  // query tiles at or beyond round_up(kv_len, 128) are padding: exit at once
+  // DROP kernels (training forward): keep bits of the attention weights, row (b*H + h)*Tq + q, drop_ld words per row
+  const uint32_t* drop_bits;
+  int64_t drop_ld;
+  float drop_scale;
 };
 
 // ---- packed f32x2 helpers (sm_100 FFMA2/FADD2) ---------------------------------------------------
@@ -161,7 +165,9 @@ __device__ __forceinline__ void exp2_emulated2(unsigned long long x2, float& p0,
   p1 = __uint_as_float((__float_as_uint(t1) << 23) + __float_as_uint(q1));
 }
 
-template <int MASK_MODE, int EMU_PAIRS, int NQ>
+// DROP: nn.MultiheadAttention's dropout on the attention weights (train mode): the row sum l runs over every weight, the
+// P tile handed to P V holds the kept ones only, and the epilogue scales by 1 / (1 - p) — out = (keep o softmax(S)) V / (1 - p)
+template <int MASK_MODE, int EMU_PAIRS, int NQ, bool DROP = false>
 __global__ void __launch_bounds__(Cfg<NQ>::NUM_THREADS, Cfg<NQ>::MIN_CTAS)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -404,6 +410,24 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       uint32_t xs[128];  // scores of the current tile -> probabilities -> scores of the next tile
       const bool lane0 = pin_u32(lane == 0 ? 1u : 0u) != 0u;
+      // DROP: the 128 keep bits of this row for the current key tile (4 words), fetched one tile ahead
+      const uint4* brow = nullptr;
+      uint4 wcur = make_uint4(~0u, ~0u, ~0u, ~0u);
+      if constexpr (DROP) {
+        const int qrow = q_start + row_in_tile < p.Tq ? q_start + row_in_tile : p.Tq - 1;
+        brow = reinterpret_cast<const uint4*>(p.drop_bits + ((int64_t(b) * p.H + head) * p.Tq + qrow) * p.drop_ld);
+        if (n_kv > 0) wcur = __ldg(brow);
+      }
+      // the bf16 pair (p0, p1) = keys 2 * pair, 2 * pair + 1 of the tile with the dropped weights zeroed
+      auto pack_kept = [&](int pair, float p0, float p1) {
+        if constexpr (DROP) {
+          const uint32_t w = pair < 16 ? wcur.x : (pair < 32 ? wcur.y : (pair < 48 ? wcur.z : wcur.w));
+          const int bit = (2 * pair) & 31;
+          p0 = (w & (1u << bit)) ? p0 : 0.0f;
+          p1 = (w & (2u << bit)) ? p1 : 0.0f;
+        }
+        return pack_bf16x2(p0, p1);
+      };
 
       // running max of chunk c (CH scores)
       auto max_chunk = [&](int c, float& mx0, float& mx1) {
@@ -462,6 +486,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const unsigned long long negm2 = pack2(-m, -m);
         float mx0 = -INFINITY, mx1 = -INFINITY;
         uint32_t probe_pv = 0, probe_s = 0;
+        uint4 wnext = wcur;
+        if constexpr (DROP) wnext = __ldg(brow + (j + 1));
         if (tracer) TRACE(4, 2 * j);
 #pragma unroll
         for (int s = 0; s <= NCH; ++s) {
@@ -525,7 +551,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const float p0 = __uint_as_float(xs[CH * c + 2 * i]), p1 = __uint_as_float(xs[CH * c + 2 * i + 1]);
                 if (i & 1) lsumB = add2(lsumB, pack2(p0, p1));
                 else lsumA = add2(lsumA, pack2(p0, p1));
-                pk[i] = pack_bf16x2(p0, p1);
+                pk[i] = pack_kept((CH / 2) * c + i, p0, p1);
               }
               if (CH == 16) {
                 tmem_st8(t_p + (CH / 2) * c, pk);
@@ -548,6 +574,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mbar_arrive(p_ready(q, 1));
           mbar_arrive(s_free(q, 1));
         }
+        if constexpr (DROP) wcur = wnext;
         {
           if (tile_needs_mask(j + 1)) mask_tile(j + 1, mx0, mx1);
           const float mnext = fmaxf(m, fmaxf(mx0, mx1));
@@ -608,7 +635,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               }
               if (i & 1) lsumB = add2(lsumB, pack2(p0, p1));
               else lsumA = add2(lsumA, pack2(p0, p1));
-              pk[i] = pack_bf16x2(p0, p1);
+              pk[i] = pack_kept((CH / 2) * c + i, p0, p1);
             }
             if (CH == 16) tmem_st8(t_p + (CH / 2) * c, pk);
             else tmem_st16(t_p + (CH / 2) * c, pk);
@@ -633,6 +660,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         unpack2(lsumB, b0, b1);
         const float l_row = (a0 + a1) + (b0 + b1);
         inv_l = 1.0f / l_row;
+        if constexpr (DROP) inv_l *= p.drop_scale;
         if (p.lse != nullptr && q_start + row_in_tile < p.Tq)
           p.lse[(int64_t(b) * p.H + head) * p.Tq + q_start + row_in_tile] = m + log2f(l_row);
         mbar_wait(pv_done(q, 0), uint32_t(n_kv - 1) & 1u);
@@ -681,20 +709,20 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 
 
-template <int MASK_MODE, int EMU_PAIRS, int NQ>
+template <int MASK_MODE, int EMU_PAIRS, int NQ, bool DROP = false>
 int launch_variant(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                    const CUtensorMap& tmO, const FmhaParams& p, cudaStream_t stream) {
   using C = Cfg<NQ>;
   static bool configured_on[kMaxDevices];
   bool& configured = configured_on[current_device()];
   if (!configured) {
-    RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ>,
+    RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ, DROP>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));
     configured = true;
   }
   dim3 grid(unsigned((p.Tq + NQ * QT - 1) / (NQ * QT)) * unsigned(p.H) * unsigned(p.B));
-  RP_CUDA_CHECK(launch_pdl(fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ>, grid, dim3(C::NUM_THREADS), C::SMEM_TOTAL, stream,
-                           tmQ, tmK, tmV, tmO, p));
+  RP_CUDA_CHECK(launch_pdl(fmha_fwd_kernel<MASK_MODE, EMU_PAIRS, NQ, DROP>, grid, dim3(C::NUM_THREADS), C::SMEM_TOTAL,
+                           stream, tmQ, tmK, tmV, tmO, p));
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;
@@ -729,7 +757,15 @@ int launch_fmha(const FmhaArgs& a, cudaStream_t stream) {
   if ((rc = make_tmap_3d(&tmO, bf, a.o, cols, a.Tq, a.B, a.ldo * 2, a.bso * 2, HD, QT))) return rc;
 
   FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride, a.lse,
-               (a.skip_padded_queries && a.kv_lens != nullptr && a.Tq == a.Tk) ? 1 : 0};
+               (a.skip_padded_queries && a.kv_lens != nullptr && a.Tq == a.Tk) ? 1 : 0,
+               a.drop_bits, a.drop_ld, a.drop_scale};
+  if (a.drop_bits != nullptr) {
+    RP_CHECK(a.mask_mode == 0, "fmha: attention-weight dropout is built for the key-padding mode");
+    RP_CHECK(a.drop_ld % 4 == 0 && a.drop_ld * 32 >= ((int64_t(a.Tk) + KT - 1) / KT) * KT &&
+                 reinterpret_cast<uintptr_t>(a.drop_bits) % 16 == 0,
+             "fmha: keep-bit rows must be 16-byte aligned and cover every 128-key tile");
+    return launch_variant<0, 1, 1, true>(tmQ, tmK, tmV, tmO, p, stream);
+  }
   // One build of the kernel ships (NQ = 1: two independent CTAs per SM; one exp2 pair in four on the FMA pipe).
   // The alternatives that were built, verified and measured — NQ = 2, 0 or 2 emulated pairs, a 64-key-tile
   // three-CTA variant and a two-warpgroup ping-pong kernel — live under tools/experiments/ with their numbers.

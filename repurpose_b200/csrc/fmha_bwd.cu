@@ -5,6 +5,8 @@
 // With S2 = Q' K^T (Q' = q log2(e)/8 as the forward stores it), P = 2^(S2 - lse2) and Dsum = rowsum(dO o O):
 //     dSt = P o (dO V^T - Dsum)            gradient w.r.t. the true logits q.k/8
 //     dV  = P^T dO        dK = ln2 dSt^T Q'  (= dSt^T q / 8)        dQ = dSt K / 8   (w.r.t. the UNSCALED q)
+// With attention-weight dropout (DROP kernels; O = (keep o P) V / (1 - p) in the forward): dV = (keep o P / (1 - p))^T dO,
+// dSt = P o (keep o (dO V^T) / (1 - p) - Dsum); Dsum = rowsum(dO o O) holds unchanged with the dropped O.
 // P is recomputed from the log-sum-exp the forward wrote (FmhaArgs::lse); nothing of size T x T is stored.
 //
 // Two kernels, both deterministic (no atomics):
@@ -36,6 +38,10 @@ struct BwdParams {
   const int32_t* kv_lens;
   const float* lse;    // [B, H, T] log2-domain log-sum-exp from the forward
   const float* dsum;   // [B, H, T] rowsum(dO o O)
+  // DROP kernels: keep bits of the forward's attention-weight dropout (fmha.cu), row (b*H + h)*T + q, drop_ld words per row
+  const uint32_t* drop_bits;
+  int64_t drop_ld;
+  float drop_scale;
 };
 
 // bf16 rows of 128 bytes -> swizzled (SWIZZLE_128B) staging tile for a TMA store: row r, 16-byte chunk c
@@ -74,6 +80,7 @@ constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;
 constexpr int TM_S = 0, TM_DP = 64, TM_DS = 128, TM_DQ = 160, TMEM_COLS = 256;
 }  // namespace dq
 
+template <bool DROP>
 __global__ void __launch_bounds__(192, 2)
 fmha_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -195,7 +202,12 @@ fmha_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float lse_r = valid ? p.lse[stat] : INFINITY;
     const float dsum_r = valid ? p.dsum[stat] : 0.0f;
     const uint32_t t_lane = tmem + (uint32_t(warp * 32) << 16);
+    const uint2* brow = nullptr;  // DROP: this query row's keep bits, two words per 64-key tile
+    if constexpr (DROP)
+      brow = reinterpret_cast<const uint2*>(p.drop_bits + ((int64_t(b) * p.H + head) * p.T + (valid ? qrow : p.T - 1)) * p.drop_ld);
     for (int j = 0; j < n_kv; ++j) {
+      uint2 wj = make_uint2(~0u, ~0u);
+      if constexpr (DROP) wj = __ldg(brow + j);  // (requested before the barrier wait)
       mbar_wait(sdp_full, uint32_t(j) & 1u);
       tc_fence_after();
       const int nv = kv_len - j * KT;  // valid keys in this tile (>= KT: all)
@@ -217,7 +229,9 @@ fmha_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int e = 0; e < 2; ++e) {
             const int c = 32 * half + 2 * i + e;
             const float pr = c < nv ? ex2_approx(__uint_as_float(s[2 * i + e]) - lse_r) : 0.0f;
-            d2[e] = pr * (__uint_as_float(dp[2 * i + e]) - dsum_r) * 0.125f;
+            float dpv = __uint_as_float(dp[2 * i + e]);
+            if constexpr (DROP) dpv = ((half ? wj.y : wj.x) & (1u << (2 * i + e))) ? dpv * p.drop_scale : 0.0f;
+            d2[e] = pr * (dpv - dsum_r) * 0.125f;
           }
           pk[i] = pack_bf16x2(d2[0], d2[1]);
         }
@@ -266,11 +280,13 @@ constexpr int KT = 128, QT = 64, STAGES = 3;
 constexpr int KV_BYTES = KT * HD * 2, Q_BYTES = QT * HD * 2;
 constexpr int SMEM_K = 0, SMEM_V = KV_BYTES, SMEM_RING = 2 * KV_BYTES;  // stage s: Q_i at +2 s Q_BYTES, dO_i after it
 constexpr int SMEM_STAT = SMEM_RING + STAGES * 2 * Q_BYTES;             // [2 buffers][lse 64 | dsum 64] floats
-constexpr int SMEM_BAR = SMEM_STAT + 2 * 128 * 4;
+constexpr int SMEM_DROP = SMEM_STAT + 2 * 128 * 4;                      // [2 buffers][64 queries][4 words] keep bits
+constexpr int SMEM_BAR = SMEM_DROP + 2 * 64 * 4 * 4;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;
 constexpr int TM_ST = 0, TM_DPT = 128, TM_PT = 256, TM_DST = 288, TM_DV = 320, TM_DK = 384, TMEM_COLS = 512;
 }  // namespace dkv
 
+template <bool DROP>
 __global__ void __launch_bounds__(192, 1)
 fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -418,10 +434,24 @@ fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (tid < 64) return qi < p.T ? p.lse[stat_base + qi] : INFINITY;
       return qi < p.T ? p.dsum[stat_base + qi] : 0.0f;
     };
+    // DROP: keep bits of this tile's 128 keys for the 64 queries of a query tile: thread tid fetches words
+    // 4 kb + 2 (tid & 1), +1 of query tid >> 1 (one tile ahead, like the statistics); warp w then reads word w of each
+    // query as a broadcast and tests bit `lane` — the transposed walk over the mask the forward used
+    uint32_t* dbits = reinterpret_cast<uint32_t*>(smem + SMEM_DROP);
+    auto fetch_bits = [&](int i) {
+      const int qi = i * QT + (tid >> 1);
+      if (qi >= p.T) return make_uint2(0u, 0u);
+      return __ldg(reinterpret_cast<const uint2*>(p.drop_bits + (stat_base + qi) * p.drop_ld + 4 * kb + 2 * (tid & 1)));
+    };
     stat[tid] = fetch_stat(0);
+    if constexpr (DROP) reinterpret_cast<uint2*>(dbits)[tid] = fetch_bits(0);
     for (int i = 0; i < n_q; ++i) {
       const int bf = i & 1;
       const float nxt = i + 1 < n_q ? fetch_stat(i + 1) : 0.0f;
+      uint2 nxt_bits = make_uint2(0u, 0u);
+      if constexpr (DROP) {
+        if (i + 1 < n_q) nxt_bits = fetch_bits(i + 1);
+      }
       named_bar_sync(1, 128);  // buffer bf is complete (written at the end of the previous iteration)
       const float4* lse4 = reinterpret_cast<const float4*>(stat + 128 * bf);
       const float4* ds4 = reinterpret_cast<const float4*>(stat + 128 * bf + 64);
@@ -447,7 +477,15 @@ fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             pr[e] = kvalid ? ex2_approx(__uint_as_float(s[4 * g + e]) - lq[e]) : 0.0f;
-            dsv[e] = pr[e] * (__uint_as_float(dp[4 * g + e]) - dq_[e]) * LN2;
+            float dpv = __uint_as_float(dp[4 * g + e]);
+            if constexpr (DROP) {
+              const bool keep = (dbits[(bf * 64 + 32 * half + 4 * g + e) * 4 + warp] >> lane) & 1u;
+              dpv = keep ? dpv * p.drop_scale : 0.0f;
+              dsv[e] = pr[e] * (dpv - dq_[e]) * LN2;
+              pr[e] = keep ? pr[e] * p.drop_scale : 0.0f;  // P_d^T feeds dV
+            } else {
+              dsv[e] = pr[e] * (dpv - dq_[e]) * LN2;
+            }
           }
           pp[2 * g] = pack_bf16x2(pr[0], pr[1]);
           pp[2 * g + 1] = pack_bf16x2(pr[2], pr[3]);
@@ -466,6 +504,7 @@ fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
       stat[128 * (bf ^ 1) + tid] = nxt;
+      if constexpr (DROP) reinterpret_cast<uint2*>(dbits)[128 * (bf ^ 1) + tid] = nxt_bits;
     }
     // ---- epilogue: dV, dK -> bf16 -> swizzled smem (the K / V tiles' slots) -> TMA stores
     mbar_wait(p_free, uint32_t(n_q - 1) & 1u);
@@ -502,7 +541,11 @@ int launch_fmha_bwd(const FmhaBwdArgs& a, cudaStream_t stream) {
   const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   int rc;
   if ((rc = launch_attn_bwd_dsum(a.o, a.d_o, a.B, a.T, a.H, a.dsum, stream))) return rc;
-  BwdParams p{a.B, a.H, a.T, a.kv_lens, a.lse, a.dsum};
+  BwdParams p{a.B, a.H, a.T, a.kv_lens, a.lse, a.dsum, a.drop_bits, a.drop_ld, a.drop_scale};
+  const bool drop = a.drop_bits != nullptr;
+  RP_CHECK(!drop || (a.drop_ld % 4 == 0 && a.drop_ld * 32 >= ((int64_t(a.T) + 127) / 128) * 128 &&
+                     reinterpret_cast<uintptr_t>(a.drop_bits) % 16 == 0),
+           "fmha_bwd: keep-bit rows must be 16-byte aligned and cover every 128-key tile");
   const uint64_t T = a.T, B = a.B;
   {
     CUtensorMap tmQ, tmK, tmV, tmdO, tmdQ;
@@ -514,11 +557,15 @@ int launch_fmha_bwd(const FmhaBwdArgs& a, cudaStream_t stream) {
     static bool configured_on[kMaxDevices];
     bool& configured = configured_on[current_device()];
     if (!configured) {
-      RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dq::SMEM_TOTAL));
+      RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dq::SMEM_TOTAL));
+      RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dq::SMEM_TOTAL));
       configured = true;
     }
     const unsigned grid = unsigned((a.T + dq::QT - 1) / dq::QT) * unsigned(a.H) * unsigned(a.B);
-    RP_CUDA_CHECK(launch_pdl(fmha_bwd_dq_kernel, dim3(grid), dim3(192), dq::SMEM_TOTAL, stream, tmQ, tmK, tmV, tmdO, tmdQ, p));
+    if (drop)
+      RP_CUDA_CHECK(launch_pdl(fmha_bwd_dq_kernel<true>, dim3(grid), dim3(192), dq::SMEM_TOTAL, stream, tmQ, tmK, tmV, tmdO, tmdQ, p));
+    else
+      RP_CUDA_CHECK(launch_pdl(fmha_bwd_dq_kernel<false>, dim3(grid), dim3(192), dq::SMEM_TOTAL, stream, tmQ, tmK, tmV, tmdO, tmdQ, p));
     count_launch();
   }
   {
@@ -532,12 +579,17 @@ int launch_fmha_bwd(const FmhaBwdArgs& a, cudaStream_t stream) {
     static bool configured_on[kMaxDevices];
     bool& configured = configured_on[current_device()];
     if (!configured) {
-      RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dkv::SMEM_TOTAL));
+      RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_bwd_dkdv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dkv::SMEM_TOTAL));
+      RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_bwd_dkdv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dkv::SMEM_TOTAL));
       configured = true;
     }
     const unsigned grid = unsigned((a.T + dkv::KT - 1) / dkv::KT) * unsigned(a.H) * unsigned(a.B);
-    RP_CUDA_CHECK(launch_pdl(fmha_bwd_dkdv_kernel, dim3(grid), dim3(192), dkv::SMEM_TOTAL, stream, tmQ, tmK, tmV, tmdO, tmdK,
-                             tmdV, p));
+    if (drop)
+      RP_CUDA_CHECK(launch_pdl(fmha_bwd_dkdv_kernel<true>, dim3(grid), dim3(192), dkv::SMEM_TOTAL, stream, tmQ, tmK, tmV, tmdO,
+                               tmdK, tmdV, p));
+    else
+      RP_CUDA_CHECK(launch_pdl(fmha_bwd_dkdv_kernel<false>, dim3(grid), dim3(192), dkv::SMEM_TOTAL, stream, tmQ, tmK, tmV, tmdO,
+                               tmdK, tmdV, p));
     count_launch();
   }
   RP_CUDA_CHECK(cudaGetLastError());

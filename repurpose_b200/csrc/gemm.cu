@@ -89,6 +89,7 @@ struct GemmArgs {
   const int32_t* row_count = nullptr;
   int splits = 1;        // split-K: split s reduces k-blocks [s * kb_per_split, ...) and writes rows [s*M, (s+1)*M) of D
   int kb_per_split = 0;  // (0 = all)
+  DropKey drop;          // train-mode forward: nn.Dropout on (acc + bias [ReLU]) before the residual add (thr = 0: off)
 };
 
 // TR selects the operand layouts (the backward GEMMs of the training step):
@@ -378,6 +379,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int i = 0; i < 32; ++i)
               v[i] = __float_as_uint(fmaxf(__uint_as_float(v[i]), 0.0f));
           }
+          if constexpr (EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_BIAS_RESID_F32) {
+            if (g.drop.thr != 0u) {  // (uniform branch on a kernel parameter; inference launches never take it)
+              const uint32_t k0 = (uint32_t(row0 + lane) * uint32_t(g.N) + uint32_t(col0)) >> 1;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float a0 = __uint_as_float(v[2 * i]), a1 = __uint_as_float(v[2 * i + 1]);
+                drop_pair(k0 + uint32_t(i), g.drop, a0, a1);
+                v[2 * i] = __float_as_uint(a0);
+                v[2 * i + 1] = __float_as_uint(a1);
+              }
+            }
+          }
           const uint32_t row_addr = slab + uint32_t(lane) * 128u;
           if constexpr (OUT_F32) {
 #pragma unroll
@@ -649,7 +662,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
 template <int CG>
 int launch_cg(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd,
               const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
-              const GemmLnFusion& ln, cudaStream_t stream, const RowMap* rows) {
+              const GemmLnFusion& ln, cudaStream_t stream, const RowMap* rows, const DropKey* drop = nullptr) {
   const bool resid_epi = (epilogue == EPI_BIAS_RESID_F32 || epilogue == EPI_BIAS_RESID_LN);
   const bool out_f32 = (epilogue == EPI_BIAS_F32 || resid_epi);
   CUtensorMap tmA, tmB, tmD, tmR, tmU;
@@ -670,6 +683,7 @@ int launch_cg(int epilogue, const void* A, int64_t lda, const void* W, int64_t l
     return rc;
 
   GemmArgs g{M, N, K, bias, ln};
+  if (drop != nullptr) g.drop = *drop;
   if (CG == 2 && rows != nullptr) {  // (256-row blocks are the CTA pair's tile height)
     g.row_blocks = rows->blocks;
     g.row_count = rows->count;
@@ -781,9 +795,10 @@ int launch_gemm_head_dot(const void* A, int64_t lda, const void* W, int64_t ldw,
   return launch_one<EPI_HEAD_DOT, 1>(tmA, tmB, tmA, tmA, tmA, g, 1, stream);
 }
 
-int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
-                   int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
-                   const GemmLnFusion& ln, cudaStream_t stream, const RowMap* rows) {
+namespace {
+int launch_gemm_checked(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
+                        int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
+                        const GemmLnFusion& ln, cudaStream_t stream, const RowMap* rows, const DropKey* drop) {
   RP_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   RP_CHECK(N % BN == 0, "gemm: N=%d must be a multiple of %d", N, BN);
   RP_CHECK(K % BK == 0, "gemm: K=%d must be a multiple of %d", K, BK);
@@ -802,8 +817,25 @@ int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int6
            "gemm: pointers must be 16-byte aligned");
   // CTA pairs (cta_group::2) need two 128-row blocks; a problem of at most 128 rows runs the single-CTA kernel
   if (M <= BM && epilogue != EPI_BIAS_RESID_LN)
-    return launch_cg<1>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, ln, stream, nullptr);
-  return launch_cg<2>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, ln, stream, rows);
+    return launch_cg<1>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, ln, stream, nullptr, drop);
+  return launch_cg<2>(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, ln, stream, rows, drop);
+}
+}  // namespace
+
+int launch_gemm_ln(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
+                   int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
+                   const GemmLnFusion& ln, cudaStream_t stream, const RowMap* rows) {
+  return launch_gemm_checked(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, ln, stream, rows, nullptr);
+}
+
+int launch_gemm_dropout(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
+                        int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
+                        const DropKey& drop, cudaStream_t stream) {
+  RP_CHECK(epilogue == EPI_BIAS_RELU_BF16 || epilogue == EPI_BIAS_RESID_F32,
+           "gemm_dropout: dropout follows the ReLU (epilogue 1) or precedes the residual add (epilogue 3)");
+  RP_CHECK(int64_t(M) * N < (int64_t(1) << 32), "gemm_dropout: M * N must stay below 2^32 elements");
+  return launch_gemm_checked(epilogue, A, lda, W, ldw, D, ldd, bias, resid, ldr, M, N, K, GemmLnFusion{}, stream,
+                             nullptr, &drop);
 }
 
 int launch_gemm(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,

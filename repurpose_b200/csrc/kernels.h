@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dropout.cuh"
+
 namespace rp {
 
 // ---- GEMM: D[M,N] = A[M,K] (bf16, K-major) * W[N,K]^T (bf16, K-major) + epilogue --------------
@@ -24,6 +26,11 @@ struct RowMap {
 int launch_gemm(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
                 int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
                 cudaStream_t stream, const RowMap* rows = nullptr);
+// the same with nn.Dropout applied to (acc + bias [ReLU]) before the residual is added (dropout.cuh; element index =
+// row * N + column): the train-mode forward of out_proj / linear1 / linear2 / the head layers
+int launch_gemm_dropout(int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D,
+                        int64_t ldd, const float* bias, const float* resid, int64_t ldr, int M, int N, int K,
+                        const DropKey& drop, cudaStream_t stream);
 
 // cls_head / reg_head tail (models/MMCTransformer.py:71-93): Linear(256,256) + ReLU + Linear(256, nj) (+ final ReLU for
 // reg_head) fused: out[m, j] = act(sum_c relu(A[m,:] . W[c,:] + bias[c]) * w7[j, c] + b7[j]), nj = 1 or 2, fp32 out.
@@ -74,8 +81,18 @@ struct FmhaArgs {
   // mask_mode 0 only: query tiles that start at or beyond round_up(kv_lens[b], 128) are padding (self-attention over a
   // padded batch): their CTAs exit at once and their output rows are left untouched
   bool skip_padded_queries = false;
+  // training forward with attention-weight dropout (mask_mode 0 only): keep bits [B*H*Tq rows, drop_ld words], bit
+  // (k & 31) of word k >> 5 = key k of that row kept (launch_attn_dropout_bits); the row sum runs over all weights,
+  // P V over the kept ones, the output is scaled by drop_scale = 1 / (1 - p)
+  const uint32_t* drop_bits = nullptr;
+  int64_t drop_ld = 0;
+  float drop_scale = 1.0f;
 };
 int launch_fmha(const FmhaArgs& a, cudaStream_t stream);
+// keep bits of one attention-dropout site: n_words words, word w covers elements 32 w .. 32 w + 31 of the site
+int launch_attn_dropout_bits(uint32_t* bits, int64_t n_words, const DropKey& drop, cudaStream_t stream);
+// keep[i] = 1 / 0 for the first n elements of an element-wise site (what the tests feed to the autograd reference)
+int launch_dropout_mask_u8(uint8_t* keep, int64_t n, const DropKey& drop, cudaStream_t stream);
 
 // ---- memory-bound kernels ------------------------------------------------------------------------
 // concat(vis, aud, txt) fp32 -> bf16 [M, Cv+Ca+Ct]
@@ -112,6 +129,7 @@ struct LnArgs {
   const float* pe;
   float* out_f32; void* y_bf16; void* y2_bf16;
   float eps;
+  DropKey drop;  // mode 2 only: feature_map's Dropout on f (before the head LayerNorms), element index = row * 512 + column
 };
 int launch_layernorm512(int mode, const LnArgs& a, cudaStream_t stream);
 
@@ -162,9 +180,12 @@ int launch_focal_loss_grad(const float* logits, const float* targets, const uint
 int64_t layernorm512_bwd_scratch_floats();
 // accumulate: dx += (the residual stream's gradient); dx_bf16 (optional): bf16 copy of the final dx; dx_colsum
 // (optional): column sums [512] of the final dx = the bias gradient of the Linear whose output gradient dx is
+// drop (optional): dx is the output gradient of a residual branch that ends in nn.Dropout (dropout1 / dropout2): dx_bf16
+// and dx_colsum then hold dropout's backward of dx (kept ? dx * scale : 0) — the dY of that branch's Linear — while dx
+// itself stays the residual stream's gradient
 int launch_layernorm512_bwd(const float* x, const float* dy, const float* gamma, int64_t M, float eps, float* dx,
                             float* dgamma, float* dbeta, float* scratch, cudaStream_t stream, bool accumulate = false,
-                            void* dx_bf16 = nullptr, float* dx_colsum = nullptr);
+                            void* dx_bf16 = nullptr, float* dx_colsum = nullptr, const DropKey* drop = nullptr);
 // one torch.optim.Adam step (L2 weight decay added to the gradient) on a flat fp32 buffer; p_bf16 (optional): bf16 copy
 int launch_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                      float eps, float weight_decay, int step, void* p_bf16, cudaStream_t stream);
@@ -176,13 +197,15 @@ int launch_splitk_reduce(const float* part, int splits, int64_t n, float* out, c
 // out[N] = column sums of bf16 x[M, N] (bias gradients); scratch: train_scratch_floats() fp32 values
 int64_t train_scratch_floats();
 int launch_colsum_bf16(const void* x, int64_t M, int N, float* out, float* scratch, cudaStream_t stream);
-// dy = act > 0 ? dy : 0, in place; f32: both fp32, else both bf16; n % 8 == 0
-int launch_relu_bwd(void* dy, const void* act, int64_t n, bool f32, cudaStream_t stream);
+// dy = act > 0 ? dy * scale : 0, in place; f32: both fp32, else both bf16; n % 8 == 0.  scale = 1 for a plain ReLU;
+// 1 / (1 - p) when `act` is dropout(relu(.)) as the train-mode forward stores it (kept and positive <=> act > 0)
+int launch_relu_bwd(void* dy, const void* act, int64_t n, bool f32, float scale, cudaStream_t stream);
 // the same for bf16 [M, N] fused with the bias gradient: colsum[N] = column sums of the masked dy
-int launch_relu_bwd_colsum(void* dy, const void* act, int64_t M, int N, float* colsum, float* scratch, cudaStream_t stream);
-// last cls_head layer: da2[M,256] bf16 = dlogit[m] w[c] where a2 > 0, dw[256], db[1]
-int launch_head_out_bwd(const float* dlogit, const void* a2, const float* w, int64_t M, void* da2, float* dw, float* db,
-                        float* scratch, cudaStream_t stream);
+int launch_relu_bwd_colsum(void* dy, const void* act, int64_t M, int N, float colscale, float* colsum, float* scratch,
+                           cudaStream_t stream);
+// last cls_head layer: da2[M,256] bf16 = dlogit[m] w[c] * scale where a2 > 0, dw[256], db[1]
+int launch_head_out_bwd(const float* dlogit, const void* a2, const float* w, int64_t M, float scale, void* da2, float* dw,
+                        float* db, float* scratch, cudaStream_t stream);
 // attention backward: q/k/v [B,T,ld_qkv] (head h in columns h*64..), o / dO dense [B,T,H*64], lse from the forward,
 // dsum scratch [B,H,T]; writes dq (w.r.t. the unscaled q), dk, dv with row pitch ld_dqkv
 struct FmhaBwdArgs {
@@ -192,6 +215,10 @@ struct FmhaBwdArgs {
   int64_t ld_qkv, ld_o, ld_dqkv;
   int B, H, T;
   const int32_t* kv_lens;
+  // attention-weight dropout of the forward (FmhaArgs::drop_bits): P_d = keep o P * scale feeds dV, dP = keep o dP_d * scale
+  const uint32_t* drop_bits = nullptr;
+  int64_t drop_ld = 0;
+  float drop_scale = 1.0f;
 };
 int launch_fmha_bwd(const FmhaBwdArgs& a, cudaStream_t stream);
 

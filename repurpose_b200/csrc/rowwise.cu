@@ -199,6 +199,14 @@ layernorm512_kernel(const LnArgs a) {
     } else {  // MODE 2
 #pragma unroll
       for (int i = 0; i < 16; ++i) y.v[i] = fmaxf(y.v[i], 0.0f);
+      if (a.drop.thr != 0u) {  // train mode: feature_map[3] = nn.Dropout on relu(LN(.)); the heads see the dropped row
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t k = (uint32_t(row) * 512u + uint32_t(128 * i + 4 * lane)) >> 1;
+          drop_pair(k, a.drop, y.v[4 * i], y.v[4 * i + 1]);
+          drop_pair(k + 1u, a.drop, y.v[4 * i + 2], y.v[4 * i + 3]);
+        }
+      }
       row_store_f32(y, a.out_f32 + row * 512, lane);
       // both head LayerNorms normalise the same row: one set of statistics, two affine maps
       float mean, rstd;

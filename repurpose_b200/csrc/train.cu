@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 2)
 layernorm512_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
                         int64_t M, float eps, float* __restrict__ dx, float* __restrict__ part_g,
                         float* __restrict__ part_b, int accumulate, __nv_bfloat16* __restrict__ dx_bf16,
-                        float* __restrict__ part_c) {
+                        float* __restrict__ part_c, const DropKey drop) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float acc_g[16], acc_b[16], acc_c[16];
 #pragma unroll
@@ -121,6 +121,11 @@ layernorm512_bwd_kernel(const float* __restrict__ x, const float* __restrict__ d
       o4.z = old[4 * i + 2] + rstd * (dv[4 * i + 2] - s1 - xv[4 * i + 2] * s2);
       o4.w = old[4 * i + 3] + rstd * (dv[4 * i + 3] - s1 - xv[4 * i + 3] * s2);
       *(reinterpret_cast<float4*>(dx + row * 512) + i * 32 + lane) = o4;
+      if (drop.thr != 0u) {  // dropout1 / dropout2 backward: the branch's Linear sees kept ? dx * scale : 0
+        const uint32_t k = (uint32_t(row) * 512u + uint32_t(4 * (32 * i + lane))) >> 1;
+        drop_pair(k, drop, o4.x, o4.y);
+        drop_pair(k + 1u, drop, o4.z, o4.w);
+      }
       acc_c[4 * i] += o4.x; acc_c[4 * i + 1] += o4.y; acc_c[4 * i + 2] += o4.z; acc_c[4 * i + 3] += o4.w;
       if (dx_bf16 != nullptr) {
         uint2 pk;
@@ -228,16 +233,22 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ part, int parts, 
 }
 
 // ---- ReLU backward: dy = act > 0 ? dy : 0 (bf16 in place; fp32 gradient against an fp32 activation) ----------
-__global__ void relu_bwd_bf16_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ act, int64_t n8) {
+// two bf16 gradients scaled by `scale` (dropout backward; scale == 1: untouched bits)
+__device__ __forceinline__ uint32_t scale_bf16x2(uint32_t dv, float scale) {
+  if (scale == 1.0f) return dv;
+  return pack_bf16x2(__uint_as_float(dv << 16) * scale, __uint_as_float(dv & 0xffff0000u) * scale);
+}
+__global__ void relu_bwd_bf16_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ act, int64_t n8,
+                                     float scale) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   uint4 d = reinterpret_cast<const uint4*>(dy)[i];
   const uint4 a = __ldcs(reinterpret_cast<const uint4*>(act) + i);
   // bf16 > 0: sign bit clear and not zero
-  auto mask2 = [](uint32_t dv, uint32_t av) {
+  auto mask2 = [scale](uint32_t dv, uint32_t av) {
     const uint32_t lo = (av & 0x8000u) == 0u && (av & 0x7fffu) != 0u ? 0xffffu : 0u;
     const uint32_t hi = (av & 0x80000000u) == 0u && (av & 0x7fff0000u) != 0u ? 0xffff0000u : 0u;
-    return dv & (lo | hi);
+    return scale_bf16x2(dv & (lo | hi), scale);
   };
   d.x = mask2(d.x, a.x); d.y = mask2(d.y, a.y); d.z = mask2(d.z, a.z); d.w = mask2(d.w, a.w);
   reinterpret_cast<uint4*>(dy)[i] = d;
@@ -246,7 +257,7 @@ __global__ void relu_bwd_bf16_kernel(__nv_bfloat16* __restrict__ dy, const __nv_
 // per-block partial column sums of the masked dy (block = a strip of rows, thread = groups of 8 consecutive columns)
 __global__ void __launch_bounds__(256)
 relu_bwd_colsum_bf16_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ act, int64_t M, int N,
-                            int64_t rows_per, float* __restrict__ part) {
+                            int64_t rows_per, float* __restrict__ part, float scale) {
   const int64_t r0 = int64_t(blockIdx.x) * rows_per;
   const int64_t r1 = r0 + rows_per < M ? r0 + rows_per : M;
   const int groups = N >> 3;
@@ -264,7 +275,7 @@ relu_bwd_colsum_bf16_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16*
       for (int i = 0; i < 4; ++i) {
         const uint32_t lo = (aw[i] & 0x8000u) == 0u && (aw[i] & 0x7fffu) != 0u ? 0xffffu : 0u;
         const uint32_t hi = (aw[i] & 0x80000000u) == 0u && (aw[i] & 0x7fff0000u) != 0u ? 0xffff0000u : 0u;
-        dw[i] &= (lo | hi);
+        dw[i] = scale_bf16x2(dw[i] & (lo | hi), scale);
         acc[2 * i] += __uint_as_float(dw[i] << 16);
         acc[2 * i + 1] += __uint_as_float(dw[i] & 0xffff0000u);
       }
@@ -280,12 +291,13 @@ relu_bwd_colsum_bf16_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16*
   }
 }
 
-__global__ void relu_bwd_f32_kernel(float* __restrict__ dy, const float* __restrict__ act, int64_t n4) {
+__global__ void relu_bwd_f32_kernel(float* __restrict__ dy, const float* __restrict__ act, int64_t n4, float scale) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 d = reinterpret_cast<const float4*>(dy)[i];
   const float4 a = __ldcs(reinterpret_cast<const float4*>(act) + i);
-  d.x = a.x > 0.f ? d.x : 0.f; d.y = a.y > 0.f ? d.y : 0.f; d.z = a.z > 0.f ? d.z : 0.f; d.w = a.w > 0.f ? d.w : 0.f;
+  d.x = a.x > 0.f ? d.x * scale : 0.f; d.y = a.y > 0.f ? d.y * scale : 0.f;
+  d.z = a.z > 0.f ? d.z * scale : 0.f; d.w = a.w > 0.f ? d.w * scale : 0.f;
   reinterpret_cast<float4*>(dy)[i] = d;
 }
 
@@ -294,9 +306,9 @@ __global__ void relu_bwd_f32_kernel(float* __restrict__ dy, const float* __restr
 // dw[c] = sum_m dlogit[m] a2[m, c] and db = sum_m dlogit[m] (reduced in order by colsum_reduce_kernel).
 __global__ void __launch_bounds__(256)
 head_out_bwd_kernel(const float* __restrict__ dlogit, const __nv_bfloat16* __restrict__ a2, const float* __restrict__ w,
-                    int64_t M, int64_t rows_per, __nv_bfloat16* __restrict__ da2, float* __restrict__ part) {
+                    int64_t M, int64_t rows_per, __nv_bfloat16* __restrict__ da2, float* __restrict__ part, float scale) {
   const int c = threadIdx.x;  // 256 columns
-  const float wc = w[c];
+  const float wc = w[c] * scale;  // (scale: backward of the Dropout between the ReLU and this layer; dw uses the stored a2)
   const int64_t r0 = int64_t(blockIdx.x) * rows_per;
   const int64_t r1 = r0 + rows_per < M ? r0 + rows_per : M;
   float dw = 0.f, db = 0.f;
@@ -342,7 +354,48 @@ attn_bwd_dsum_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* _
     }
   }
 }
+
+// ---- dropout masks (dropout.cuh) -------------------------------------------------------------------------------------
+// keep bits of an attention-dropout site: thread = one 32-bit word = 32 consecutive keys of one (batch, head, query) row
+__global__ void __launch_bounds__(256)
+attn_dropout_bits_kernel(uint32_t* __restrict__ bits, int64_t n_words, const DropKey drop) {
+  const int64_t w = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  const uint32_t k0 = uint32_t(w) * 16u;
+  uint32_t word = 0u;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t h = drop_hash(k0 + uint32_t(i), drop.a, drop.b);
+    word |= ((h & 0xffffu) >= drop.thr ? 1u : 0u) << (2 * i);
+    word |= ((h >> 16) >= drop.thr ? 1u : 0u) << (2 * i + 1);
+  }
+  bits[w] = word;
+}
+__global__ void dropout_mask_u8_kernel(uint8_t* __restrict__ keep, int64_t n, const DropKey drop) {
+  const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;  // pair index
+  if (2 * k >= n) return;
+  const uint32_t h = drop_hash(uint32_t(k), drop.a, drop.b);
+  keep[2 * k] = (h & 0xffffu) >= drop.thr ? 1 : 0;
+  if (2 * k + 1 < n) keep[2 * k + 1] = (h >> 16) >= drop.thr ? 1 : 0;
+}
 }  // namespace
+
+int launch_attn_dropout_bits(uint32_t* bits, int64_t n_words, const DropKey& drop, cudaStream_t stream) {
+  RP_CHECK(bits != nullptr && n_words > 0 && n_words * 16 < (int64_t(1) << 32),
+           "attn_dropout_bits: 0 < 32 * n_words < 2^33 elements per site");
+  attn_dropout_bits_kernel<<<unsigned((n_words + 255) / 256), 256, 0, stream>>>(bits, n_words, drop);
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
+int launch_dropout_mask_u8(uint8_t* keep, int64_t n, const DropKey& drop, cudaStream_t stream) {
+  RP_CHECK(keep != nullptr && n > 0 && n < (int64_t(1) << 32), "dropout_mask: 0 < n < 2^32");
+  const int64_t pairs = (n + 1) / 2;
+  dropout_mask_u8_kernel<<<unsigned((pairs + 255) / 256), 256, 0, stream>>>(keep, n, drop);
+  count_launch();
+  RP_CUDA_CHECK(cudaGetLastError());
+  return RP_OK;
+}
 
 int launch_focal_loss_grad(const float* logits, const float* targets, const uint8_t* mask, int64_t n, float alpha,
                            float gamma, float scale, float* dlogits, cudaStream_t stream) {
@@ -358,8 +411,9 @@ int64_t layernorm512_bwd_scratch_floats() { return int64_t(3) * 2 * num_sms() * 
 
 int launch_layernorm512_bwd(const float* x, const float* dy, const float* gamma, int64_t M, float eps, float* dx,
                             float* dgamma, float* dbeta, float* scratch, cudaStream_t stream, bool accumulate,
-                            void* dx_bf16, float* dx_colsum) {
+                            void* dx_bf16, float* dx_colsum, const DropKey* drop) {
   RP_CHECK(M > 0, "layernorm512_bwd: empty");
+  RP_CHECK(drop == nullptr || M * 512 < (int64_t(1) << 32), "layernorm512_bwd: dropout sites hold fewer than 2^32 elements");
   const int sms = num_sms();
   int grid = 2 * sms;  // two resident blocks per SM walk the rows
   if (int64_t(grid) * LNB_WARPS > M) grid = int((M + LNB_WARPS - 1) / LNB_WARPS);
@@ -368,7 +422,8 @@ int launch_layernorm512_bwd(const float* x, const float* dy, const float* gamma,
   float* part_c = dx_colsum != nullptr ? scratch + int64_t(4) * sms * 512 : nullptr;
   layernorm512_bwd_kernel<<<grid, LNB_WARPS * 32, 0, stream>>>(x, dy, gamma, M, eps, dx, part_g, part_b,
                                                                accumulate ? 1 : 0,
-                                                               reinterpret_cast<__nv_bfloat16*>(dx_bf16), part_c);
+                                                               reinterpret_cast<__nv_bfloat16*>(dx_bf16), part_c,
+                                                               drop != nullptr ? *drop : DropKey{});
   layernorm512_bwd_reduce_kernel<<<4, 128, 0, stream>>>(part_g, part_b, part_c, grid, dgamma, dbeta, dx_colsum);
   count_launch(2);
   RP_CUDA_CHECK(cudaGetLastError());
@@ -415,20 +470,21 @@ int launch_colsum_bf16(const void* x, int64_t M, int N, float* out, float* scrat
   return RP_OK;
 }
 
-int launch_relu_bwd(void* dy, const void* act, int64_t n, bool f32, cudaStream_t stream) {
+int launch_relu_bwd(void* dy, const void* act, int64_t n, bool f32, float scale, cudaStream_t stream) {
   RP_CHECK(n > 0 && n % 8 == 0, "relu_bwd: n must be a positive multiple of 8");
   if (f32)
     relu_bwd_f32_kernel<<<unsigned((n / 4 + 255) / 256), 256, 0, stream>>>(static_cast<float*>(dy),
-                                                                           static_cast<const float*>(act), n / 4);
+                                                                           static_cast<const float*>(act), n / 4, scale);
   else
     relu_bwd_bf16_kernel<<<unsigned((n / 8 + 255) / 256), 256, 0, stream>>>(
-        static_cast<__nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(act), n / 8);
+        static_cast<__nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(act), n / 8, scale);
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;
 }
 
-int launch_relu_bwd_colsum(void* dy, const void* act, int64_t M, int N, float* colsum, float* scratch, cudaStream_t stream) {
+int launch_relu_bwd_colsum(void* dy, const void* act, int64_t M, int N, float scale, float* colsum, float* scratch,
+                           cudaStream_t stream) {
   RP_CHECK(M > 0 && N > 0 && N % 8 == 0, "relu_bwd_colsum: N must be a positive multiple of 8");
   // scratch holds blocks x N partials: train_scratch_floats() >= 4 SMs x 1024 -> blocks <= that / N
   int64_t blocks = train_scratch_floats() / N;
@@ -439,22 +495,22 @@ int launch_relu_bwd_colsum(void* dy, const void* act, int64_t M, int N, float* c
   blocks = (M + rows_per - 1) / rows_per;
   relu_bwd_colsum_bf16_kernel<<<unsigned(blocks), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(dy),
                                                                     static_cast<const __nv_bfloat16*>(act), M, N, rows_per,
-                                                                    scratch);
+                                                                    scratch, scale);
   colsum_reduce_kernel<<<(N + 127) / 128, 128, 0, stream>>>(scratch, int(blocks), N, colsum);
   count_launch(2);
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;
 }
 
-int launch_head_out_bwd(const float* dlogit, const void* a2, const float* w, int64_t M, void* da2, float* dw, float* db,
-                        float* scratch, cudaStream_t stream) {
+int launch_head_out_bwd(const float* dlogit, const void* a2, const float* w, int64_t M, float scale, void* da2, float* dw,
+                        float* db, float* scratch, cudaStream_t stream) {
   RP_CHECK(M > 0, "head_out_bwd: empty");
   int blocks = 4 * num_sms();
   if (blocks > M) blocks = int(M);
   const int64_t rows_per = (M + blocks - 1) / blocks;
   blocks = int((M + rows_per - 1) / rows_per);
   head_out_bwd_kernel<<<blocks, 256, 0, stream>>>(dlogit, static_cast<const __nv_bfloat16*>(a2), w, M, rows_per,
-                                                  static_cast<__nv_bfloat16*>(da2), scratch);
+                                                  static_cast<__nv_bfloat16*>(da2), scratch, scale);
   // the 257 partial columns: dw[0..256) and db
   colsum_reduce_kernel<<<3, 128, 0, stream>>>(scratch, blocks, 257, scratch + int64_t(blocks) * 257);
   RP_CUDA_CHECK(cudaMemcpyAsync(dw, scratch + int64_t(blocks) * 257, 256 * sizeof(float), cudaMemcpyDeviceToDevice, stream));

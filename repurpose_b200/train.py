@@ -9,16 +9,40 @@
   allreduce_flat_(flat_grads, group)                  <- DDP's gradient averaging (utils/distributed.py:415-428):
                                                          ONE all-reduce over the flat gradient buffer
 
-All compute is in librepurpose_b200.so; there is no PyTorch fallback.  Deviation from the reference's training graph,
-listed in DESIGN.md §7: dropout (p = 0.1 in the encoder layers, the attention weights and the heads) is not applied —
-the step is the reference's with `dropout = 0`, which is also the graph the parity test differentiates with autograd."""
+All compute is in librepurpose_b200.so; there is no PyTorch fallback.  Dropout: the reference trains under
+model.train() (main.py:285) with nn.Dropout(0.1) in the encoder layers, on the attention weights and in the heads;
+`TrainStep(dropout=0.1)` applies all of them with counter-based masks (csrc/dropout.cuh; `dropout_keys` below derives a
+stream per site and step).  The draws differ from torch's Philox stream, the distribution does not; the parity tests
+feed these masks to autograd over the reference graph."""
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
 
+import ctypes
+
 from . import _lib
 from ._lib import check, cur_stream, ptr
+
+_M32 = 0xFFFFFFFF
+
+
+def _fmix32(x: int) -> int:
+    """MurmurHash3's 32-bit finaliser (the device's drop_hash uses the same rounds)"""
+    x &= _M32
+    x ^= x >> 16
+    x = (x * 0x85EBCA6B) & _M32
+    x ^= x >> 13
+    x = (x * 0xC2B2AE35) & _M32
+    x ^= x >> 16
+    return x
+
+
+def dropout_keys(seed: int, step: int, site: int):
+    """(key_a, key_b) of one dropout site at one training step: every (seed, step, site) draws from its own stream"""
+    a = _fmix32((seed & _M32) ^ _fmix32(site * 0x9E3779B1 + step * 0x632BE5AB + 1))
+    b = _fmix32(((seed >> 32) & _M32) ^ _fmix32(site * 0x85EBCA6B + step * 0x27D4EB2F + 2))
+    return a, b
 
 
 def _cuda(t, what):
@@ -135,7 +159,14 @@ class TrainStep:
     reg_head receives no gradient in the reference (the loss is the focal classification term only,
     models/MMCTransformer.py:159-179) — torch's Adam skips such parameters, and so does this step."""
 
-    def __init__(self, model, lr=1e-3, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, group=None):
+    def __init__(self, model, lr=1e-3, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, group=None, dropout=0.1,
+                 seed=0):
+        """dropout: the p of every nn.Dropout of the reference graph (0.1 there; 0 = the eval-mode graph);
+        seed: base of the dropout streams (use a different one per data-parallel rank, as torch's per-process
+        generators are)"""
+        if not 0.0 <= dropout < 1.0:
+            raise ValueError("TrainStep: 0 <= dropout < 1")
+        self.p, self.seed, self.step_index = float(dropout), int(seed), 0
         self.model = model
         self.cfg = c = model._cfg
         if c["d_model"] != 512 or c["head_hidden"] != 256 or c["num_heads"] * 64 != c["d_model"]:
@@ -218,8 +249,54 @@ class TrainStep:
         d["d512"] = torch.empty(M, 512, **b16)                    # dattn
         d["dsum"] = torch.empty(B, c["num_heads"], T, **f32)
         d["lens"] = torch.empty(B, dtype=torch.int32, device=dev)
+        if self.p > 0:
+            # keep bits of the attention-weight dropout, one buffer per layer (the backward reads them again): rows of
+            # round_up(T, 128) / 32 words per (batch, head, query) — 55 MB per layer at B = 16, T = 1801
+            d["bits_ld"] = ((T + 127) // 128) * 4
+            d["bits"] = [torch.empty(B * c["num_heads"] * T, d["bits_ld"], dtype=torch.int32, device=dev) for _ in range(L)]
         self._bufs = d
         return d
+
+    # ---- dropout sites -----------------------------------------------------------------------------------------------
+    def site(self, name, layer=0):
+        """stream index of a dropout site: 'attn' / 'drop1' / 'ffn' / 'drop2' of an encoder layer, or 'feats',
+        'cls1', 'cls2', 'reg1', 'reg2' (feature_map[3], cls_head[3] / [6], reg_head[3] / [6])"""
+        L = self.cfg["num_layers"]
+        per_layer = {"attn": 0, "drop1": 1, "ffn": 2, "drop2": 3}
+        if name in per_layer:
+            return 4 * layer + per_layer[name]
+        return 4 * L + ("feats", "cls1", "cls2", "reg1", "reg2").index(name)
+
+    def _drop(self, site):
+        """rp_dropout of a site at the current step (None when dropout is off)"""
+        if self.p <= 0 or site is None:
+            return None
+        a, b = dropout_keys(self.seed, self.step_index, site)
+        return _lib.RpDropout(a, b, self.p)
+
+    @property
+    def drop_scale(self):
+        return 1.0 / (1.0 - self.p) if self.p > 0 else 1.0
+
+    def keep_mask(self, site, shape):
+        """the keep mask (bool, `shape`) of an element-wise site at the current step — what the kernels apply"""
+        n = 1
+        for k in shape:
+            n *= int(k)
+        out = torch.empty(n, dtype=torch.uint8, device=self.dev)
+        with torch.cuda.device(self.dev):
+            check(self.lib.rp_dropout_mask_u8(ctypes.byref(self._drop(site)), n, ptr(out), cur_stream()), "rp_dropout_mask_u8")
+        return out.view(*shape).bool()
+
+    def attention_keep_mask(self, layer):
+        """[B, H, T, T] bool keep mask of layer `layer`'s attention weights, unpacked from the bits of the last forward"""
+        d = self._bufs
+        B, T = d["shape"]
+        H = self.cfg["num_heads"]
+        words = d["bits"][layer].view(B, H, T, d["bits_ld"]).to(torch.int64) & _M32
+        shifts = torch.arange(32, device=self.dev, dtype=torch.int64)
+        bits = ((words[..., None] >> shifts) & 1).reshape(B, H, T, d["bits_ld"] * 32)
+        return bits[..., :T].bool()
 
     # ---- per-kernel-class device timing (CUDA events on the launch stream) ----------------------------------------
     _PROFILED = {"_gemm": "fwd_gemm", "_ln": "fwd_layernorm", "_dgrad": "bwd_dgrad", "_wgrad": "bwd_wgrad",
@@ -265,13 +342,27 @@ class TrainStep:
         return out
 
     # ---- thin wrappers over the C ABI ------------------------------------------------------------------------------
-    def _gemm(self, epi, A, W, D, bias, resid=None):
+    def _gemm(self, epi, A, W, D, bias, resid=None, site=None):
+        """site: the nn.Dropout that follows this Linear (after its ReLU / before the residual add) in train mode"""
         M, K = A.shape
         N = W.shape[0]
+        drop = self._drop(site)
+        if drop is not None:
+            check(self.lib.rp_gemm_bf16_dropout(epi, ptr(A), K, ptr(W), K, ptr(D), N, ptr(bias), ptr(resid),
+                                                N if resid is not None else 0, M, N, K, ctypes.byref(drop), cur_stream()),
+                  "rp_gemm_bf16_dropout")
+            return
         check(self.lib.rp_gemm_bf16(epi, ptr(A), K, ptr(W), K, ptr(D), N, ptr(bias), ptr(resid), N if resid is not None else 0,
                                     M, N, K, cur_stream()), "rp_gemm_bf16")
 
-    def _ln(self, mode, x, M, T, g0, b0, g1=None, b1=None, g2=None, b2=None, pe=None, out_f32=None, y=None, y2=None):
+    def _ln(self, mode, x, M, T, g0, b0, g1=None, b1=None, g2=None, b2=None, pe=None, out_f32=None, y=None, y2=None,
+            site=None):
+        drop = self._drop(site)
+        if drop is not None:
+            check(self.lib.rp_layernorm512_dropout(mode, ptr(x), M, T, ptr(g0), ptr(b0), ptr(g1), ptr(b1), ptr(g2), ptr(b2),
+                                                   ptr(pe), ptr(out_f32), ptr(y), ptr(y2), ctypes.byref(drop), cur_stream()),
+                  "rp_layernorm512_dropout")
+            return
         check(self.lib.rp_layernorm512(mode, ptr(x), M, T, ptr(g0), ptr(b0), ptr(g1), ptr(b1), ptr(g2), ptr(b2), ptr(pe),
                                        ptr(out_f32), ptr(y), ptr(y2), cur_stream()), "rp_layernorm512")
 
@@ -305,27 +396,33 @@ class TrainStep:
         check(self.lib.rp_colsum_bf16(ptr(X), M, N, ptr(out), ptr(self._scratch), self._scratch.numel(), cur_stream()),
               "rp_colsum_bf16")
 
-    def _ln_bwd(self, x, dy, prefix, dh, dh16, accumulate, bias_grad=None):
+    def _ln_bwd(self, x, dy, prefix, dh, dh16, accumulate, bias_grad=None, site=None):
         """dh (+)= LayerNorm backward of the branch `prefix` (…weight / …bias receive their gradients); dh16 = bf16 copy
         of the resulting dh; bias_grad (a parameter name) receives its column sums — the bias gradient of the Linear
-        whose output gradient dh is"""
+        whose output gradient dh is.  site: that Linear's output passed through this nn.Dropout before it joined the
+        residual stream (dropout1 / dropout2): dh16 and the bias gradient then carry dropout's backward of dh"""
         M = x.shape[0] if x.dim() == 2 else x.numel() // 512
-        check(self.lib.rp_layernorm512_bwd_acc(ptr(x), ptr(dy), ptr(self.w32(prefix + "weight")), M, 1e-5,
-                                               1 if accumulate else 0, ptr(dh), ptr(dh16),
-                                               ptr(self.grad(bias_grad)) if bias_grad else 0,
-                                               ptr(self.grad(prefix + "weight")), ptr(self.grad(prefix + "bias")),
-                                               ptr(self._scratch), self._scratch.numel(), cur_stream()),
-              "rp_layernorm512_bwd_acc")
+        drop = self._drop(site)
+        args = (ptr(x), ptr(dy), ptr(self.w32(prefix + "weight")), M, 1e-5, 1 if accumulate else 0, ptr(dh), ptr(dh16),
+                ptr(self.grad(bias_grad)) if bias_grad else 0, ptr(self.grad(prefix + "weight")),
+                ptr(self.grad(prefix + "bias")), ptr(self._scratch), self._scratch.numel())
+        if drop is not None:
+            check(self.lib.rp_layernorm512_bwd_acc_dropout(*args, ctypes.byref(drop), cur_stream()),
+                  "rp_layernorm512_bwd_acc_dropout")
+            return
+        check(self.lib.rp_layernorm512_bwd_acc(*args, cur_stream()), "rp_layernorm512_bwd_acc")
 
     def _relu_bwd_bias(self, dy, act, bias_name):
-        """dy = act > 0 ? dy : 0 in place, and grad(bias_name) = column sums of the masked dy"""
+        """dy = act > 0 ? dy * drop_scale : 0 in place (act = dropout(relu(.)) as stored: the ReLU and the Dropout behind it
+        in one mask), and grad(bias_name) = column sums of the result"""
         M, N = dy.shape
-        check(self.lib.rp_relu_bwd_colsum(ptr(dy), ptr(act), M, N, ptr(self.grad(bias_name)), ptr(self._scratch),
-                                          self._scratch.numel(), cur_stream()), "rp_relu_bwd_colsum")
+        check(self.lib.rp_relu_bwd_colsum_scaled(ptr(dy), ptr(act), M, N, self.drop_scale, ptr(self.grad(bias_name)),
+                                                 ptr(self._scratch), self._scratch.numel(), cur_stream()),
+              "rp_relu_bwd_colsum_scaled")
 
     def _relu_bwd(self, dy, act):
-        check(self.lib.rp_relu_bwd(ptr(dy), ptr(act), dy.numel(), 1 if dy.dtype == torch.float32 else 0, cur_stream()),
-              "rp_relu_bwd")
+        check(self.lib.rp_relu_bwd_scaled(ptr(dy), ptr(act), dy.numel(), 1 if dy.dtype == torch.float32 else 0,
+                                          self.drop_scale, cur_stream()), "rp_relu_bwd_scaled")
 
     # ---- forward (train graph, activations kept) -------------------------------------------------------------------
     def forward(self, batch):
@@ -353,25 +450,35 @@ class TrainStep:
                 p = lay.format(l)
                 self._gemm(0, d["u1"][l], self._wqkv16[l], d["qkv"][l], self._bqkv[l])
                 q = d["qkv"][l]
+                if self.p > 0:
+                    with self._timed("dropout_bits"):
+                        check(lib.rp_attn_dropout_bits(ctypes.byref(self._drop(self.site("attn", l))), d["bits"][l].numel(),
+                                                       ptr(d["bits"][l]), st), "rp_attn_dropout_bits")
                 with self._timed("fwd_fmha"):
-                    check(lib.rp_fmha_train(ptr(q), ptr(q) + 1024, ptr(q) + 2048, ptr(d["attn"][l]), 1536, 512, B, H, T,
-                                            ptr(d["lens"]), ptr(d["lse"][l]), st), "rp_fmha_train")
+                    if self.p > 0:
+                        check(lib.rp_fmha_train_dropout(ptr(q), ptr(q) + 1024, ptr(q) + 2048, ptr(d["attn"][l]), 1536, 512,
+                                                        B, H, T, ptr(d["lens"]), ptr(d["lse"][l]), ptr(d["bits"][l]),
+                                                        d["bits_ld"], self.p, st), "rp_fmha_train_dropout")
+                    else:
+                        check(lib.rp_fmha_train(ptr(q), ptr(q) + 1024, ptr(q) + 2048, ptr(d["attn"][l]), 1536, 512, B, H, T,
+                                                ptr(d["lens"]), ptr(d["lse"][l]), st), "rp_fmha_train")
                 self._gemm(3, d["attn"][l], self.w16(p + "self_attn.out_proj.weight"), d["hmid"][l],
-                           self.w32(p + "self_attn.out_proj.bias"), resid=d["h"][l])
+                           self.w32(p + "self_attn.out_proj.bias"), resid=d["h"][l], site=self.site("drop1", l))
                 self._ln(0, d["hmid"][l], M, T, self.w32(p + "norm2.weight"), self.w32(p + "norm2.bias"), y=d["u2"][l])
-                self._gemm(1, d["u2"][l], self.w16(p + "linear1.weight"), d["ffn"][l], self.w32(p + "linear1.bias"))
+                self._gemm(1, d["u2"][l], self.w16(p + "linear1.weight"), d["ffn"][l], self.w32(p + "linear1.bias"),
+                           site=self.site("ffn", l))
                 self._gemm(3, d["ffn"][l], self.w16(p + "linear2.weight"), d["h"][l + 1], self.w32(p + "linear2.bias"),
-                           resid=d["hmid"][l])
+                           resid=d["hmid"][l], site=self.site("drop2", l))
                 nxt = lay.format(l + 1) + "norm1." if l + 1 < L else "encoder_norm."
                 self._ln(0, d["h"][l + 1], M, T, self.w32(nxt + "weight"), self.w32(nxt + "bias"), y=d["u1"][l + 1])
             self._gemm(2, d["u1"][L], self.w16("feature_map.0.weight"), d["fm"], self.w32("feature_map.0.bias"))
             self._ln(2, d["fm"], M, T, self.w32("feature_map.1.weight"), self.w32("feature_map.1.bias"),
                      self.w32("cls_head.0.weight"), self.w32("cls_head.0.bias"), self.w32("reg_head.0.weight"),
-                     self.w32("reg_head.0.bias"), out_f32=d["feats"], y=d["uc"], y2=d["ur"])
-            self._gemm(1, d["uc"], self.w16("cls_head.1.weight"), d["a1c"], self.w32("cls_head.1.bias"))
-            self._gemm(1, d["a1c"], self.w16("cls_head.4.weight"), d["a2c"], self.w32("cls_head.4.bias"))
-            self._gemm(1, d["ur"], self.w16("reg_head.1.weight"), d["a1r"], self.w32("reg_head.1.bias"))
-            self._gemm(1, d["a1r"], self.w16("reg_head.4.weight"), d["a2r"], self.w32("reg_head.4.bias"))
+                     self.w32("reg_head.0.bias"), out_f32=d["feats"], y=d["uc"], y2=d["ur"], site=self.site("feats"))
+            self._gemm(1, d["uc"], self.w16("cls_head.1.weight"), d["a1c"], self.w32("cls_head.1.bias"), site=self.site("cls1"))
+            self._gemm(1, d["a1c"], self.w16("cls_head.4.weight"), d["a2c"], self.w32("cls_head.4.bias"), site=self.site("cls2"))
+            self._gemm(1, d["ur"], self.w16("reg_head.1.weight"), d["a1r"], self.w32("reg_head.1.bias"), site=self.site("reg1"))
+            self._gemm(1, d["a1r"], self.w16("reg_head.4.weight"), d["a2r"], self.w32("reg_head.4.bias"), site=self.site("reg2"))
             check(lib.rp_head_out(ptr(d["a2c"]), ptr(d["a2r"]), ptr(self.w32("cls_head.7.weight")), ptr(self.w32("cls_head.7.bias")),
                                   ptr(self.w32("reg_head.7.weight")), ptr(self.w32("reg_head.7.bias")), ptr(d["logits"]),
                                   ptr(d["offsets"]), M, st), "rp_head_out")
@@ -390,9 +497,10 @@ class TrainStep:
             # cls head: Linear(256,1) <- ReLU <- Linear(256,256) <- ReLU <- Linear(512,256) <- LayerNorm
             da2 = d["dwide"].view(-1)[:M * 256].view(M, 256)
             da1 = d["dwide"].view(-1)[M * 256:2 * M * 256].view(M, 256)
-            check(lib.rp_head_out_bwd(ptr(dlogits), ptr(d["a2c"]), ptr(self.w32("cls_head.7.weight")), M, ptr(da2),
-                                      ptr(self.grad("cls_head.7.weight")), ptr(self.grad("cls_head.7.bias")), ptr(self._scratch),
-                                      self._scratch.numel(), st), "rp_head_out_bwd")
+            check(lib.rp_head_out_bwd_scaled(ptr(dlogits), ptr(d["a2c"]), ptr(self.w32("cls_head.7.weight")), M,
+                                             self.drop_scale, ptr(da2), ptr(self.grad("cls_head.7.weight")),
+                                             ptr(self.grad("cls_head.7.bias")), ptr(self._scratch), self._scratch.numel(), st),
+                  "rp_head_out_bwd_scaled")
             self._wgrad(da2, d["a1c"], "cls_head.4.")
             self._colsum(da2, self.grad("cls_head.4.bias"))
             self._dgrad(da2, self.w16("cls_head.4.weight"), da1)
@@ -407,7 +515,8 @@ class TrainStep:
             self._wgrad(dh16, d["u1"][L], "feature_map.0.")
             self._dgrad(dh16, self.w16("feature_map.0.weight"), du)                  # du = d encoder_norm output
             self._ln_bwd(d["h"][L], du, "encoder_norm.", dh, dh16, accumulate=False,
-                         bias_grad=lay.format(L - 1) + "linear2.bias")               # dh = d h[L] = dY of the last linear2
+                         bias_grad=lay.format(L - 1) + "linear2.bias",               # dh = d h[L]; dh16 = dY of the last linear2
+                         site=self.site("drop2", L - 1))
             dffn, dattn = d["dwide"], d["d512"]
             dqkv = d["dwide"].view(-1)[:M * 1536].view(M, 1536)
             for l in range(L - 1, -1, -1):
@@ -419,20 +528,28 @@ class TrainStep:
                 self._wgrad(dffn, d["u2"][l], p + "linear1.")
                 self._dgrad(dffn, self.w16(p + "linear1.weight"), du)
                 self._ln_bwd(d["hmid"][l], du, p + "norm2.", dh, dh16, accumulate=True,
-                             bias_grad=p + "self_attn.out_proj.bias")                # dh = d hmid = dY of out_proj
+                             bias_grad=p + "self_attn.out_proj.bias",                # dh = d hmid; dh16 = dY of out_proj
+                             site=self.site("drop1", l))
                 # attention: hmid = h + attn Wo^T + bo
                 self._wgrad(dh16, d["attn"][l], p + "self_attn.out_proj.")
                 self._dgrad(dh16, self.w16(p + "self_attn.out_proj.weight"), dattn)
                 q = d["qkv"][l]
                 with self._timed("bwd_fmha"):
-                    check(lib.rp_fmha_bwd(ptr(q), ptr(q) + 1024, ptr(q) + 2048, ptr(d["attn"][l]), ptr(dattn), ptr(d["lse"][l]),
-                                          ptr(d["dsum"]), ptr(dqkv), ptr(dqkv) + 1024, ptr(dqkv) + 2048, 1536, 512, 1536, B, H,
-                                          T, ptr(d["lens"]), st), "rp_fmha_bwd")
+                    if self.p > 0:
+                        check(lib.rp_fmha_bwd_dropout(ptr(q), ptr(q) + 1024, ptr(q) + 2048, ptr(d["attn"][l]), ptr(dattn),
+                                                      ptr(d["lse"][l]), ptr(d["dsum"]), ptr(dqkv), ptr(dqkv) + 1024,
+                                                      ptr(dqkv) + 2048, 1536, 512, 1536, B, H, T, ptr(d["lens"]),
+                                                      ptr(d["bits"][l]), d["bits_ld"], self.p, st), "rp_fmha_bwd_dropout")
+                    else:
+                        check(lib.rp_fmha_bwd(ptr(q), ptr(q) + 1024, ptr(q) + 2048, ptr(d["attn"][l]), ptr(dattn),
+                                              ptr(d["lse"][l]), ptr(d["dsum"]), ptr(dqkv), ptr(dqkv) + 1024, ptr(dqkv) + 2048,
+                                              1536, 512, 1536, B, H, T, ptr(d["lens"]), st), "rp_fmha_bwd")
                 self._wgrad(dqkv, d["u1"][l], p + "self_attn.in_proj_weight")
                 self._colsum(dqkv, self.grad(p + "self_attn.in_proj_bias"))
                 self._dgrad(dqkv, self.w16(p + "self_attn.in_proj_weight"), du)
-                self._ln_bwd(d["h"][l], du, p + "norm1.", dh, dh16, accumulate=True,  # dh = d h[l] = dY of layer l-1's linear2
-                             bias_grad=(lay.format(l - 1) + "linear2.bias") if l > 0 else None)
+                self._ln_bwd(d["h"][l], du, p + "norm1.", dh, dh16, accumulate=True,  # dh = d h[l]; dh16 = dY of layer l-1's linear2
+                             bias_grad=(lay.format(l - 1) + "linear2.bias") if l > 0 else None,
+                             site=self.site("drop2", l - 1) if l > 0 else None)
             # h0 = LayerNorm(x W_in^T + b_in) + PE
             self._ln_bwd(d["xproj"], dh, "input_norm.", du, dh16, accumulate=False, bias_grad="input_projection.bias")
             self._wgrad(dh16, d["xcat"], "input_projection.")
@@ -455,4 +572,5 @@ class TrainStep:
         with self._timed("adam_and_recast"):
             self.opt.step()
             self.refresh_weights()
+        self.step_index += 1     # the next iteration draws fresh dropout masks
         return loss

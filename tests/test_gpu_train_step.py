@@ -65,7 +65,7 @@ def test_gradients_match_autograd_of_the_reference_graph(layers, lens):
     cfg, model, batch = _setup(layers, lens, seed=5 + layers)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     B = len(lens)
-    ts = TrainStep(model, lr=1e-3)
+    ts = TrainStep(model, lr=1e-3, dropout=0.0)
     loss = ts.loss_and_grads(batch, batch_size=B)
     ref_loss, ref_grads = _autograd_reference(sd, batch, B)
     _, amp_grads = _autograd_reference(sd, batch, B, autocast=True)
@@ -93,7 +93,7 @@ def test_gradients_match_the_staged_reference_module():
     out = rmodel(batch)
     rloss = rmodel.losses(*out)["cls_loss"] / B
     rloss.backward()
-    ts = TrainStep(model, lr=1e-3)
+    ts = TrainStep(model, lr=1e-3, dropout=0.0)
     loss = ts.loss_and_grads(batch, batch_size=B)
     assert abs(float(loss) - float(rloss)) <= 2e-2 * abs(float(rloss))
     _, amp_grads = _autograd_reference(sd, batch, B, autocast=True)
@@ -104,7 +104,7 @@ def test_training_iterations_reduce_the_loss_and_update_inference():
     from repurpose_b200.train import TrainStep
     cfg, model, batch = _setup(2, [256, 200], seed=33)
     before = {n: p.detach().clone() for n, p in model.named_parameters()}
-    ts = TrainStep(model, lr=3e-4)
+    ts = TrainStep(model, lr=3e-4, dropout=0.0)
     losses = [float(ts.step(batch)) for _ in range(8)]
     print("loss per iteration:", [round(x, 4) for x in losses])
     assert losses[-1] < 0.8 * losses[0], losses

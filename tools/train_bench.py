@@ -16,14 +16,14 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 
-def run_train_bench(B, T, steps, warmup=2, rank=0, world=1, dev=None):
+def run_train_bench(B, T, steps, warmup=2, rank=0, world=1, dev=None, dropout=0.1):
     from repurpose_b200 import synth
     from repurpose_b200.models.MMCTransformer import MMCTransformer
     from repurpose_b200.train import TrainStep
     dev = dev or torch.device("cuda", torch.cuda.current_device())
     torch.manual_seed(0)
     model = MMCTransformer(**synth.MODEL_CFG).to(dev)
-    ts = TrainStep(model, lr=1e-4, weight_decay=1e-4)
+    ts = TrainStep(model, lr=1e-4, weight_decay=1e-4, dropout=dropout, seed=1000 + rank)
     batch = synth.make_batch([T] * B, seed=100 + rank)
     g = torch.Generator().manual_seed(7 + rank)
     batch["labels"] = (torch.rand(B, T, generator=g) < 0.3).float()
@@ -61,8 +61,10 @@ def run_train_bench(B, T, steps, warmup=2, rank=0, world=1, dev=None):
             "videos_per_s": world * B / (ms * 1e-3), "model_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
             "loss_first_last": [losses[0], losses[-1]], "kernel_classes_ms": prof,
             "activation_gb": 16 * B * T * 14.3e3 / 1e9,
+            "dropout": dropout,
             "what": "forward (activations kept) + masked focal loss + backward + one flat gradient all-reduce + Adam; "
-                    "dropout off (documented deviation)"}
+                    + ("train mode: nn.Dropout(%.2f) at every site of the reference graph (counter-based masks)" % dropout
+                       if dropout > 0 else "dropout off (the eval-mode graph)")}
 
 
 if __name__ == "__main__":
@@ -70,6 +72,7 @@ if __name__ == "__main__":
     ap.add_argument("--B", type=int, default=16)
     ap.add_argument("--T", type=int, default=1801)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--dropout", type=float, default=0.1)
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -77,7 +80,7 @@ if __name__ == "__main__":
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    r = run_train_bench(a.B, a.T, a.steps, rank=rank, world=world)
+    r = run_train_bench(a.B, a.T, a.steps, rank=rank, world=world, dropout=a.dropout)
     if rank == 0:
         print(json.dumps(r))
     if world > 1:
