@@ -18,7 +18,10 @@
 //                         row; lse / Dsum of the tile's 64 queries staged in shared memory) -> P^T, dSt^T as bf16 A
 //                         operands in TMEM -> dV += P^T dO_i, dK += dSt^T Q_i (Q_i / dO_i as MN-major B operands)
 // S and dP are computed twice (once per kernel): 7 MMAs per tile pair instead of 5, in exchange for no atomics on dQ.
-// Roles per CTA (192 threads): warps 0-3 softmax (TMEM lane quarter = warp), warp 4 TMA producer, warp 5 MMA issuer.
+// Roles per CTA: dQ kernel (192 threads, two CTAs per SM) warps 0-3 softmax (TMEM lane quarter = warp), warp 4 TMA producer,
+// warp 5 MMA issuer; dK/dV kernel (320 threads, one CTA per SM: its TMEM budget is the whole 512 columns) warps 0-7 softmax
+// — warps w and w + 4 share lane quarter w and each walks 32 of the tile's 64 query columns, so two instruction streams per
+// SM sub-partition overlap —, warp 8 TMA producer, warp 9 MMA issuer.
 #include <math.h>
 #include <stdlib.h>
 
@@ -72,12 +75,16 @@ __device__ __forceinline__ void store_acc_row(uint32_t taddr, uint32_t tile, int
 // dQ
 // ============================================================================================================
 namespace dq {
-constexpr int QT = 128, KT = 64, STAGES = 3;
+// K/V ring: a TMA tile takes ~4000 cycles from issue to complete_tx under load, a key tile ~1200 cycles per SM: three stages
+// left the MMA warp waiting for operands (ncu: 41 % of the samples in mbarrier polls); four is what two CTAs per SM can hold
+constexpr int QT = 128, KT = 64, STAGES = 4;
 constexpr int Q_BYTES = QT * HD * 2, KV_BYTES = KT * HD * 2;
 constexpr int SMEM_Q = 0, SMEM_DO = Q_BYTES, SMEM_K = 2 * Q_BYTES, SMEM_V = SMEM_K + STAGES * KV_BYTES;
 constexpr int SMEM_BAR = SMEM_V + STAGES * KV_BYTES;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;
-constexpr int TM_S = 0, TM_DP = 64, TM_DS = 128, TM_DQ = 160, TMEM_COLS = 256;
+// dSt (the bf16 A operand of dQ += dSt K) is double-buffered: a single buffer chains consecutive key tiles through the
+// completion of the previous tile's dQ MMAs (store -> ds_ready -> issue -> MMAs -> dq_done -> next store)
+constexpr int TM_S = 0, TM_DP = 64, TM_DS = 128, TM_DQ = 160, TM_DS1 = 224, TMEM_COLS = 256;
 }  // namespace dq
 
 template <bool DROP>
@@ -91,10 +98,13 @@ fmha_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
   const uint32_t bar = base + SMEM_BAR;
-  const uint32_t qdo_full = bar, sdp_full = bar + 56, sdp_free = bar + 64, ds_ready = bar + 72, dq_done = bar + 80;
+  static_assert(STAGES <= 4, "barrier map");
+  const uint32_t qdo_full = bar, sdp_full = bar + 72, sdp_free = bar + 80;
+  auto ds_ready = [&](int b_) { return bar + 88u + 8u * b_; };
+  auto dq_done = [&](int b_) { return bar + 104u + 8u * b_; };
   auto kv_full = [&](int s) { return bar + 8u + 8u * s; };
-  auto kv_empty = [&](int s) { return bar + 32u + 8u * s; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 96);
+  auto kv_empty = [&](int s) { return bar + 40u + 8u * s; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqb = (p.T + QT - 1) / QT;
@@ -118,11 +128,13 @@ fmha_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     mbar_init(sdp_full, 1);
     mbar_init(sdp_free, 4);
-    mbar_init(ds_ready, 4);
-    mbar_init(dq_done, 1);
+    for (int b_ = 0; b_ < 2; ++b_) {
+      mbar_init(ds_ready(b_), 4);
+      mbar_init(dq_done(b_), 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<TMEM_COLS>(base + SMEM_BAR + 96);
+  if (warp == 5) tmem_alloc<TMEM_COLS>(base + SMEM_BAR + 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -157,14 +169,15 @@ fmha_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       constexpr uint32_t idesc_q = make_idesc_bf16(QT, HD, false, true);  // K_j as MN-major B
       auto issue_dq = [&](int jj) {
         const int st = jj % STAGES;
-        mbar_wait(ds_ready, uint32_t(jj) & 1u);
+        mbar_wait(ds_ready(jj & 1), uint32_t(jj >> 1) & 1u);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t db = make_smem_desc_sw128(base + SMEM_K + st * KV_BYTES, 1024, 1024);
+          const uint32_t t_ds = tmem + uint32_t((jj & 1) ? TM_DS1 : TM_DS);
 #pragma unroll
           for (int k = 0; k < KT / 16; ++k)
-            mma_ts(tmem + TM_DQ, tmem + TM_DS + 8 * k, db + uint64_t(128 * k), idesc_q, (jj > 0 || k > 0) ? 1u : 0u);
-          tc_commit(dq_done);
+            mma_ts(tmem + TM_DQ, t_ds + 8 * k, db + uint64_t(128 * k), idesc_q, (jj > 0 || k > 0) ? 1u : 0u);
+          tc_commit(dq_done(jj & 1));
           tc_commit(kv_empty(st));
         }
         __syncwarp();
@@ -235,21 +248,21 @@ fmha_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           pk[i] = pack_bf16x2(d2[0], d2[1]);
         }
-        if (half == 0 && j > 0) {  // dQ += dSt_{j-1} K_{j-1} must have read the previous dSt
-          mbar_wait(dq_done, uint32_t(j - 1) & 1u);
+        if (half == 0 && j >= 2) {  // dQ += dSt_{j-2} K_{j-2} must have read this dSt buffer
+          mbar_wait(dq_done(j & 1), (uint32_t(j >> 1) + 1u) & 1u);
           tc_fence_after();
         }
-        tmem_st16(t_lane + TM_DS + 16 * half, pk);
+        tmem_st16(t_lane + uint32_t((j & 1) ? TM_DS1 : TM_DS) + 16 * half, pk);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_ready);
+      if (lane == 0) mbar_arrive(ds_ready(j & 1));
     }
     // ---- epilogue: dQ -> bf16 -> swizzled smem (the Q tile's slot) -> TMA store
     const uint32_t tile = base + SMEM_Q;
     if (n_kv > 0) {
-      mbar_wait(dq_done, uint32_t(n_kv - 1) & 1u);
+      mbar_wait(dq_done((n_kv - 1) & 1), uint32_t((n_kv - 1) >> 1) & 1u);  // (MMAs retire in order: the last commit covers all)
       tc_fence_after();
       store_acc_row(t_lane + TM_DQ, tile, row);
     } else {
@@ -276,18 +289,22 @@ fmha_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // dK, dV
 // ============================================================================================================
 namespace dkv {
-constexpr int KT = 128, QT = 64, STAGES = 3;
+// Q/dO ring: eight stages (128 KB; one CTA per SM) keep the ~4000-cycle TMA latency off the tile loop
+constexpr int KT = 128, QT = 64, STAGES = 8;
 constexpr int KV_BYTES = KT * HD * 2, Q_BYTES = QT * HD * 2;
 constexpr int SMEM_K = 0, SMEM_V = KV_BYTES, SMEM_RING = 2 * KV_BYTES;  // stage s: Q_i at +2 s Q_BYTES, dO_i after it
 constexpr int SMEM_STAT = SMEM_RING + STAGES * 2 * Q_BYTES;             // [2 buffers][lse 64 | dsum 64] floats
 constexpr int SMEM_DROP = SMEM_STAT + 2 * 128 * 4;                      // [2 buffers][64 queries][4 words] keep bits
 constexpr int SMEM_BAR = SMEM_DROP + 2 * 64 * 4 * 4;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;
-constexpr int TM_ST = 0, TM_DPT = 128, TM_PT = 256, TM_DST = 288, TM_DV = 320, TM_DK = 384, TMEM_COLS = 512;
+// P^T / dSt^T (bf16 A operands) double-buffered for the same reason as dSt in the dQ kernel: all 512 columns are used
+constexpr int TM_ST = 0, TM_DPT = 128, TM_PT = 256, TM_DST = 288, TM_DV = 320, TM_DK = 384, TM_PT1 = 448, TM_DST1 = 480,
+              TMEM_COLS = 512;
 }  // namespace dkv
 
+constexpr int DKV_THREADS = 320, DKV_PRODUCER = 8, DKV_MMA = 9;
 template <bool DROP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(DKV_THREADS, 1)
 fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                      const __grid_constant__ CUtensorMap tmdK, const __grid_constant__ CUtensorMap tmdV,
@@ -298,12 +315,15 @@ fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
   const uint32_t bar = base + SMEM_BAR;
-  const uint32_t kv_full = bar, p_ready = bar + 88, p_free = bar + 96;
+  const uint32_t kv_full = bar;
+  static_assert(STAGES <= 8, "barrier map");
+  auto p_ready = [&](int b_) { return bar + 168u + 8u * b_; };
+  auto p_free = [&](int b_) { return bar + 184u + 8u * b_; };
   auto q_full = [&](int s) { return bar + 8u + 8u * s; };
-  auto q_empty = [&](int s) { return bar + 32u + 8u * s; };
-  auto st_full = [&](int f) { return bar + 56u + 8u * f; };
-  auto st_free = [&](int f) { return bar + 72u + 8u * f; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 112);
+  auto q_empty = [&](int s) { return bar + 72u + 8u * s; };
+  auto st_full = [&](int f) { return bar + 136u + 8u * f; };
+  auto st_free = [&](int f) { return bar + 152u + 8u * f; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 208);
   float* stat = reinterpret_cast<float*>(smem + SMEM_STAT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -331,7 +351,7 @@ fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     return;
   }
 
-  if (warp == 4 && lane == 0) {
+  if (warp == DKV_PRODUCER && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -345,20 +365,22 @@ fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     for (int f = 0; f < 2; ++f) {
       mbar_init(st_full(f), 1);
-      mbar_init(st_free(f), 4);
+      mbar_init(st_free(f), 8);
     }
-    mbar_init(p_ready, 4);
-    mbar_init(p_free, 1);
+    for (int b_ = 0; b_ < 2; ++b_) {
+      mbar_init(p_ready(b_), 8);
+      mbar_init(p_free(b_), 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<TMEM_COLS>(base + SMEM_BAR + 112);
+  if (warp == DKV_MMA) tmem_alloc<TMEM_COLS>(base + SMEM_BAR + 208);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   pdl_wait();
 
-  if (warp == 4) {
+  if (warp == DKV_PRODUCER) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       mbar_expect_tx(kv_full, 2 * KV_BYTES);
@@ -376,24 +398,25 @@ fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       __syncwarp();
     }
-  } else if (warp == 5) {
+  } else if (warp == DKV_MMA) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_t = make_idesc_bf16(KT, QT, false, false);  // S^T / dP^T: [128 keys, 64 queries]
     constexpr uint32_t idesc_o = make_idesc_bf16(KT, HD, false, true);   // dV / dK: B = dO_i / Q_i, MN-major
     auto issue_dkdv = [&](int ii) {
       const int st = ii % STAGES;
-      mbar_wait(p_ready, uint32_t(ii) & 1u);
+      mbar_wait(p_ready(ii & 1), uint32_t(ii >> 1) & 1u);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t dq_mn = make_smem_desc_sw128(base + SMEM_RING + st * 2 * Q_BYTES, 1024, 1024);
         const uint64_t ddo_mn = make_smem_desc_sw128(base + SMEM_RING + st * 2 * Q_BYTES + Q_BYTES, 1024, 1024);
+        const uint32_t t_pt = tmem + uint32_t((ii & 1) ? TM_PT1 : TM_PT), t_dst = tmem + uint32_t((ii & 1) ? TM_DST1 : TM_DST);
 #pragma unroll
         for (int k = 0; k < QT / 16; ++k)
-          mma_ts(tmem + TM_DV, tmem + TM_PT + 8 * k, ddo_mn + uint64_t(128 * k), idesc_o, (ii > 0 || k > 0) ? 1u : 0u);
+          mma_ts(tmem + TM_DV, t_pt + 8 * k, ddo_mn + uint64_t(128 * k), idesc_o, (ii > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < QT / 16; ++k)
-          mma_ts(tmem + TM_DK, tmem + TM_DST + 8 * k, dq_mn + uint64_t(128 * k), idesc_o, (ii > 0 || k > 0) ? 1u : 0u);
-        tc_commit(p_free);
+          mma_ts(tmem + TM_DK, t_dst + 8 * k, dq_mn + uint64_t(128 * k), idesc_o, (ii > 0 || k > 0) ? 1u : 0u);
+        tc_commit(p_free(ii & 1));
         tc_commit(q_empty(st));
       }
       __syncwarp();
@@ -422,11 +445,14 @@ fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     issue_dkdv(n_q - 1);
   } else {
-    // ------------------------------------------------------------------ softmax warps: thread <-> key row
-    const int row = warp * 32 + lane;
+    // ------------------------------------------------------------------ softmax warps: thread <-> (key row, half of the
+    // tile's query columns)
+    const int wq = warp & 3;    // TMEM lane quarter
+    const int half = warp >> 2; // query columns 32 half .. 32 half + 31 of every tile
+    const int row = wq * 32 + lane;
     const bool kvalid = k_start + row < kv_len;
-    const uint32_t t_lane = tmem + (uint32_t(warp * 32) << 16);
-    const int tid = threadIdx.x;  // 0..127
+    const uint32_t t_lane = tmem + (uint32_t(wq * 32) << 16);
+    const int tid = threadIdx.x;  // 0..255; threads 0..127 also fetch the tiles' statistics / keep bits
     const int64_t stat_base = (int64_t(b) * p.H + head) * p.T;
     // lse (threads 0-63) / Dsum (threads 64-127) of the tile's queries, fetched one tile ahead
     auto fetch_stat = [&](int i) {
@@ -436,34 +462,37 @@ fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     };
     // DROP: keep bits of this tile's 128 keys for the 64 queries of a query tile: thread tid fetches words
     // 4 kb + 2 (tid & 1), +1 of query tid >> 1 (one tile ahead, like the statistics); warp w then reads word w of each
-    // query as a broadcast and tests bit `lane` — the transposed walk over the mask the forward used
+    // query (lane quarter w) as a broadcast and tests bit `lane` — the transposed walk over the mask the forward used
     uint32_t* dbits = reinterpret_cast<uint32_t*>(smem + SMEM_DROP);
     auto fetch_bits = [&](int i) {
       const int qi = i * QT + (tid >> 1);
       if (qi >= p.T) return make_uint2(0u, 0u);
       return __ldg(reinterpret_cast<const uint2*>(p.drop_bits + (stat_base + qi) * p.drop_ld + 4 * kb + 2 * (tid & 1)));
     };
-    stat[tid] = fetch_stat(0);
-    if constexpr (DROP) reinterpret_cast<uint2*>(dbits)[tid] = fetch_bits(0);
+    const bool fetcher = tid < 128;
+    if (fetcher) {
+      stat[tid] = fetch_stat(0);
+      if constexpr (DROP) reinterpret_cast<uint2*>(dbits)[tid] = fetch_bits(0);
+    }
     for (int i = 0; i < n_q; ++i) {
       const int bf = i & 1;
-      const float nxt = i + 1 < n_q ? fetch_stat(i + 1) : 0.0f;
+      float nxt = 0.0f;
       uint2 nxt_bits = make_uint2(0u, 0u);
-      if constexpr (DROP) {
-        if (i + 1 < n_q) nxt_bits = fetch_bits(i + 1);
+      if (fetcher && i + 1 < n_q) {
+        nxt = fetch_stat(i + 1);
+        if constexpr (DROP) nxt_bits = fetch_bits(i + 1);
       }
-      named_bar_sync(1, 128);  // buffer bf is complete (written at the end of the previous iteration)
+      named_bar_sync(1, 256);  // buffer bf is complete (written at the end of the previous iteration)
       const float4* lse4 = reinterpret_cast<const float4*>(stat + 128 * bf);
       const float4* ds4 = reinterpret_cast<const float4*>(stat + 128 * bf + 64);
       mbar_wait(st_full(bf), uint32_t(i >> 1) & 1u);
       tc_fence_after();
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      {
         uint32_t s[32], dp[32], pp[16], pd[16];
         tmem_ld32(t_lane + TM_ST + 64 * bf + 32 * half, s);
         tmem_ld32(t_lane + TM_DPT + 64 * bf + 32 * half, dp);
         tmem_ld_wait();
-        if (half == 1) {
+        {  // this warp's part of S^T / dP^T is in registers: MMAs two tiles ahead may overwrite the buffer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(st_free(bf));
@@ -479,7 +508,7 @@ fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             pr[e] = kvalid ? ex2_approx(__uint_as_float(s[4 * g + e]) - lq[e]) : 0.0f;
             float dpv = __uint_as_float(dp[4 * g + e]);
             if constexpr (DROP) {
-              const bool keep = (dbits[(bf * 64 + 32 * half + 4 * g + e) * 4 + warp] >> lane) & 1u;
+              const bool keep = (dbits[(bf * 64 + 32 * half + 4 * g + e) * 4 + wq] >> lane) & 1u;
               dpv = keep ? dpv * p.drop_scale : 0.0f;
               dsv[e] = pr[e] * (dpv - dq_[e]) * LN2;
               pr[e] = keep ? pr[e] * p.drop_scale : 0.0f;  // P_d^T feeds dV
@@ -492,27 +521,29 @@ fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pd[2 * g] = pack_bf16x2(dsv[0], dsv[1]);
           pd[2 * g + 1] = pack_bf16x2(dsv[2], dsv[3]);
         }
-        if (half == 0 && i > 0) {  // dV / dK MMAs of the previous tile must have read P^T / dSt^T
-          mbar_wait(p_free, uint32_t(i - 1) & 1u);
+        if (i >= 2) {  // the dV / dK MMAs of tile i - 2 must have read this P^T / dSt^T buffer
+          mbar_wait(p_free(bf), (uint32_t(i >> 1) + 1u) & 1u);
           tc_fence_after();
         }
-        tmem_st16(t_lane + TM_PT + 16 * half, pp);
-        tmem_st16(t_lane + TM_DST + 16 * half, pd);
+        tmem_st16(t_lane + uint32_t(bf ? TM_PT1 : TM_PT) + 16 * half, pp);
+        tmem_st16(t_lane + uint32_t(bf ? TM_DST1 : TM_DST) + 16 * half, pd);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
-      stat[128 * (bf ^ 1) + tid] = nxt;
-      if constexpr (DROP) reinterpret_cast<uint2*>(dbits)[128 * (bf ^ 1) + tid] = nxt_bits;
+      if (lane == 0) mbar_arrive(p_ready(bf));
+      if (fetcher) {
+        stat[128 * (bf ^ 1) + tid] = nxt;
+        if constexpr (DROP) reinterpret_cast<uint2*>(dbits)[128 * (bf ^ 1) + tid] = nxt_bits;
+      }
     }
-    // ---- epilogue: dV, dK -> bf16 -> swizzled smem (the K / V tiles' slots) -> TMA stores
-    mbar_wait(p_free, uint32_t(n_q - 1) & 1u);
+    // ---- epilogue: dV (warps 0-3), dK (warps 4-7) -> bf16 -> swizzled smem (the K / V tiles' slots) -> TMA stores
+    mbar_wait(p_free((n_q - 1) & 1), uint32_t((n_q - 1) >> 1) & 1u);  // (MMAs retire in order: the last commit covers all)
     tc_fence_after();
-    store_acc_row(t_lane + TM_DV, base + SMEM_K, row);
-    store_acc_row(t_lane + TM_DK, base + SMEM_V, row);
+    if (half == 0) store_acc_row(t_lane + TM_DV, base + SMEM_K, row);
+    else store_acc_row(t_lane + TM_DK, base + SMEM_V, row);
     fence_proxy_async_smem();
-    named_bar_sync(1, 128);
+    named_bar_sync(1, 256);
     if (threadIdx.x == 0) {
       tma_store_3d(&tmdV, base + SMEM_K, col, k_start, b);
       tma_store_3d(&tmdK, base + SMEM_V, col, k_start, b);
@@ -522,7 +553,7 @@ fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == DKV_MMA) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem);
   }
@@ -585,11 +616,11 @@ int launch_fmha_bwd(const FmhaBwdArgs& a, cudaStream_t stream) {
     }
     const unsigned grid = unsigned((a.T + dkv::KT - 1) / dkv::KT) * unsigned(a.H) * unsigned(a.B);
     if (drop)
-      RP_CUDA_CHECK(launch_pdl(fmha_bwd_dkdv_kernel<true>, dim3(grid), dim3(192), dkv::SMEM_TOTAL, stream, tmQ, tmK, tmV, tmdO,
-                               tmdK, tmdV, p));
+      RP_CUDA_CHECK(launch_pdl(fmha_bwd_dkdv_kernel<true>, dim3(grid), dim3(DKV_THREADS), dkv::SMEM_TOTAL, stream, tmQ, tmK, tmV,
+                               tmdO, tmdK, tmdV, p));
     else
-      RP_CUDA_CHECK(launch_pdl(fmha_bwd_dkdv_kernel<false>, dim3(grid), dim3(192), dkv::SMEM_TOTAL, stream, tmQ, tmK, tmV, tmdO,
-                               tmdK, tmdV, p));
+      RP_CUDA_CHECK(launch_pdl(fmha_bwd_dkdv_kernel<false>, dim3(grid), dim3(DKV_THREADS), dkv::SMEM_TOTAL, stream, tmQ, tmK, tmV,
+                               tmdO, tmdK, tmdV, p));
     count_launch();
   }
   RP_CUDA_CHECK(cudaGetLastError());
