@@ -56,15 +56,24 @@ constexpr int KT = 128;
 constexpr int HD = 64;
 constexpr int TILE_BYTES = QT * HD * 2;  // 16 KB (Q, K and V tiles are all 128 x 64 bf16)
 
+// K ring depth of the two-CTAs-per-SM kernel.  K_{i+1} is requested when Q K^T_{i-1} retires and needed about 1.5
+// iterations (~3900 cycles) later; a TMA tile that misses L2 takes ~4000 cycles under load, so two stages leave no
+// slack.  The third stage only fits next to a second CTA when the alignment slack of the dynamic segment shrinks to
+// 256 bytes.  Measured (profiles/r02_notes.md 1.5): +0.2 .. 0.4 % on the kernel alone at T = 1801 / 1792 / 8192.
+#ifndef RP_FMHA_KSTAGES
+#define RP_FMHA_KSTAGES 3
+#endif
 template <int NQ>
 struct Cfg {
-  static constexpr int K_STAGES = NQ == 2 ? 3 : 2;
+  static constexpr int K_STAGES = NQ == 2 ? 3 : RP_FMHA_KSTAGES;
   static constexpr int V_STAGES = 3;  // V_j is needed 1.5 iterations after its slot frees with 2 stages: not enough for the TMA latency
   static constexpr int SMEM_Q_OFF = 0;
   static constexpr int SMEM_K_OFF = NQ * TILE_BYTES;
   static constexpr int SMEM_V_OFF = SMEM_K_OFF + K_STAGES * TILE_BYTES;
   static constexpr int SMEM_BAR_OFF = SMEM_V_OFF + V_STAGES * TILE_BYTES;
-  static constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 512 + 1024;
+  // barriers + TMEM slot: 256 bytes; alignment slack of the (1024-aligned, checked at run time) dynamic segment
+  static constexpr int SMEM_SLACK = (NQ == 1 && K_STAGES == 3) ? 256 : 1024;
+  static constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 256 + SMEM_SLACK;
   static constexpr int SOFTMAX_WARPS = 4 * NQ;
   static constexpr int PRODUCER_WARP = 4 * NQ;
   static constexpr int MMA_WARP = 4 * NQ + 1;
@@ -177,10 +186,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int SMEM_Q_OFF = C::SMEM_Q_OFF, SMEM_K_OFF = C::SMEM_K_OFF, SMEM_V_OFF = C::SMEM_V_OFF;
   constexpr int SMEM_BAR_OFF = C::SMEM_BAR_OFF;
   constexpr int TM_S = C::TM_S, TM_P = C::TM_P, TM_O = C::TM_O, TMEM_COLS = C::TMEM_COLS;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
+  if (base - raw_addr > uint32_t(C::SMEM_SLACK)) __trap();  // the budget leaves SMEM_SLACK bytes of alignment slack
 
   const uint32_t bar_base = pin_u32(base + SMEM_BAR_OFF);
   auto q_full = [&](int q) { return bar_base + 8u * q; };

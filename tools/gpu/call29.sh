@@ -1,0 +1,6 @@
+#!/bin/bash
+# round 2, call 29: ncu of the persistent attention kernel vs the shipped one (same shape)
+mkdir -p gpurun_out
+RP_FMHA_PERSIST=1 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"fmha_fwd_persist" -s 2 -c 1 -o gpurun_out/r02_fmha_persist python tools/kernel_bench.py fmha --iters 1 > gpurun_out/ncu_persist.log 2>&1; echo "ncu exit $?"
+RP_FMHA_PERSIST=0 timeout 600 ncu --set full --import-source on --clock-control none -k regex:"fmha_fwd_kernel" -s 2 -c 1 -o gpurun_out/r02_fmha_shipped python tools/kernel_bench.py fmha --iters 1 > gpurun_out/ncu_shipped.log 2>&1; echo "ncu exit $?"
+ls -la gpurun_out/r02_fmha_*.ncu-rep
