@@ -221,6 +221,12 @@ int32_t rp_fmha_train(const void* q, const void* k, const void* v, void* o, int6
 int32_t rp_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                     float* dsum, void* dq, void* dk, void* dv, int64_t ld_qkv, int64_t ld_o, int64_t ld_dqkv,
                     int32_t B, int32_t H, int32_t T, const int32_t* kv_lens, void* stream);
+/* rp_fmha_bwd / rp_fmha_bwd_dropout run ONE kernel for dK, dV and dQ by default; its dQ is summed over the key tiles by
+ * fp32 adds in L2 whose order is not fixed, so dq is reproducible to the rounding of a T/128-term fp32 sum, not bit for bit
+ * (torch's own attention backward makes the same trade unless torch.use_deterministic_algorithms is set).  on = 1 selects
+ * the two deterministic kernels (about 20 % slower), on = 0 the fused one, on < 0 the default (environment
+ * RP_FMHA_BWD_FUSED, fused unless it is 0).  Process-wide. */
+int32_t rp_set_attn_bwd_deterministic(int32_t on);
 
 /* ---- train-mode dropout (the nn.Dropout(0.1) sites of the reference graph under model.train(), main.py:285:
  * nn.TransformerEncoderLayer's dropout1 / dropout / dropout2 and the attention-weight dropout of its

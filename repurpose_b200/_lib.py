@@ -80,6 +80,7 @@ SIGNATURES = {
     "rp_gemm_resid_ln": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64,
                                  c_i32, c_i32, c_vp]),
     "rp_set_skip_padding": (c_i32, [c_vp, c_i32]),
+    "rp_set_attn_bwd_deterministic": (c_i32, [c_i32]),
     "rp_profile_begin": (c_i32, [c_vp]),
     "rp_profile_end": (c_i32, [c_vp, c_vp, c_vp]),
     "rp_decode_nms": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, C.POINTER(RpDecodeCfg), c_i32,

@@ -690,6 +690,11 @@ int32_t rp_fmha_bwd(const void* q, const void* k, const void* v, const void* o, 
   return launch_fmha_bwd(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int32_t rp_set_attn_bwd_deterministic(int32_t on) {
+  set_fmha_bwd_deterministic(on);
+  return RP_OK;
+}
+
 int32_t rp_fmha_bwd_dropout(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                             float* dsum, void* dq, void* dk, void* dv, int64_t ld_qkv, int64_t ld_o, int64_t ld_dqkv,
                             int32_t B, int32_t H, int32_t T, const int32_t* kv_lens, const uint32_t* keep_bits,

@@ -22,6 +22,7 @@
 // warp 5 MMA issuer; dK/dV kernel (320 threads, one CTA per SM: its TMEM budget is the whole 512 columns) warps 0-7 softmax
 // — warps w and w + 4 share lane quarter w and each walks 32 of the tile's 64 query columns, so two instruction streams per
 // SM sub-partition overlap —, warp 8 TMA producer, warp 9 MMA issuer.
+#include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -559,9 +560,374 @@ fmha_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+
+// ============================================================================================================
+// dK, dV and dQ in one kernel (five contractions per tile pair instead of seven; dQ accumulated in L2)
+// ============================================================================================================
+// The dK/dV kernel above, extended by the third product of the tile pair: dQ_i += dSt_i K_j.  What changes:
+//   * dSt^T leaves the softmax threads through SHARED memory (bf16 [128 keys][64 queries], 128-byte rows, SWIZZLE_128B)
+//     instead of TMEM: the one tile is the K-major A operand of dK += dSt^T Q_i and — read transposed, as an MN-major A
+//     operand — of dQ_i(partial) = dSt K_j (K_j as MN-major B, like V in the forward).
+//   * The dQ MMA runs with M = 128 although a tile has 64 queries: its descriptor starts 16 KB BELOW the dSt tile with
+//     LBO = 16 KB, so rows 0-63 of A are whatever precedes the tile (never read back) and rows 64-127 are the tile: the 64
+//     real accumulator rows land in TMEM lanes 64-127, the lane quarters of warps 10 and 11 of the auxiliary warpgroup.
+//     Those two otherwise idle warps drain them (tcgen05.ld -> fp32 staging tile in shared memory) and one thread hands the
+//     16 KB tile to the TMA reduce path: cp.reduce.async.bulk .add.f32 into the fp32 accumulator of the (batch, head)'s
+//     dQ — the adds happen in L2 (measured tools/ubench/tma_reduce.cu: 5.4 TB/s = 870 cycles per tile and SM when the 15
+//     key-tile CTAs of a head add into the same 29 tiles, against ~1600 cycles per iteration here).
+//   * The accumulator is laid out per tile as [16 column chunks][64 queries][4 floats] (what the drain warps can write
+//     without bank conflicts); attn_bwd_dq_convert_kernel turns it into the bf16 dQ rows and applies 1 / (8 ln 2) (the
+//     shared dSt tile carries the ln 2 factor of dK).
+// The fp32 adds of the 15 key tiles arrive in no fixed order: dQ is reproducible to fp32 rounding of a 15-term sum, not
+// bit for bit.  RP_FMHA_BWD_FUSED=0 selects the two deterministic kernels above.
+namespace fus {
+constexpr int KT = 128, QT = 64, STAGES = 6;
+constexpr int KV_BYTES = KT * HD * 2, Q_BYTES = QT * HD * 2, DQ_BYTES = QT * HD * 4;
+constexpr int SMEM_K = 0, SMEM_V = KV_BYTES, SMEM_RING = 2 * KV_BYTES;  // stage s: Q_i at +2 s Q_BYTES, dO_i after it
+constexpr int SMEM_DST = SMEM_RING + STAGES * 2 * Q_BYTES;              // [2 buffers] dSt^T tiles (16 KB each)
+constexpr int SMEM_DQ = SMEM_DST + 2 * KV_BYTES;                        // [2 buffers] fp32 dQ partial tiles (16 KB each)
+constexpr int SMEM_STAT = SMEM_DQ + 2 * DQ_BYTES;                       // [2 buffers][lse 64 | dsum 64] floats
+constexpr int SMEM_DROP = SMEM_STAT + 2 * 128 * 4;                      // [2 buffers][64 queries][4 words] keep bits
+constexpr int SMEM_BAR = SMEM_DROP + 2 * 64 * 4 * 4;
+constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;
+static_assert(SMEM_DST % 1024 == 0 && SMEM_DQ % 1024 == 0 && SMEM_DST >= KV_BYTES, "swizzled tiles are 1024-byte aligned");
+static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+constexpr int TM_ST = 0, TM_DPT = 128, TM_PT = 256, TM_PT1 = 288, TM_DV = 320, TM_DK = 384, TM_DQ = 448, TMEM_COLS = 512;
+constexpr int THREADS = 384, PRODUCER = 8, MMA = 9, DRAIN0 = 10;  // warps 10, 11 drain dQ (TMEM lane quarters 2, 3)
+}  // namespace fus
+
+template <bool DROP>
+__global__ void __launch_bounds__(fus::THREADS, 1)
+fmha_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                      const __grid_constant__ CUtensorMap tmdK, const __grid_constant__ CUtensorMap tmdV,
+                      const BwdParams p, float* __restrict__ dq_acc) {
+  using namespace fus;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t bar = base + SMEM_BAR;
+  const uint32_t kv_full = bar;
+  static_assert(STAGES <= 8, "barrier map");
+  auto q_full = [&](int s) { return bar + 8u + 8u * s; };
+  auto q_empty = [&](int s) { return bar + 72u + 8u * s; };
+  auto st_full = [&](int f) { return bar + 136u + 8u * f; };
+  auto st_free = [&](int f) { return bar + 152u + 8u * f; };
+  auto p_ready = [&](int b_) { return bar + 168u + 8u * b_; };
+  auto p_free = [&](int b_) { return bar + 184u + 8u * b_; };
+  const uint32_t dq_full = bar + 200u, dq_free = bar + 208u;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SMEM_BAR + 224);
+  float* stat = reinterpret_cast<float*>(smem + SMEM_STAT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (p.T + KT - 1) / KT;
+  const int kb = int(blockIdx.x) % nkb, bh = int(blockIdx.x) / nkb;
+  const int head = bh % p.H, b = bh / p.H;
+  const int k_start = kb * KT;
+  const int col = head * HD;
+  int kv_len = p.kv_lens != nullptr ? p.kv_lens[b] : p.T;
+  kv_len = kv_len < 0 ? 0 : (kv_len > p.T ? p.T : kv_len);
+  const int n_q = (p.T + QT - 1) / QT;
+
+  if (k_start >= kv_len) {
+    // every key of this tile is padding: its K / V rows receive no gradient and it adds nothing to dQ
+    pdl_wait();
+    for (int i = threadIdx.x; i < KV_BYTES / 16; i += blockDim.x) st_shared_v4(base + SMEM_K + 16 * i, 0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tma_store_3d(&tmdK, base + SMEM_K, col, k_start, b);
+      tma_store_3d(&tmdV, base + SMEM_K, col, k_start, b);
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+    return;
+  }
+
+  if (warp == PRODUCER && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmdK);
+    tma_prefetch_desc(&tmdV);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 1);
+    }
+    for (int f = 0; f < 2; ++f) {
+      mbar_init(st_full(f), 1);
+      mbar_init(st_free(f), 8);
+      mbar_init(p_ready(f), 8);
+      mbar_init(p_free(f), 1);
+    }
+    mbar_init(dq_full, 1);
+    mbar_init(dq_free, 2);
+    fence_mbar_init();
+  }
+  if (warp == MMA) tmem_alloc<TMEM_COLS>(base + SMEM_BAR + 224);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  if (warp == PRODUCER) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_expect_tx(kv_full, 2 * KV_BYTES);
+      tma_load_3d(base + SMEM_K, &tmK, kv_full, col, k_start, b);
+      tma_load_3d(base + SMEM_V, &tmV, kv_full, col, k_start, b);
+    }
+    __syncwarp();
+    for (int i = 0; i < n_q; ++i) {
+      const int st = i % STAGES;
+      mbar_wait(q_empty(st), (uint32_t(i / STAGES) & 1u) ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(q_full(st), 2 * Q_BYTES);
+        tma_load_3d(base + SMEM_RING + st * 2 * Q_BYTES, &tmQ, q_full(st), col, i * QT, b);
+        tma_load_3d(base + SMEM_RING + st * 2 * Q_BYTES + Q_BYTES, &tmdO, q_full(st), col, i * QT, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == MMA) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_t = make_idesc_bf16(KT, QT, false, false);   // S^T / dP^T: [128 keys, 64 queries]
+    constexpr uint32_t idesc_o = make_idesc_bf16(KT, HD, false, true);    // dV / dK: B = dO_i / Q_i, MN-major
+    constexpr uint32_t idesc_q = make_idesc_bf16(128, HD, true, true);    // dQ: A = dSt (MN-major, rows 64-127), B = K_j
+    auto issue_grads = [&](int ii) {
+      const int st = ii % STAGES, bf = ii & 1;
+      mbar_wait(p_ready(bf), uint32_t(ii >> 1) & 1u);
+      if (ii > 0) mbar_wait(dq_free, uint32_t(ii - 1) & 1u);  // the drain warps have read the previous tile's dQ partial
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dq_mn = make_smem_desc_sw128(base + SMEM_RING + st * 2 * Q_BYTES, 1024, 1024);
+        const uint64_t ddo_mn = make_smem_desc_sw128(base + SMEM_RING + st * 2 * Q_BYTES + Q_BYTES, 1024, 1024);
+        const uint32_t dst_tile = base + SMEM_DST + bf * KV_BYTES;
+        const uint64_t dst_k = make_smem_desc_sw128(dst_tile, 1024, 16);                 // [128 keys][64 q], K-major A
+        const uint64_t dst_mn = make_smem_desc_sw128(dst_tile - KV_BYTES, 1024, KV_BYTES);  // transposed: tile = rows 64-127
+        const uint64_t dk_mn = make_smem_desc_sw128(base + SMEM_K, 1024, 1024);
+        const uint32_t t_pt = tmem + uint32_t(bf ? TM_PT1 : TM_PT);
+#pragma unroll
+        for (int k = 0; k < QT / 16; ++k)
+          mma_ts(tmem + TM_DV, t_pt + 8 * k, ddo_mn + uint64_t(128 * k), idesc_o, (ii > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < QT / 16; ++k)
+          mma_ss(tmem + TM_DK, dst_k + uint64_t(2 * k), dq_mn + uint64_t(128 * k), idesc_o, (ii > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < KT / 16; ++k)
+          mma_ss(tmem + TM_DQ, dst_mn + uint64_t(128 * k), dk_mn + uint64_t(128 * k), idesc_q, k > 0 ? 1u : 0u);
+        tc_commit(dq_full);
+        tc_commit(p_free(bf));
+        tc_commit(q_empty(st));
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    for (int i = 0; i < n_q; ++i) {
+      const int st = i % STAGES, bf = i & 1;
+      mbar_wait(q_full(st), uint32_t(i / STAGES) & 1u);
+      if (i >= 2) mbar_wait(st_free(bf), (uint32_t(i >> 1) + 1u) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dk = make_smem_desc_sw128(base + SMEM_K, 1024, 16);
+        const uint64_t dv = make_smem_desc_sw128(base + SMEM_V, 1024, 16);
+        const uint64_t dq_ = make_smem_desc_sw128(base + SMEM_RING + st * 2 * Q_BYTES, 1024, 16);
+        const uint64_t ddo = make_smem_desc_sw128(base + SMEM_RING + st * 2 * Q_BYTES + Q_BYTES, 1024, 16);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          mma_ss(tmem + TM_ST + 64 * bf, dk + uint64_t(2 * k), dq_ + uint64_t(2 * k), idesc_t, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          mma_ss(tmem + TM_DPT + 64 * bf, dv + uint64_t(2 * k), ddo + uint64_t(2 * k), idesc_t, k > 0 ? 1u : 0u);
+        tc_commit(st_full(bf));
+      }
+      __syncwarp();
+      if (i > 0) issue_grads(i - 1);
+    }
+    issue_grads(n_q - 1);
+  } else if (warp >= DRAIN0) {
+    // ------------------------------------------------------------------ dQ drain: TMEM lanes 64-127 -> fp32 staging tile
+    // -> TMA reduce (add.f32) into this (batch, head)'s accumulator tile i
+    const int row = (warp - DRAIN0) * 32 + lane;  // query row of the tile
+    const uint32_t t_lane = tmem + (uint32_t(64 + (warp - DRAIN0) * 32) << 16) + TM_DQ;
+    const bool leader = warp == DRAIN0 && lane == 0;
+    float* acc = dq_acc + int64_t(bh) * n_q * (QT * HD);
+    for (int i = 0; i < n_q; ++i) {
+      const uint32_t stage = base + SMEM_DQ + (i & 1) * DQ_BYTES;
+      uint32_t a[32], c[32];
+      mbar_wait(dq_full, uint32_t(i) & 1u);
+      tc_fence_after();
+      tmem_ld32(t_lane, a);
+      tmem_ld32(t_lane + 32, c);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free);
+      named_bar_sync(2, 64);  // the reduce that last read this staging buffer has finished reading (leader, below)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        st_shared_v4(stage + uint32_t(j * 64 + row) * 16u, a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+        st_shared_v4(stage + uint32_t((8 + j) * 64 + row) * 16u, c[4 * j], c[4 * j + 1], c[4 * j + 2], c[4 * j + 3]);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, 64);
+      if (leader) {
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(acc + int64_t(i) * (QT * HD)),
+                     "r"(stage), "n"(DQ_BYTES)
+                     : "memory");
+        tma_store_commit();
+        tma_store_wait_read<1>();  // every reduce but this one has read its staging buffer: the other buffer is free
+      }
+    }
+    if (leader) tma_store_wait_all<0>();
+  } else {
+    // ------------------------------------------------------------------ softmax warps: thread <-> (key row, half of the
+    // tile's query columns)
+    const int wq = warp & 3;    // TMEM lane quarter
+    const int half = warp >> 2; // query columns 32 half .. 32 half + 31 of every tile
+    const int row = wq * 32 + lane;
+    const bool kvalid = k_start + row < kv_len;
+    const uint32_t t_lane = tmem + (uint32_t(wq * 32) << 16);
+    const int tid = threadIdx.x;  // 0..255; threads 0..127 also fetch the tiles' statistics / keep bits
+    const int64_t stat_base = (int64_t(b) * p.H + head) * p.T;
+    auto fetch_stat = [&](int i) {
+      const int qi = i * QT + (tid & 63);
+      if (tid < 64) return qi < p.T ? p.lse[stat_base + qi] : INFINITY;
+      return qi < p.T ? p.dsum[stat_base + qi] : 0.0f;
+    };
+    uint32_t* dbits = reinterpret_cast<uint32_t*>(smem + SMEM_DROP);
+    auto fetch_bits = [&](int i) {
+      const int qi = i * QT + (tid >> 1);
+      if (qi >= p.T) return make_uint2(0u, 0u);
+      return __ldg(reinterpret_cast<const uint2*>(p.drop_bits + (stat_base + qi) * p.drop_ld + 4 * kb + 2 * (tid & 1)));
+    };
+    const bool fetcher = tid < 128;
+    if (fetcher) {
+      stat[tid] = fetch_stat(0);
+      if constexpr (DROP) reinterpret_cast<uint2*>(dbits)[tid] = fetch_bits(0);
+    }
+    for (int i = 0; i < n_q; ++i) {
+      const int bf = i & 1;
+      float nxt = 0.0f;
+      uint2 nxt_bits = make_uint2(0u, 0u);
+      if (fetcher && i + 1 < n_q) {
+        nxt = fetch_stat(i + 1);
+        if constexpr (DROP) nxt_bits = fetch_bits(i + 1);
+      }
+      named_bar_sync(1, 256);  // buffer bf is complete (written at the end of the previous iteration)
+      const float4* lse4 = reinterpret_cast<const float4*>(stat + 128 * bf);
+      const float4* ds4 = reinterpret_cast<const float4*>(stat + 128 * bf + 64);
+      mbar_wait(st_full(bf), uint32_t(i >> 1) & 1u);
+      tc_fence_after();
+      {
+        uint32_t s[32], dp[32], pp[16], pd[16];
+        tmem_ld32(t_lane + TM_ST + 64 * bf + 32 * half, s);
+        tmem_ld32(t_lane + TM_DPT + 64 * bf + 32 * half, dp);
+        tmem_ld_wait();
+        {  // this warp's part of S^T / dP^T is in registers: MMAs two tiles ahead may overwrite the buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(st_free(bf));
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 l4 = lse4[8 * half + g];
+          const float4 d4 = ds4[8 * half + g];
+          const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq_[4] = {d4.x, d4.y, d4.z, d4.w};
+          float pr[4], dsv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            pr[e] = kvalid ? ex2_approx(__uint_as_float(s[4 * g + e]) - lq[e]) : 0.0f;
+            float dpv = __uint_as_float(dp[4 * g + e]);
+            if constexpr (DROP) {
+              const bool keep = (dbits[(bf * 64 + 32 * half + 4 * g + e) * 4 + wq] >> lane) & 1u;
+              dpv = keep ? dpv * p.drop_scale : 0.0f;
+              dsv[e] = pr[e] * (dpv - dq_[e]) * LN2;
+              pr[e] = keep ? pr[e] * p.drop_scale : 0.0f;  // P_d^T feeds dV
+            } else {
+              dsv[e] = pr[e] * (dpv - dq_[e]) * LN2;
+            }
+          }
+          pp[2 * g] = pack_bf16x2(pr[0], pr[1]);
+          pp[2 * g + 1] = pack_bf16x2(pr[2], pr[3]);
+          pd[2 * g] = pack_bf16x2(dsv[0], dsv[1]);
+          pd[2 * g + 1] = pack_bf16x2(dsv[2], dsv[3]);
+        }
+        if (i >= 2) {  // the dV / dK / dQ MMAs of tile i - 2 must have read this P^T buffer and this dSt^T tile
+          mbar_wait(p_free(bf), (uint32_t(i >> 1) + 1u) & 1u);
+          tc_fence_after();
+        }
+        tmem_st16(t_lane + uint32_t(bf ? TM_PT1 : TM_PT) + 16 * half, pp);
+        const uint32_t dst_tile = base + SMEM_DST + bf * KV_BYTES;  // key row `row`, query columns 32 half .. +31 = 64 bytes
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(swz(dst_tile, row, 4 * half + j), pd[4 * j], pd[4 * j + 1], pd[4 * j + 2], pd[4 * j + 3]);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready(bf));
+      if (fetcher) {
+        stat[128 * (bf ^ 1) + tid] = nxt;
+        if constexpr (DROP) reinterpret_cast<uint2*>(dbits)[128 * (bf ^ 1) + tid] = nxt_bits;
+      }
+    }
+    // ---- epilogue: dV (warps 0-3), dK (warps 4-7) -> bf16 -> swizzled smem (the K / V tiles' slots) -> TMA stores
+    mbar_wait(p_free((n_q - 1) & 1), uint32_t((n_q - 1) >> 1) & 1u);  // (MMAs retire in order: the last commit covers all)
+    tc_fence_after();
+    if (half == 0) store_acc_row(t_lane + TM_DV, base + SMEM_K, row);
+    else store_acc_row(t_lane + TM_DK, base + SMEM_V, row);
+    fence_proxy_async_smem();
+    named_bar_sync(1, 256);
+    if (threadIdx.x == 0) {
+      tma_store_3d(&tmdV, base + SMEM_K, col, k_start, b);
+      tma_store_3d(&tmdK, base + SMEM_V, col, k_start, b);
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == fus::MMA) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem);
+  }
+}
+
+// fp32 dQ accumulator (per (batch, head): [query tiles][16 column chunks][64 queries][4 floats]) -> bf16 rows of dq, scaled
+// by 1 / (8 ln 2); thread <-> (query row of the tile, four column chunks)
+__global__ void __launch_bounds__(256)
+attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t ld_dq, int T, int H, int n_q) {
+  pdl_wait();
+  const int i = int(blockIdx.x) % n_q, bh = int(blockIdx.x) / n_q;
+  const int head = bh % H, b = bh / H;
+  const int row = threadIdx.x & 63, cg = threadIdx.x >> 6;
+  const int q = i * 64 + row;
+  if (q >= T) return;
+  const float4* tile = reinterpret_cast<const float4*>(acc) + (int64_t(bh) * n_q + i) * 1024;
+  constexpr float SC = 0.125f / LN2;
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 v = tile[(4 * cg + j) * 64 + row];
+    w[2 * j] = pack_bf16x2(v.x * SC, v.y * SC);
+    w[2 * j + 1] = pack_bf16x2(v.z * SC, v.w * SC);
+  }
+  uint4* out = reinterpret_cast<uint4*>(dq + (int64_t(b) * T + q) * ld_dq + head * 64 + 16 * cg);
+  out[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  out[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 }  // namespace
 
 int launch_attn_bwd_dsum(const void* o, const void* d_o, int B, int T, int H, float* dsum, cudaStream_t stream);
+
+static int g_bwd_deterministic = -1;
+void set_fmha_bwd_deterministic(int on) { g_bwd_deterministic = on < 0 ? -1 : (on != 0 ? 1 : 0); }
 
 int launch_fmha_bwd(const FmhaBwdArgs& a, cudaStream_t stream) {
   RP_CHECK(a.B > 0 && a.H > 0 && a.T > 0, "fmha_bwd: empty problem");
@@ -578,6 +944,55 @@ int launch_fmha_bwd(const FmhaBwdArgs& a, cudaStream_t stream) {
                      reinterpret_cast<uintptr_t>(a.drop_bits) % 16 == 0),
            "fmha_bwd: keep-bit rows must be 16-byte aligned and cover every 128-key tile");
   const uint64_t T = a.T, B = a.B;
+  static const bool fused_default = !(getenv("RP_FMHA_BWD_FUSED") && atoi(getenv("RP_FMHA_BWD_FUSED")) == 0);
+  const bool fused = g_bwd_deterministic < 0 ? fused_default : g_bwd_deterministic == 0;
+  if (fused) {
+    // per-device fp32 dQ accumulator, grown on demand and kept (an attention backward of the same shape follows every step)
+    static float* acc_on[kMaxDevices];
+    static size_t acc_bytes_on[kMaxDevices];
+    const int dev = current_device();
+    const int n_q = (a.T + fus::QT - 1) / fus::QT;
+    const size_t need = size_t(a.B) * a.H * n_q * fus::DQ_BYTES;
+    if (acc_bytes_on[dev] < need) {
+      if (acc_on[dev] != nullptr) {
+        RP_CUDA_CHECK(cudaStreamSynchronize(stream));
+        RP_CUDA_CHECK(cudaFree(acc_on[dev]));
+        acc_on[dev] = nullptr;
+        acc_bytes_on[dev] = 0;
+      }
+      RP_CUDA_CHECK(cudaMalloc(&acc_on[dev], need));
+      acc_bytes_on[dev] = need;
+    }
+    float* acc = acc_on[dev];
+    RP_CUDA_CHECK(cudaMemsetAsync(acc, 0, need, stream));
+    CUtensorMap tmQ, tmK, tmV, tmdO, tmdK, tmdV;
+    if ((rc = make_tmap_3d(&tmQ, bf, a.q, cols, T, B, a.ld_qkv * 2, T * a.ld_qkv * 2, HD, fus::QT))) return rc;
+    if ((rc = make_tmap_3d(&tmK, bf, a.k, cols, T, B, a.ld_qkv * 2, T * a.ld_qkv * 2, HD, fus::KT))) return rc;
+    if ((rc = make_tmap_3d(&tmV, bf, a.v, cols, T, B, a.ld_qkv * 2, T * a.ld_qkv * 2, HD, fus::KT))) return rc;
+    if ((rc = make_tmap_3d(&tmdO, bf, a.d_o, cols, T, B, a.ld_o * 2, T * a.ld_o * 2, HD, fus::QT))) return rc;
+    if ((rc = make_tmap_3d(&tmdK, bf, a.dk, cols, T, B, a.ld_dqkv * 2, T * a.ld_dqkv * 2, HD, fus::KT))) return rc;
+    if ((rc = make_tmap_3d(&tmdV, bf, a.dv, cols, T, B, a.ld_dqkv * 2, T * a.ld_dqkv * 2, HD, fus::KT))) return rc;
+    static bool configured_on[kMaxDevices];
+    bool& configured = configured_on[dev];
+    if (!configured) {
+      RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_bwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fus::SMEM_TOTAL));
+      RP_CUDA_CHECK(cudaFuncSetAttribute(fmha_bwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fus::SMEM_TOTAL));
+      configured = true;
+    }
+    const unsigned grid = unsigned((a.T + fus::KT - 1) / fus::KT) * unsigned(a.H) * unsigned(a.B);
+    if (drop)
+      RP_CUDA_CHECK(launch_pdl(fmha_bwd_fused_kernel<true>, dim3(grid), dim3(fus::THREADS), fus::SMEM_TOTAL, stream, tmQ, tmK, tmV,
+                               tmdO, tmdK, tmdV, p, acc));
+    else
+      RP_CUDA_CHECK(launch_pdl(fmha_bwd_fused_kernel<false>, dim3(grid), dim3(fus::THREADS), fus::SMEM_TOTAL, stream, tmQ, tmK, tmV,
+                               tmdO, tmdK, tmdV, p, acc));
+    count_launch();
+    RP_CUDA_CHECK(launch_pdl(attn_bwd_dq_convert_kernel, dim3(unsigned(n_q) * unsigned(a.H) * unsigned(a.B)), dim3(256), 0, stream,
+                             static_cast<const float*>(acc), static_cast<__nv_bfloat16*>(a.dq), a.ld_dqkv, a.T, a.H, n_q));
+    count_launch();
+    RP_CUDA_CHECK(cudaGetLastError());
+    return RP_OK;
+  }
   {
     CUtensorMap tmQ, tmK, tmV, tmdO, tmdQ;
     if ((rc = make_tmap_3d(&tmQ, bf, a.q, cols, T, B, a.ld_qkv * 2, T * a.ld_qkv * 2, HD, dq::QT))) return rc;

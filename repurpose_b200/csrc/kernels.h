@@ -221,5 +221,8 @@ struct FmhaBwdArgs {
   float drop_scale = 1.0f;
 };
 int launch_fmha_bwd(const FmhaBwdArgs& a, cudaStream_t stream);
+// 1: the two deterministic kernels (dQ, then dK/dV; S and dP recomputed); 0: the fused kernel whose dQ is summed over the
+// key tiles by fp32 adds in L2 (no fixed order); -1: the default (RP_FMHA_BWD_FUSED, fused unless it is 0)
+void set_fmha_bwd_deterministic(int on);
 
 }  // namespace rp

@@ -160,12 +160,17 @@ class TrainStep:
     models/MMCTransformer.py:159-179) — torch's Adam skips such parameters, and so does this step."""
 
     def __init__(self, model, lr=1e-3, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, group=None, dropout=0.1,
-                 seed=0):
+                 seed=0, deterministic=None):
         """dropout: the p of every nn.Dropout of the reference graph (0.1 there; 0 = the eval-mode graph);
         seed: base of the dropout streams (use a different one per data-parallel rank, as torch's per-process
-        generators are)"""
+        generators are);
+        deterministic: True = bit-reproducible gradients (the attention backward runs its two deterministic kernels,
+        about 20 % slower), False = the fused attention backward whose dQ is summed by fp32 adds in L2 in no fixed order,
+        None = leave the process-wide setting (rp_set_attn_bwd_deterministic / RP_FMHA_BWD_FUSED) as it is"""
         if not 0.0 <= dropout < 1.0:
             raise ValueError("TrainStep: 0 <= dropout < 1")
+        if deterministic is not None:
+            check(_lib.load().rp_set_attn_bwd_deterministic(1 if deterministic else 0), "rp_set_attn_bwd_deterministic")
         self.p, self.seed, self.step_index = float(dropout), int(seed), 0
         self.model = model
         self.cfg = c = model._cfg

@@ -326,10 +326,21 @@ def test_train_step_gradients_with_dropout(layers, lens):
     for l2, cos, amp, name in rows:
         assert cos >= 0.99, (name, cos)
         assert l2 <= max(2e-2, 1.3 * amp), (name, l2, amp)
-    # the same step index draws the same masks (bit-identical gradients); the next one draws new ones
+    # the same step index draws the same masks: gradients equal to the rounding of the fused attention backward's dQ sums
+    # (fp32 adds in L2, no fixed order) — and bit-identical with the deterministic kernels; the next index draws new masks
     g1 = ts.opt.grad.clone()
     ts.loss_and_grads(batch, batch_size=B)
-    assert torch.equal(g1, ts.opt.grad)
+    assert float((g1 - ts.opt.grad).norm() / g1.norm()) < 1e-3
+    from repurpose_b200 import _lib
+    lib = _lib.load()
+    try:
+        _lib.check(lib.rp_set_attn_bwd_deterministic(1), "rp_set_attn_bwd_deterministic")
+        ts.loss_and_grads(batch, batch_size=B)
+        g1 = ts.opt.grad.clone()
+        ts.loss_and_grads(batch, batch_size=B)
+        assert torch.equal(g1, ts.opt.grad)
+    finally:
+        _lib.check(lib.rp_set_attn_bwd_deterministic(-1), "rp_set_attn_bwd_deterministic")
     m0 = ts.keep_mask(ts.site("ffn", 0), (B, max(lens), 2048)).clone()
     ts.step_index += 1
     m1 = ts.keep_mask(ts.site("ffn", 0), (B, max(lens), 2048))

@@ -139,9 +139,19 @@ def _attention_case(B, T, lens, seed):
     return H, D, qkv.bfloat16(), qs.bfloat16(), d_o, lens_t
 
 
+@pytest.fixture(params=["fused", "deterministic"])
+def attn_bwd_mode(request):
+    """both attention-backward paths: the fused kernel (dQ summed by TMA reduce adds in L2, the default) and the two
+    deterministic kernels (rp_set_attn_bwd_deterministic)"""
+    L, lib = _lib()
+    L.check(lib.rp_set_attn_bwd_deterministic(1 if request.param == "deterministic" else 0), "set mode")
+    yield request.param
+    L.check(lib.rp_set_attn_bwd_deterministic(-1), "set mode")
+
+
 @pytest.mark.parametrize("B,T,lens", [(1, 128, [128]), (2, 200, [200, 77]), (2, 333, [333, 129]), (1, 700, [641]),
                                       (3, 1801, [1801, 1211, 64])])
-def test_fmha_backward_matches_autograd(B, T, lens):
+def test_fmha_backward_matches_autograd(B, T, lens, attn_bwd_mode):
     L, lib = _lib()
     H, D, qkv, qs, d_o, lens_t = _attention_case(B, T, lens, 17 * T + B)
     o = torch.empty(B, T, D, dtype=torch.bfloat16, device=DEV)
@@ -174,6 +184,48 @@ def test_fmha_backward_matches_autograd(B, T, lens):
         assert err < 3e-2, (name, err)
     for b, n in enumerate(lens):   # padded keys receive exactly zero gradient
         assert (dqkv[b, n:, D:].float() == 0).all()
+    # a second launch: bit-identical with the deterministic kernels; with the fused kernel dK / dV are, and dQ agrees to
+    # the rounding of its fp32 sums over the key tiles (their order in L2 is not fixed)
+    again = torch.full_like(dqkv, float("nan"))
+    L.check(lib.rp_fmha_bwd(L.ptr(qs), L.ptr(qs) + 2 * D, L.ptr(qs) + 4 * D, L.ptr(o), L.ptr(d_o), L.ptr(lse), L.ptr(dsum),
+                            L.ptr(again), L.ptr(again) + 2 * D, L.ptr(again) + 4 * D, 3 * D, D, 3 * D, B, H, T, L.ptr(lens_t),
+                            L.cur_stream()), "fmha_bwd")
+    torch.cuda.synchronize()
+    assert torch.equal(again[..., D:], dqkv[..., D:])
+    if attn_bwd_mode == "deterministic":
+        assert torch.equal(again, dqkv)
+    else:
+        assert _rel(again[..., :D], dqkv[..., :D]) < 1e-2
+
+
+def test_fmha_backward_fused_agrees_with_the_deterministic_kernels():
+    """same inputs through both paths: dK and dV bit-identical (the same bf16 dSt^T / P^T tiles feed the same MMAs), dQ equal
+    up to the bf16 rounding of differently ordered fp32 sums"""
+    L, lib = _lib()
+    B, T, lens = 2, 1801, [1801, 700]
+    H, D, qkv, qs, d_o, lens_t = _attention_case(B, T, lens, 5)
+    o = torch.empty(B, T, D, dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(B, H, T, device=DEV)
+    L.check(lib.rp_fmha_train(L.ptr(qs), L.ptr(qs) + 2 * D, L.ptr(qs) + 4 * D, L.ptr(o), 3 * D, D, B, H, T, L.ptr(lens_t),
+                              L.ptr(lse), L.cur_stream()), "fmha_train")
+    out = {}
+    try:
+        for mode in (0, 1):
+            L.check(lib.rp_set_attn_bwd_deterministic(mode), "set mode")
+            dqkv = torch.full((B, T, 3 * D), float("nan"), dtype=torch.bfloat16, device=DEV)
+            dsum = torch.empty(B, H, T, device=DEV)
+            L.check(lib.rp_fmha_bwd(L.ptr(qs), L.ptr(qs) + 2 * D, L.ptr(qs) + 4 * D, L.ptr(o), L.ptr(d_o), L.ptr(lse),
+                                    L.ptr(dsum), L.ptr(dqkv), L.ptr(dqkv) + 2 * D, L.ptr(dqkv) + 4 * D, 3 * D, D, 3 * D, B, H, T,
+                                    L.ptr(lens_t), L.cur_stream()), "fmha_bwd")
+            torch.cuda.synchronize()
+            out[mode] = dqkv
+    finally:
+        L.check(lib.rp_set_attn_bwd_deterministic(-1), "set mode")
+    assert not torch.isnan(out[0].float()).any()
+    assert torch.equal(out[0][..., D:], out[1][..., D:])
+    err = _rel(out[0][..., :D], out[1][..., :D])
+    print("dQ fused vs deterministic: relative error", err)
+    assert err < 1e-2
 
 
 def test_gemm_wgrad_refuses_an_empty_split():

@@ -71,10 +71,21 @@ def test_gradients_match_autograd_of_the_reference_graph(layers, lens):
     _, amp_grads = _autograd_reference(sd, batch, B, autocast=True)
     assert abs(float(loss) - float(ref_loss)) <= 2e-2 * abs(float(ref_loss)), (float(loss), float(ref_loss))
     _check_grads(ts, ref_grads, amp_grads)
-    # deterministic: a second pass over the same batch gives bit-identical gradients
+    # a second pass over the same batch: gradients equal to the rounding of the fused attention backward's dQ sums (fp32 adds
+    # in L2, no fixed order), and bit-identical with TrainStep(deterministic=True)
     g1 = ts.opt.grad.clone()
     ts.loss_and_grads(batch, batch_size=B)
-    assert torch.equal(g1, ts.opt.grad)
+    assert float((g1 - ts.opt.grad).norm() / g1.norm()) < 1e-3
+    from repurpose_b200 import _lib
+    try:
+        td = TrainStep(model, lr=1e-3, dropout=0.0, deterministic=True)
+        td.loss_and_grads(batch, batch_size=B)
+        g1 = td.opt.grad.clone()
+        td.loss_and_grads(batch, batch_size=B)
+        assert torch.equal(g1, td.opt.grad)
+        _check_grads(td, ref_grads, amp_grads)
+    finally:
+        _lib.check(_lib.load().rp_set_attn_bwd_deterministic(-1), "rp_set_attn_bwd_deterministic")
 
 
 def test_gradients_match_the_staged_reference_module():
