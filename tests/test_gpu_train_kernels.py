@@ -198,6 +198,26 @@ def test_fmha_backward_matches_autograd(B, T, lens, attn_bwd_mode):
         assert _rel(again[..., :D], dqkv[..., :D]) < 1e-2
 
 
+def test_fmha_backward_of_a_video_without_keys(attn_bwd_mode):
+    """kv_len = 0 (a slot of a fixed-shape batch that holds no video): the forward writes lse = +inf and O = 0, the backward
+    exact zeros for that batch element — in both modes, and without touching its neighbour"""
+    L, lib = _lib()
+    B, T, lens = 2, 200, [200, 0]
+    H, D, qkv, qs, d_o, lens_t = _attention_case(B, T, lens, 23)
+    o = torch.full((B, T, D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(B, H, T, device=DEV)
+    L.check(lib.rp_fmha_train(L.ptr(qs), L.ptr(qs) + 2 * D, L.ptr(qs) + 4 * D, L.ptr(o), 3 * D, D, B, H, T, L.ptr(lens_t),
+                              L.ptr(lse), L.cur_stream()), "fmha_train")
+    dqkv = torch.full((B, T, 3 * D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    dsum = torch.empty(B, H, T, device=DEV)
+    L.check(lib.rp_fmha_bwd(L.ptr(qs), L.ptr(qs) + 2 * D, L.ptr(qs) + 4 * D, L.ptr(o), L.ptr(d_o), L.ptr(lse), L.ptr(dsum),
+                            L.ptr(dqkv), L.ptr(dqkv) + 2 * D, L.ptr(dqkv) + 4 * D, 3 * D, D, 3 * D, B, H, T, L.ptr(lens_t),
+                            L.cur_stream()), "fmha_bwd")
+    torch.cuda.synchronize()
+    assert (o[1].float() == 0).all() and (dqkv[1].float() == 0).all()
+    assert not torch.isnan(dqkv[0].float()).any() and float(dqkv[0].float().abs().max()) > 0
+
+
 def test_fmha_backward_fused_agrees_with_the_deterministic_kernels():
     """same inputs through both paths: dK and dV bit-identical (the same bf16 dSt^T / P^T tiles feed the same MMAs), dQ equal
     up to the bf16 rounding of differently ordered fp32 sums"""
