@@ -586,9 +586,9 @@ constexpr int KV_BYTES = KT * HD * 2, Q_BYTES = QT * HD * 2, DQ_BYTES = QT * HD 
 constexpr int SMEM_K = 0, SMEM_V = KV_BYTES, SMEM_RING = 2 * KV_BYTES;  // stage s: Q_i at +2 s Q_BYTES, dO_i after it
 constexpr int SMEM_DST = SMEM_RING + STAGES * 2 * Q_BYTES;              // [2 buffers] dSt^T tiles (16 KB each)
 constexpr int SMEM_DQ = SMEM_DST + 2 * KV_BYTES;                        // [2 buffers] fp32 dQ partial tiles (16 KB each)
-constexpr int SMEM_STAT = SMEM_DQ + 2 * DQ_BYTES;                       // [2 buffers][lse 64 | dsum 64] floats
-constexpr int SMEM_DROP = SMEM_STAT + 2 * 128 * 4;                      // [2 buffers][64 queries][4 words] keep bits
-constexpr int SMEM_BAR = SMEM_DROP + 2 * 64 * 4 * 4;
+constexpr int SMEM_STAT = SMEM_DQ + 2 * DQ_BYTES;                       // [8 warps][2 buffers][lse 32 | dsum 32] floats
+constexpr int SMEM_DROP = SMEM_STAT + 8 * 128 * 4;                      // [8 warps][2 buffers][32 queries] keep-bit words
+constexpr int SMEM_BAR = SMEM_DROP + 8 * 64 * 4;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;
 static_assert(SMEM_DST % 1024 == 0 && SMEM_DQ % 1024 == 0 && SMEM_DST >= KV_BYTES, "swizzled tiles are 1024-byte aligned");
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
@@ -791,35 +791,34 @@ fmha_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int row = wq * 32 + lane;
     const bool kvalid = k_start + row < kv_len;
     const uint32_t t_lane = tmem + (uint32_t(wq * 32) << 16);
-    const int tid = threadIdx.x;  // 0..255; threads 0..127 also fetch the tiles' statistics / keep bits
     const int64_t stat_base = (int64_t(b) * p.H + head) * p.T;
-    auto fetch_stat = [&](int i) {
-      const int qi = i * QT + (tid & 63);
-      if (tid < 64) return qi < p.T ? p.lse[stat_base + qi] : INFINITY;
-      return qi < p.T ? p.dsum[stat_base + qi] : 0.0f;
+    // No barrier ties the eight warps together: each one stages the statistics (and keep bits) of ITS 32 query columns in
+    // its own shared-memory rows, one tile ahead (lane l fetches column l; every lane then reads them as broadcasts)
+    float* wst = stat + warp * 128;  // [2 buffers][lse 32 | Dsum 32]
+    // DROP: word 4 kb + wq of a query's keep bits holds this warp's 32 keys; bit `lane` is this thread's key
+    uint32_t* wbits = reinterpret_cast<uint32_t*>(smem + SMEM_DROP) + warp * 64;  // [2 buffers][32 queries]
+    float l_n = INFINITY, d_n = 0.0f;
+    uint32_t b_n = 0u;
+    auto fetch = [&](int i) {
+      const int qi = i * QT + 32 * half + lane;
+      const bool in = qi < p.T;
+      l_n = in ? p.lse[stat_base + qi] : INFINITY;
+      d_n = in ? p.dsum[stat_base + qi] : 0.0f;
+      if constexpr (DROP) b_n = in ? __ldg(p.drop_bits + (stat_base + qi) * p.drop_ld + 4 * kb + wq) : 0u;
     };
-    uint32_t* dbits = reinterpret_cast<uint32_t*>(smem + SMEM_DROP);
-    auto fetch_bits = [&](int i) {
-      const int qi = i * QT + (tid >> 1);
-      if (qi >= p.T) return make_uint2(0u, 0u);
-      return __ldg(reinterpret_cast<const uint2*>(p.drop_bits + (stat_base + qi) * p.drop_ld + 4 * kb + 2 * (tid & 1)));
+    auto stage = [&](int bf) {
+      wst[64 * bf + lane] = l_n;
+      wst[64 * bf + 32 + lane] = d_n;
+      if constexpr (DROP) wbits[32 * bf + lane] = b_n;
+      __syncwarp();
     };
-    const bool fetcher = tid < 128;
-    if (fetcher) {
-      stat[tid] = fetch_stat(0);
-      if constexpr (DROP) reinterpret_cast<uint2*>(dbits)[tid] = fetch_bits(0);
-    }
+    fetch(0);
+    stage(0);
     for (int i = 0; i < n_q; ++i) {
       const int bf = i & 1;
-      float nxt = 0.0f;
-      uint2 nxt_bits = make_uint2(0u, 0u);
-      if (fetcher && i + 1 < n_q) {
-        nxt = fetch_stat(i + 1);
-        if constexpr (DROP) nxt_bits = fetch_bits(i + 1);
-      }
-      named_bar_sync(1, 256);  // buffer bf is complete (written at the end of the previous iteration)
-      const float4* lse4 = reinterpret_cast<const float4*>(stat + 128 * bf);
-      const float4* ds4 = reinterpret_cast<const float4*>(stat + 128 * bf + 64);
+      if (i + 1 < n_q) fetch(i + 1);  // in flight over the whole tile
+      const float4* lse4 = reinterpret_cast<const float4*>(wst + 64 * bf);
+      const float4* ds4 = reinterpret_cast<const float4*>(wst + 64 * bf + 32);
       mbar_wait(st_full(bf), uint32_t(i >> 1) & 1u);
       tc_fence_after();
       {
@@ -834,8 +833,8 @@ fmha_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          const float4 l4 = lse4[8 * half + g];
-          const float4 d4 = ds4[8 * half + g];
+          const float4 l4 = lse4[g];
+          const float4 d4 = ds4[g];
           const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq_[4] = {d4.x, d4.y, d4.z, d4.w};
           float pr[4], dsv[4];
 #pragma unroll
@@ -843,7 +842,7 @@ fmha_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             pr[e] = kvalid ? ex2_approx(__uint_as_float(s[4 * g + e]) - lq[e]) : 0.0f;
             float dpv = __uint_as_float(dp[4 * g + e]);
             if constexpr (DROP) {
-              const bool keep = (dbits[(bf * 64 + 32 * half + 4 * g + e) * 4 + wq] >> lane) & 1u;
+              const bool keep = (wbits[32 * bf + 4 * g + e] >> lane) & 1u;
               dpv = keep ? dpv * p.drop_scale : 0.0f;
               dsv[e] = pr[e] * (dpv - dq_[e]) * LN2;
               pr[e] = keep ? pr[e] * p.drop_scale : 0.0f;  // P_d^T feeds dV
@@ -871,10 +870,7 @@ fmha_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready(bf));
-      if (fetcher) {
-        stat[128 * (bf ^ 1) + tid] = nxt;
-        if constexpr (DROP) reinterpret_cast<uint2*>(dbits)[128 * (bf ^ 1) + tid] = nxt_bits;
-      }
+      if (i + 1 < n_q) stage(bf ^ 1);
     }
     // ---- epilogue: dV (warps 0-3), dK (warps 4-7) -> bf16 -> swizzled smem (the K / V tiles' slots) -> TMA stores
     mbar_wait(p_free((n_q - 1) & 1), uint32_t((n_q - 1) >> 1) & 1u);  // (MMAs retire in order: the last commit covers all)
