@@ -817,8 +817,16 @@ fmha_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int i = 0; i < n_q; ++i) {
       const int bf = i & 1;
       if (i + 1 < n_q) fetch(i + 1);  // in flight over the whole tile
+      // the tile's statistics are read BEFORE the barrier wait and the TMEM loads (which are compiler barriers): their
+      // shared-memory latency then overlaps both instead of following them
       const float4* lse4 = reinterpret_cast<const float4*>(wst + 64 * bf);
       const float4* ds4 = reinterpret_cast<const float4*>(wst + 64 * bf + 32);
+      float4 lpre[8], dpre[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        lpre[g] = lse4[g];
+        dpre[g] = ds4[g];
+      }
       mbar_wait(st_full(bf), uint32_t(i >> 1) & 1u);
       tc_fence_after();
       {
@@ -833,8 +841,8 @@ fmha_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          const float4 l4 = lse4[g];
-          const float4 d4 = ds4[g];
+          const float4 l4 = lpre[g];
+          const float4 d4 = dpre[g];
           const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq_[4] = {d4.x, d4.y, d4.z, d4.w};
           float pr[4], dsv[4];
 #pragma unroll
