@@ -745,8 +745,12 @@ fmha_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tc_commit(st_full(bf));
       }
       __syncwarp();
-      if (i > 0) issue_grads(i - 1);
+      // the gradient MMAs of tile i - 2, not i - 1: S^T / dP^T of tile i then sit in the tensor-core queue AHEAD of them and
+      // are complete long before the softmax warps finish tile i - 1 (issued behind the gradient MMAs of tile i - 1 they
+      // arrived when the softmax warps already waited: 17 % of their samples, profiles/r02_notes.md 8)
+      if (i > 1) issue_grads(i - 2);
     }
+    if (n_q > 1) issue_grads(n_q - 2);
     issue_grads(n_q - 1);
   } else if (warp >= DRAIN0) {
     // ------------------------------------------------------------------ dQ drain: TMEM lanes 64-127 -> fp32 staging tile
