@@ -225,7 +225,9 @@ int32_t rp_fmha_bwd(const void* q, const void* k, const void* v, const void* o, 
  * fp32 adds in L2 whose order is not fixed, so dq is reproducible to the rounding of a T/128-term fp32 sum, not bit for bit
  * (torch's own attention backward makes the same trade unless torch.use_deterministic_algorithms is set).  on = 1 selects
  * the two deterministic kernels (about 20 % slower), on = 0 the fused one, on < 0 the default (environment
- * RP_FMHA_BWD_FUSED, fused unless it is 0).  Process-wide. */
+ * RP_FMHA_BWD_FUSED, fused unless it is 0).  Process-wide.  The fused path keeps one fp32 dQ accumulator per device
+ * (B * H * ceil(T/64) * 16 KB, allocated on first use and grown on demand): calls on the SAME device must be ordered on
+ * one stream (as a training step's are); the deterministic kernels have no such state. */
 int32_t rp_set_attn_bwd_deterministic(int32_t on);
 
 /* ---- train-mode dropout (the nn.Dropout(0.1) sites of the reference graph under model.train(), main.py:285:
