@@ -164,10 +164,11 @@ struct Workspace {
   __nv_bfloat16* ffn;   // [M,d_ff]   }
   int32_t* row_blocks;  // RowMap: [ceil(M/256)] valid 256-row blocks + their count (padding-only blocks are skipped)
   int32_t* row_count;
+  int32_t* batch_order;  // [B] batch elements by decreasing length (the attention kernel's CTA layout)
   int64_t bytes;
 };
 
-Workspace carve(const rp_model_cfg& c, int64_t M, void* base) {
+Workspace carve(const rp_model_cfg& c, int64_t M, int64_t B, void* base) {
   Workspace w;
   const int64_t D = c.d_model;
   const int64_t Cin = int64_t(c.vis_dim) + c.aud_dim + c.text_dim;
@@ -184,6 +185,7 @@ Workspace carve(const rp_model_cfg& c, int64_t M, void* base) {
   if (wide < M * Cin * 2) wide = M * Cin * 2;
   const int64_t o_q = take(wide);
   const int64_t o_m = take(((M + 255) / 256 + 1) * 4);
+  const int64_t o_b = take(B * 4);
   uint8_t* b = reinterpret_cast<uint8_t*>(base);
   w.h = reinterpret_cast<float*>(b + o_h);
   w.u = reinterpret_cast<__nv_bfloat16*>(b + o_u);
@@ -192,6 +194,7 @@ Workspace carve(const rp_model_cfg& c, int64_t M, void* base) {
   w.ffn = w.qkv + M * 3 * D;
   w.row_count = reinterpret_cast<int32_t*>(b + o_m);
   w.row_blocks = w.row_count + 1;
+  w.batch_order = reinterpret_cast<int32_t*>(b + o_b);
   w.bytes = off;
   return w;
 }
@@ -291,7 +294,7 @@ int32_t rp_weights_complete(const rp_handle* h) {
 
 int64_t rp_workspace_bytes(const rp_handle* h, int32_t B, int32_t T) {
   if (h == nullptr || B <= 0 || T <= 0) return -1;
-  return carve(h->cfg, int64_t(B) * T, nullptr).bytes;
+  return carve(h->cfg, int64_t(B) * T, B, nullptr).bytes;
 }
 
 // Ragged input description (rp_forward_ragged); all null for the padded entry point.
@@ -321,7 +324,7 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
   const int64_t M64 = int64_t(B) * T;
   RP_CHECK(M64 < (int64_t(1) << 31), "rp_forward: B*T too large");
   const int M = int(M64);
-  Workspace w = carve(c, M, workspace);
+  Workspace w = carve(c, M, B, workspace);
   if (w.bytes > workspace_bytes) {
     set_last_error("rp_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes,
                    (long long)w.bytes);
@@ -354,8 +357,10 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
   const bool skip = h->skip_padding && M > 128;
   RowMap rmap{w.row_blocks, w.row_count};
   const RowMap* rows = skip ? &rmap : nullptr;
-  if (skip) {
-    rc = launch_row_map(lens, B, T, w.row_blocks, w.row_count, st);
+  // (the same tiny kernel ranks the videos by length for the attention kernel's CTA layout: useful with or without the skip)
+  const bool ranked = skip || B > 1;
+  if (ranked) {
+    rc = launch_row_map(lens, B, T, w.row_blocks, w.row_count, w.batch_order, st);
     if (rc) return rc;
   }
   // (1) concat + cast, input projection (fp32 out), input_norm + PE -> h, layers[0].norm1 -> u
@@ -388,6 +393,7 @@ static int32_t forward_core(rp_handle* h, const void* vis_v, const void* aud_v, 
     fa.ldq = fa.ldk = fa.ldv = 3 * D; fa.ldo = D;
     fa.bsq = fa.bsk = fa.bsv = int64_t(T) * 3 * D; fa.bso = int64_t(T) * D;
     fa.B = B; fa.H = H; fa.Tq = T; fa.Tk = T; fa.kv_lens = lens; fa.mask_mode = 0; fa.skip_padded_queries = skip;
+    fa.batch_order = ranked ? w.batch_order : nullptr;
     RUN(RP_TAG_FMHA, launch_fmha(fa, st));
     if (ln_in_gemm) {
       // The LayerNorm that follows each residual update runs inside the GEMM epilogue (clusters of

@@ -122,6 +122,7 @@ struct FmhaParams {
   const uint32_t* drop_bits;
   int64_t drop_ld;
   float drop_scale;
+  const int32_t* batch_order;  // optional [B]: block index -> batch element (longest first)
 };
 
 // ---- packed f32x2 helpers (sm_100 FFMA2/FADD2) ---------------------------------------------------
@@ -220,7 +221,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     bh = int(blockIdx.x) - n_lead;
   }
   const int head = bh % p.H;
-  const int b = bh / p.H;
+  const int b = p.batch_order != nullptr ? p.batch_order[bh / p.H] : bh / p.H;
 
   const int q_start0 = qb * (NQ * QT);
   const bool q1_active = NQ == 2 && (q_start0 + QT) < p.Tq;
@@ -768,7 +769,7 @@ int launch_fmha(const FmhaArgs& a, cudaStream_t stream) {
 
   FmhaParams p{a.B, a.H, a.Tq, a.Tk, a.kv_lens, a.mask, a.mask_b_stride, a.mask_q_stride, a.lse,
                (a.skip_padded_queries && a.kv_lens != nullptr && a.Tq == a.Tk) ? 1 : 0,
-               a.drop_bits, a.drop_ld, a.drop_scale};
+               a.drop_bits, a.drop_ld, a.drop_scale, a.batch_order};
   if (a.drop_bits != nullptr) {
     RP_CHECK(a.mask_mode == 0, "fmha: attention-weight dropout is built for the key-padding mode");
     RP_CHECK(a.drop_ld % 4 == 0 && a.drop_ld * 32 >= ((int64_t(a.Tk) + KT - 1) / KT) * KT &&

@@ -87,6 +87,9 @@ struct FmhaArgs {
   const uint32_t* drop_bits = nullptr;
   int64_t drop_ld = 0;
   float drop_scale = 1.0f;
+  // optional [B] permutation of the batch indices (device): CTAs are laid out over batch_order[0], batch_order[1], ... —
+  // longest videos first (launch_row_map), so that the short CTAs of a ragged batch fill the end of the launch
+  const int32_t* batch_order = nullptr;
 };
 int launch_fmha(const FmhaArgs& a, cudaStream_t stream);
 // keep bits of one attention-dropout site: n_words words, word w covers elements 32 w .. 32 w + 31 of the site
@@ -110,7 +113,7 @@ int launch_mask_lens(const uint8_t* mask, int B, int T, int32_t* lens, int32_t* 
 // blocks / count of the RowMap of a padded [B, T] batch: block m (rows 256 m .. 256 m + 255 of the flattened [B*T]
 // matrix) is valid iff it holds a row (b, t) with t < min(T, round_up(lens[b], 128)) — every row an attention key tile
 // of a valid query can touch is computed, whole-padding blocks are not
-int launch_row_map(const int32_t* lens, int B, int T, int32_t* blocks, int32_t* count, cudaStream_t stream);
+int launch_row_map(const int32_t* lens, int B, int T, int32_t* blocks, int32_t* count, int32_t* order, cudaStream_t stream);
 // zero the rows t >= lens[b] of the three forward outputs (padded steps carry no information; with block skipping
 // they would otherwise hold whatever the buffers held before)
 int launch_zero_padded_rows(float* logits, float* offsets, float* feats, const int32_t* lens, int B, int T, int D,

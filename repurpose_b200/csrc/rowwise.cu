@@ -313,7 +313,21 @@ head_out_kernel(const __nv_bfloat16* __restrict__ ac, const __nv_bfloat16* __res
 // RowMap of a padded batch (kernels.h): one block; flags per 256-row block, then an ordered compaction by warp 0
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-row_map_kernel(const int32_t* __restrict__ lens, int B, int T, int32_t* __restrict__ blocks, int32_t* __restrict__ count) {
+row_map_kernel(const int32_t* __restrict__ lens, int B, int T, int32_t* __restrict__ blocks, int32_t* __restrict__ count,
+               int32_t* __restrict__ order) {
+  // order[r] = the batch element with the r-th longest video (ties by index): the attention kernel lays its CTAs out
+  // longest video first, so the short CTAs of a ragged batch end the launch instead of a long one starting last
+  if (order != nullptr) {
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+      const int li = lens[i];
+      int rank = 0;
+      for (int j = 0; j < B; ++j) {
+        const int lj = lens[j];
+        rank += (lj > li || (lj == li && j < i)) ? 1 : 0;
+      }
+      order[rank] = i;
+    }
+  }
   const int64_t M = int64_t(B) * T;
   const int nblk = int((M + 255) / 256);
   // pass 1: flag[m] kept in `blocks` itself (0 / 1)
@@ -453,9 +467,9 @@ int launch_mask_lens(const uint8_t* mask, int B, int T, int32_t* lens, int32_t* 
   return RP_OK;
 }
 
-int launch_row_map(const int32_t* lens, int B, int T, int32_t* blocks, int32_t* count, cudaStream_t stream) {
+int launch_row_map(const int32_t* lens, int B, int T, int32_t* blocks, int32_t* count, int32_t* order, cudaStream_t stream) {
   RP_CHECK(B > 0 && T > 0 && lens && blocks && count, "row_map: bad arguments");
-  row_map_kernel<<<1, 256, 0, stream>>>(lens, B, T, blocks, count);
+  row_map_kernel<<<1, 256, 0, stream>>>(lens, B, T, blocks, count, order);
   count_launch();
   RP_CUDA_CHECK(cudaGetLastError());
   return RP_OK;
