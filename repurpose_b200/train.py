@@ -186,6 +186,18 @@ class TrainStep:
         self._frozen16 = {n: p.data.to(torch.bfloat16) for n, p in named if n.startswith("reg_head.") and p.dim() == 2}
         self._frozen32 = {n: p.data for n, p in named if n.startswith("reg_head.")}
         self.group = group
+        # bucketed, overlapped gradient all-reduce (what DDP's buckets do, utils/distributed.py:415-428): the flat buffer is in
+        # parameter order and the backward pass fills it from the end, so once the backward of layer l is through, everything
+        # from that layer's first parameter to the end of the (not yet reduced) buffer is final and can travel while the
+        # earlier layers still compute.  Cuts every four layers; the head of the buffer goes last, in step().
+        self.overlap_allreduce = True
+        self._layer_start = {}
+        for n, i in self._index.items():
+            if n.startswith("multimodal_encoder.layers."):
+                l = int(n.split(".")[2])
+                pos = self.opt._slices[i][0]
+                self._layer_start[l] = min(self._layer_start.get(l, pos), pos)
+        self._ar_pending, self._ar_hi = [], None
         self.lib = _lib.load()
         self._bufs = None
         self._scratch = torch.empty(int(self.lib.rp_train_scratch_bytes()), dtype=torch.uint8, device=self.dev)
@@ -490,8 +502,22 @@ class TrainStep:
         return masks, d["logits"], d["offsets"], batch.get("labels"), batch.get("segments"), d["feats"]
 
     # ---- backward ----------------------------------------------------------------------------------------------------
-    def backward(self, dlogits):
-        """gradients of every trainable parameter into the flat gradient buffer, given d loss / d logits [B,T,1]"""
+    def _reduce_tail_async(self, lo):
+        """start the all-reduce of grad[lo : end of the not yet reduced part] (NCCL's own stream; it waits for the kernels
+        enqueued so far on the current stream and runs beside the ones enqueued after)"""
+        hi = self._ar_hi
+        if hi is None or lo >= hi:
+            return
+        with self._timed("allreduce"):
+            self._ar_pending.append(dist.all_reduce(self.opt.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
+                                                    async_op=True))
+        self._ar_hi = lo
+
+    def backward(self, dlogits, overlap_allreduce=False):
+        """gradients of every trainable parameter into the flat gradient buffer, given d loss / d logits [B,T,1];
+        overlap_allreduce (step() sets it under a multi-rank NCCL group): finished tails of the buffer are all-reduced
+        while the earlier layers' backward still runs — the caller must finish with _finish_allreduce()"""
+        self._ar_pending, self._ar_hi = [], (self.opt.grad.numel() if overlap_allreduce else None)
         c, lib, d = self.cfg, self.lib, self._bufs
         B, T = d["shape"]
         M, L, H = B * T, c["num_layers"], c["num_heads"]
@@ -555,25 +581,43 @@ class TrainStep:
                 self._ln_bwd(d["h"][l], du, p + "norm1.", dh, dh16, accumulate=True,  # dh = d h[l]; dh16 = dY of layer l-1's linear2
                              bias_grad=(lay.format(l - 1) + "linear2.bias") if l > 0 else None,
                              site=self.site("drop2", l - 1) if l > 0 else None)
+                if overlap_allreduce and l > 0 and l % 4 == 0:
+                    self._reduce_tail_async(self._layer_start[l])
             # h0 = LayerNorm(x W_in^T + b_in) + PE
             self._ln_bwd(d["xproj"], dh, "input_norm.", du, dh16, accumulate=False, bias_grad="input_projection.bias")
             self._wgrad(dh16, d["xcat"], "input_projection.")
 
     # ---- one iteration ------------------------------------------------------------------------------------------------
-    def loss_and_grads(self, batch, batch_size=None):
+    def loss_and_grads(self, batch, batch_size=None, _overlap_allreduce=False):
         """forward + loss + backward (no parameter update): -> cls_loss / batch_size as a device scalar"""
         out = self.forward(batch)
         masks, logits, _, labels, _, _ = out
         bs = int(batch_size if batch_size is not None else logits.shape[0])
         loss = self.model.losses(*out)["cls_loss"] / bs
         dlogits = focal_loss_grad(masks, logits, labels, batch_size=bs)
-        self.backward(dlogits)
+        self.backward(dlogits, overlap_allreduce=_overlap_allreduce)
         return loss
 
+    def _multi_rank_nccl(self):
+        return (dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+                and dist.get_backend(self.group) == "nccl")
+
+    def _finish_allreduce(self):
+        """the head of the buffer, then wait for every bucket and average"""
+        self._reduce_tail_async(0)
+        for w in self._ar_pending:
+            w.wait()
+        self._ar_pending, self._ar_hi = [], None
+        self.opt.grad.div_(dist.get_world_size(self.group))
+
     def step(self, batch, batch_size=None):
-        loss = self.loss_and_grads(batch, batch_size)
+        overlap = self.overlap_allreduce and self._multi_rank_nccl()
+        loss = self.loss_and_grads(batch, batch_size, _overlap_allreduce=overlap)
         with self._timed("allreduce"):
-            allreduce_flat_(self.opt.grad, self.group)
+            if overlap:
+                self._finish_allreduce()
+            else:
+                allreduce_flat_(self.opt.grad, self.group)
         with self._timed("adam_and_recast"):
             self.opt.step()
             self.refresh_weights()
