@@ -62,7 +62,7 @@ def run_train_bench(B, T, steps, warmup=2, rank=0, world=1, dev=None, dropout=0.
             "loss_first_last": [losses[0], losses[-1]], "kernel_classes_ms": prof,
             "activation_gb": 16 * B * T * 14.3e3 / 1e9,
             "dropout": dropout,
-            "what": "forward (activations kept) + masked focal loss + backward + one flat gradient all-reduce + Adam; "
+            "what": "forward (activations kept) + masked focal loss + backward with the flat gradient buffer all-reduced in buckets underneath + Adam; "
                     + ("train mode: nn.Dropout(%.2f) at every site of the reference graph (counter-based masks)" % dropout
                        if dropout > 0 else "dropout off (the eval-mode graph)")}
 
