@@ -849,12 +849,17 @@ fmha_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const float4 d4 = dpre[g];
           const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq_[4] = {d4.x, d4.y, d4.z, d4.w};
           float pr[4], dsv[4];
+          uint32_t kw[4] = {0u, 0u, 0u, 0u};  // DROP: the keep-bit words of these four query columns (one 16-byte load)
+          if constexpr (DROP) {
+            const uint4 w4 = reinterpret_cast<const uint4*>(wbits + 32 * bf)[g];
+            kw[0] = w4.x; kw[1] = w4.y; kw[2] = w4.z; kw[3] = w4.w;
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             pr[e] = kvalid ? ex2_approx(__uint_as_float(s[4 * g + e]) - lq[e]) : 0.0f;
             float dpv = __uint_as_float(dp[4 * g + e]);
             if constexpr (DROP) {
-              const bool keep = (wbits[32 * bf + 4 * g + e] >> lane) & 1u;
+              const bool keep = (kw[e] >> lane) & 1u;
               dpv = keep ? dpv * p.drop_scale : 0.0f;
               dsv[e] = pr[e] * (dpv - dq_[e]) * LN2;
               pr[e] = keep ? pr[e] * p.drop_scale : 0.0f;  // P_d^T feeds dV
