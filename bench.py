@@ -299,7 +299,7 @@ def run_ours(args, rank, world, local_rank):
     # DRAM bytes per FMHA launch at this shape from the committed `ncu --set full` capture
     # (profiles/r01_prof_fmha_final_summary.txt: 177.1 MB read + 42.0 MB written; algorithmic
     # 177 MB qkv in + 59 MB o out) — only valid for the default B=32, T=1801 workload
-    fmha_traffic = 220.34e6 if (BATCH, SEQ) == (32, 1801) else None
+    fmha_traffic = 232.66e6 if (BATCH, SEQ) == (32, 1801) else None  # ncu dram__bytes_read + write per launch (profiles/r02_notes.md 9)
     roofline = {"kernel": "fmha_fwd_kernel<mask=0,emu=1,nq=1>", "bound": "tensor",
                 "algorithmic": "4*B*H*T^2*64 FLOP per launch (SURVEY.md 8d: 32,768*T^2 per video over 16 layers), padded rows/keys excluded",
                 "achieved": fm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",

@@ -89,6 +89,9 @@ struct Cfg {
   static constexpr int SOFTMAX_REGS = NQ == 2 ? 232 : 216;
   static constexpr int AUX_REGS = 40;
 };
+#ifndef RP_FMHA_TAIL_DEFER
+#define RP_FMHA_TAIL_DEFER 96
+#endif
 #ifndef RP_FMHA_CHUNK
 #define RP_FMHA_CHUNK 16
 #endif
@@ -208,17 +211,30 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // 1-D grid: every (batch, head)'s query blocks but the last come first, the last ones — the only ones
-  // that can be partial, i.e. the short CTAs — at the end, where they fill the ragged end of the launch
+  // 1-D grid over (batch, head, query block), (batch, head) major.  A (batch, head)'s LAST query block is the only one that can
+  // be partial, i.e. a short CTA; the short CTAs of the last RP_FMHA_TAIL_DEFER (batch, head) pairs are moved to the end of the
+  // launch, where they fill its ragged end.  Only those: a deferred CTA re-reads its K / V, which is still in L2 for the
+  // pairs that ran last but long evicted for the early ones (all 256 deferred: +116 MB of DRAM reads per launch at
+  // B = 32, T = 1801 — profiles/r02_notes.md 9).
   const int nqb = (p.Tq + NQ * QT - 1) / (NQ * QT);
-  const int n_lead = (nqb - 1) * p.H * p.B;
+  const int n_bh = p.H * p.B;
+  const int n_def = nqb > 1 ? (n_bh < RP_FMHA_TAIL_DEFER ? n_bh : RP_FMHA_TAIL_DEFER) : 0;
+  const int n_first = (n_bh - n_def) * nqb;       // in order, tails included
+  const int n_second = n_def * (nqb - 1);         // the last pairs' full blocks
   int qb, bh;
-  if (int(blockIdx.x) < n_lead) {
-    qb = int(blockIdx.x) % (nqb - 1);
-    bh = int(blockIdx.x) / (nqb - 1);
-  } else {
-    qb = nqb - 1;
-    bh = int(blockIdx.x) - n_lead;
+  {
+    int x = int(blockIdx.x);
+    if (x < n_first) {
+      qb = x % nqb;
+      bh = x / nqb;
+    } else if (x - n_first < n_second) {
+      x -= n_first;
+      qb = x % (nqb - 1);
+      bh = (n_bh - n_def) + x / (nqb - 1);
+    } else {
+      qb = nqb - 1;
+      bh = (n_bh - n_def) + (x - n_first - n_second);
+    }
   }
   const int head = bh % p.H;
   const int b = p.batch_order != nullptr ? p.batch_order[bh / p.H] : bh / p.H;
