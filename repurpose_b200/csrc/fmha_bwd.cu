@@ -9,7 +9,9 @@
 // dSt = P o (keep o (dO V^T) / (1 - p) - Dsum); Dsum = rowsum(dO o O) holds unchanged with the dropped O.
 // P is recomputed from the log-sum-exp the forward wrote (FmhaArgs::lse); nothing of size T x T is stored.
 //
-// Two kernels, both deterministic (no atomics):
+// Default: fmha_bwd_fused_kernel (further down) computes dK, dV and dQ in ONE kernel, five contractions per tile pair, dQ summed
+// over the key tiles in L2 by TMA reduce adds.  Deterministic mode (rp_set_attn_bwd_deterministic / RP_FMHA_BWD_FUSED=0):
+// two kernels, no atomics:
 //   fmha_bwd_dq_kernel    one CTA per (batch, head, 128 queries), two CTAs per SM, walks the key tiles (64 keys):
 //                         S = Q K_j^T and dP = dO V_j^T (SS MMAs) -> softmax warps (thread <-> query row) -> dSt as bf16
 //                         A operand in TMEM -> dQ += dSt K_j (K_j as MN-major B operand, like V in the forward)
